@@ -79,7 +79,7 @@ def test_hybrid_features_match_reference_fp64(golden, name):
             # numpy restatement, reference form (integral image + 4 bilinear samples)
             vis = golden[f'{name}/visible{v}_{s}']
             got = onp.collapse_relu(onp.vox_features_integral(feat, boxes, vis), w, b).reshape(-1, L, W)
-            np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
             # numpy restatement, direct coverage-weighted form (what the CUDA kernels evaluate)
             got_d = onp.collapse_relu(onp.vox_features_direct(feat, boxes, vis), w, b).reshape(-1, L, W)
             np.testing.assert_allclose(got_d, want, rtol=1e-9, atol=1e-9)
@@ -88,7 +88,7 @@ def test_hybrid_features_match_reference_fp64(golden, name):
                                          torch.from_numpy(w).double(), torch.from_numpy(b).double(),
                                          geom.grid_height, geom.cube_size, name, geom.image_size,
                                          boxes=torch.from_numpy(boxes))[0].numpy()
-            np.testing.assert_allclose(got_p, want, rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(got_p, want, rtol=1e-9, atol=1e-9)
             checked += 1
     assert checked >= 9
 
