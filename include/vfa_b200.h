@@ -1,0 +1,125 @@
+/* vfa_b200.h -- C ABI of the B200-native voxelized-feature-aggregation library (libvfa_b200.so).
+ *
+ * The reference (Jiahao-Ma/VFA) has no FFI for this path: the boundary is a Python nn.Module,
+ * `VFA.forward(feature, calib, grid)` (reference vfa/model/vfa_op.py:61-125) called in the per-view / per-scale
+ * loop of `VFANet.forward` (reference vfa/model/vfanet.py:64-82).  These entry points are what a binding for
+ * that path binds (INTEGRATION.md shows the ctypes stub); each one cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; the library never allocates, frees,
+ *     synchronises the device or keeps global state other than the thread-local last-error string;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued on it;
+ *   - every function returns VFA_OK (0) or a negative vfa_status_t; vfa_last_error() describes the failure;
+ *   - tensors are dense, row-major in the index order written in the comment.
+ */
+#ifndef VFA_B200_H_
+#define VFA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFA_ABI_VERSION 1
+#define VFA_MAX_LAYERS 16
+#define VFA_MAX_SCALES 3
+
+typedef enum {
+  VFA_OK = 0,
+  VFA_ERR_INVALID_ARGUMENT = -1,   /* null pointer, non-positive size, unknown enum value             */
+  VFA_ERR_UNSUPPORTED = -2,        /* valid request outside what the kernels implement (see message)   */
+  VFA_ERR_WORKSPACE = -3,          /* workspace too small / misaligned                                 */
+  VFA_ERR_CUDA = -4,               /* a CUDA runtime call or kernel launch failed                      */
+  VFA_ERR_NO_DEVICE = -5           /* no sm_100 device: this library has no CPU or other-arch fallback */
+} vfa_status_t;
+
+/* grid -> world conversion of the reference's per-dataset `convert` (reference vfa/model/vfa_op.py:23-44).
+ * The operation kind matters for bit-exactness: MultiviewX divides by 40, it does not multiply by 0.025. */
+typedef enum {
+  VFA_CONVERT_DIV = 0,     /* world = p / scale                       MultiviewC (1.0), MultiviewX (40.0)       */
+  VFA_CONVERT_AFFINE = 1   /* world.xy = p.xy*scale - offset.xy ; world.z = p.z*scale      Wildtrack (2.5)   */
+} vfa_convert_t;
+
+/* Static description of the voxel grid and the camera normalisation (reference VFA.__init__,
+ * vfa_op.py:47-59, plus the `args` fields it reads, vfa_op.py:38-43, :75). */
+typedef struct {
+  int32_t n_layers;                  /* nl = len(arange(0, grid_height, cube_h))                     */
+  int32_t grid_l, grid_w;            /* BEV cells: grid tensor is [L, W, 3]                          */
+  int32_t convert_kind;              /* vfa_convert_t                                                */
+  float convert_scale;
+  float convert_offset[3];
+  float cube[3];                     /* voxel (l, w, h) in grid units -> the 8 corner offsets        */
+  float layer_z[VFA_MAX_LAYERS];     /* z_n = n * cube_h as fp32 (buffer `z_corners`)                */
+  float image_w, image_h;            /* args.image_size[::-1]                                        */
+  float clamp_lo, clamp_hi;          /* `crange`, default (-1, 0.95)                                 */
+} vfa_geometry_t;
+
+/* One frame batch of multi-view, multi-scale features, channels-last. */
+typedef struct {
+  int32_t batch;                     /* B frames                                                     */
+  int32_t n_views;                   /* V cameras                                                    */
+  int32_t channels;                  /* C (input channels == output channels, reference vfanet.py:30) */
+  int32_t n_scales;                  /* 1..VFA_MAX_SCALES                                            */
+  int32_t feat_h[VFA_MAX_SCALES];
+  int32_t feat_w[VFA_MAX_SCALES];
+} vfa_shape_t;
+
+/* flags of vfa_aggregate_fwd / _bwd */
+#define VFA_FLAG_FORCE_SIMT   1u     /* never take the tcgen05 path (generic fp32 FFMA kernel)         */
+#define VFA_FLAG_FORCE_UMMA   2u     /* fail with VFA_ERR_UNSUPPORTED instead of falling to SIMT       */
+#define VFA_FLAG_BF16_MMA     4u     /* single-pass bf16 tensor-core collapse (stated looser tolerance)*/
+
+int vfa_version(void);
+const char* vfa_last_error(void);
+
+/* Human-readable name of the kernel family the last vfa_aggregate_fwd on this thread dispatched to. */
+const char* vfa_last_path(void);
+
+/* Projection table: clamped normalised bounding box of every voxel's 8 projected corners, bit-identical to
+ * the reference's `box_corners` (reference vfa_op.py:64-88 + vfa/utils.py:50-59).
+ *   d_calibs [V,3,4] fp32, d_grid [L,W,3] fp32  ->  d_boxes [V, nl, L*W, 4] fp32 (left, top, right, bottom). */
+int vfa_table_build(const vfa_geometry_t* geom, int32_t n_views, const float* d_calibs, const float* d_grid,
+                    float* d_boxes, void* stream);
+
+/* Per-scale derived table for parity checking, produced by the same device function the aggregation kernels
+ * call: area (reference vfa_op.py:104-105), visible (:106) and the fp32 sampling tap indices
+ * floor(((c+1)*S-1)/2) of F.grid_sample (:112-115).  Any output pointer may be NULL.
+ *   d_boxes [n_boxes,4] -> d_area [n_boxes] fp32, d_visible [n_boxes] u8, d_taps [n_boxes,4] i32 (xl,yt,xr,yb) */
+int vfa_table_scale(const float* d_boxes, int64_t n_boxes, int32_t feat_h, int32_t feat_w, float* d_area,
+                    uint8_t* d_visible, int32_t* d_taps, void* stream);
+
+/* Layout helpers: [n, C, HW] <-> [n, HW, C] fp32 transposes (the reference hands NCHW feature maps,
+ * reference vfanet.py:72-78; the gather kernels read channels-last). */
+int vfa_nchw_to_nhwc(const float* d_src, float* d_dst, int64_t n, int32_t channels, int64_t hw, void* stream);
+int vfa_nhwc_to_nchw(const float* d_src, float* d_dst, int64_t n, int32_t channels, int64_t hw, void* stream);
+
+/* Bytes of scratch vfa_aggregate_fwd / _bwd need for this problem (prepared weights etc.). */
+size_t vfa_aggregate_workspace_bytes(const vfa_geometry_t* geom, const vfa_shape_t* shape, uint32_t flags);
+
+/* Fused aggregation forward = the whole loop of reference vfanet.py:64-82 minus the lateral convs:
+ *   out[b] = sum_v sum_s relu( collapse_s( pooled voxels of view v at scale s ) )       (vfa_op.py:104-124)
+ *   d_boxes   [V, nl, L*W, 4] fp32 from vfa_table_build
+ *   d_feats[s] [B, V, fH_s, fW_s, C] fp32 channels-last
+ *   d_weight[s] [C, C*nl] fp32 with the reference's column order c*nl + n, d_bias[s] [C]   (vfa_op.py:59, :120)
+ *   d_out     [B, C, L, W] fp32 (fully overwritten)
+ * With batch = n_views = n_scales = 1 this is exactly one reference `VFA.forward`. */
+int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,
+                      const float* const* d_feats, const float* const* d_weight, const float* const* d_bias,
+                      float* d_out, void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* Backward of vfa_aggregate_fwd (what autograd derives for reference vfa_op.py:110-124): given d_grad_out
+ * [B,C,L,W] accumulates into d_grad_feats[s] [B,V,fH,fW,C] (must be zero-initialised by the caller),
+ * d_grad_weight[s] [C, C*nl] and d_grad_bias[s] [C] (both fully overwritten).  Any gradient pointer array
+ * entry may be NULL to skip it.  Recomputes the pooled voxels instead of saving them. */
+int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,
+                      const float* const* d_feats, const float* const* d_weight, const float* const* d_bias,
+                      const float* d_grad_out, float* const* d_grad_feats, float* const* d_grad_weight,
+                      float* const* d_grad_bias, void* d_workspace, size_t workspace_bytes, uint32_t flags,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VFA_B200_H_ */

@@ -1,0 +1,219 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+
+Bit-exact: boxes, area, visible, tap indices.  Floating point: fused fp32 features within 1e-5 relative +
+1e-6 absolute of the float64 hybrid oracle (BASELINE.json north_star).
+"""
+import hashlib
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_port                      # noqa: E402
+from oracle import vfa_oracle as onp             # noqa: E402
+import vfa_b200                                   # noqa: E402
+from vfa_b200 import geometry, synthetic          # noqa: E402
+
+NAMES = ['MultiviewC', 'MultiviewX', 'Wildtrack']
+SMALL_SIZES = [(45, 80), (30, 52), (23, 40)]
+RTOL, ATOL = 1e-5, 1e-6       # north_star tolerance for fused fp32 features
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _geom(name, grid_lw, crange=(-1.0, 0.95)):
+    g = geometry.GEOMETRIES[name]
+    zs = list(range(0, g.grid_height, g.cube_size[2]))
+    return vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid_lw, name, g.image_size, crange)
+
+
+def _within(got, want, rtol=RTOL, atol=ATOL):
+    err = np.abs(got - want)
+    ok = err <= atol + rtol * np.abs(want)
+    return ok, err
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_table_bit_exact_small(golden, name):
+    grid, calibs = golden[f'{name}/grid'], golden[f'{name}/calibs']
+    L, W = grid.shape[:2]
+    table = vfa_b200.build_table(_geom(name, (L, W)), torch.from_numpy(calibs).cuda(), torch.from_numpy(grid).cuda())
+    boxes = table.boxes.cpu().numpy()
+    for v in range(calibs.shape[0]):
+        assert np.array_equal(_bits(boxes[v]), _bits(golden[f'{name}/boxes{v}'])), (name, v)
+    for s, (fh, fw) in enumerate(SMALL_SIZES):
+        area, vis, taps = table.scale_table(fh, fw)
+        for v in range(calibs.shape[0]):
+            assert np.array_equal(_bits(area[v].cpu().numpy()), _bits(golden[f'{name}/area{v}_{s}']))
+            assert np.array_equal(vis[v].cpu().numpy(), golden[f'{name}/visible{v}_{s}'])
+            b = golden[f'{name}/boxes{v}']
+            want = np.stack([onp.tap_index(b[..., 0], fw), onp.tap_index(b[..., 1], fh),
+                             onp.tap_index(b[..., 2], fw), onp.tap_index(b[..., 3], fh)], -1)
+            assert np.array_equal(taps[v].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_table_full_size_digests(digests, name):
+    """Config-of-record grids, ring + in-field camera: identical bits to the reference at full size."""
+    g = geometry.GEOMETRIES[name]
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g, in_field=True)
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    boxes = table.boxes.cpu().numpy()
+    for v in range(calibs.shape[0]):
+        assert _digest(_bits(boxes[v])) == digests[f'{name}/boxes{v}'], (name, v)
+    for s, (fh, fw) in enumerate(g.feature_sizes()):
+        _, vis, taps = table.scale_table(fh, fw)
+        vis, taps = vis.cpu().numpy(), taps.cpu().numpy()
+        for v in range(calibs.shape[0]):
+            assert _digest(vis[v].astype(np.uint8)) == digests[f'{name}/visible{v}_{s}']
+            assert _digest(taps[v]) == digests[f'{name}/taps{v}_{s}']
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_forward_matches_hybrid_oracle_golden(golden, name):
+    """One reference `VFA.forward` per (camera, scale) of the golden set, through the drop-in module."""
+    g = geometry.GEOMETRIES[name]
+    grid, calibs = golden[f'{name}/grid'], golden[f'{name}/calibs']
+    args = SimpleNamespace(data=name, image_size=g.image_size)
+    n_checked, n_bad, worst = 0, 0, 0.0
+    ref32_bad = 0
+    for s in range(3):
+        m = vfa_b200.VFA(6, g.grid_height, g.cube_size, 1.0, args).cuda()
+        with torch.no_grad():
+            m.collapse.weight.copy_(torch.from_numpy(golden[f'{name}/weight{s}']))
+            m.collapse.bias.copy_(torch.from_numpy(golden[f'{name}/bias{s}']))
+        feat = torch.from_numpy(golden[f'{name}/feat{s}'])[None].cuda()
+        for v in range(calibs.shape[0]):
+            key = f'{name}/out64_{v}_{s}'
+            if key not in golden:
+                continue
+            with torch.no_grad():
+                out = m(feat, torch.from_numpy(calibs[v]).cuda(), torch.from_numpy(grid)[None].cuda())
+            assert out.shape == (1, 6) + grid.shape[:2]
+            want = golden[key]
+            ok, err = _within(out[0].cpu().numpy().astype(np.float64), want)
+            n_checked += ok.size
+            n_bad += int((~ok).sum())
+            worst = max(worst, float(err.max()))
+            ok32, _ = _within(golden[f'{name}/out32_{v}_{s}'].astype(np.float64), want)
+            ref32_bad += int((~ok32).sum())
+    print(f'{name}: {n_bad}/{n_checked} outside 1e-5/1e-6 (worst abs {worst:.2e}); the reference fp32 itself: {ref32_bad}')
+    assert n_bad == 0, f'{n_bad}/{n_checked} elements outside tolerance, worst abs err {worst:.3e}'
+
+
+def _port_frame(name, feats, calibs, grid, params, dtype=torch.float64):
+    g = geometry.GEOMETRIES[name]
+    f = [t.to(dtype) for t in feats]
+    p = [(w.to(dtype), b.to(dtype)) for w, b in params]
+    return ref_port.aggregate(f, calibs, grid, p, g.grid_height, g.cube_size, name, g.image_size, cache_boxes=True)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_fused_aggregate_matches_port(name):
+    """Fused multi-view / multi-scale / batched entry vs the float64 port of the reference loop, full-size grid,
+    real feature-map sizes, reduced channel count so the oracle finishes in seconds."""
+    g = geometry.GEOMETRIES[name]
+    Cc, V, B = 16, 3, 2
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g, n_views=V - 1, in_field=True)
+    feats = synthetic.features(g, batch=B, n_views=V, channels=Cc, seed=3)
+    params = synthetic.collapse_params(g, channels=Cc, seed=3)
+    want = _port_frame(name, feats, calibs, grid, params).numpy()
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    out = vfa_b200.aggregate([f.cuda() for f in feats], table, [w.cuda() for w, _ in params],
+                             [b.cuda() for _, b in params])
+    assert out.shape == want.shape
+    ok, err = _within(out.cpu().numpy().astype(np.float64), want)
+    frac = 1.0 - ok.mean()
+    print(f'{name}: outside tol {frac:.2e}, worst abs {err.max():.2e}, path {vfa_b200.last_kernel_path()}')
+    assert frac == 0.0, f'{frac:.3e} of elements outside tolerance (worst {err.max():.3e})'
+    # channels-last input is consumed zero-copy and gives identical bits
+    cl = [f.cuda().permute(0, 1, 3, 4, 2).contiguous() for f in feats]
+    out2 = vfa_b200.aggregate(cl, table, [w.cuda() for w, _ in params], [b.cuda() for _, b in params], channels_last=True)
+    assert torch.equal(out, out2)
+
+
+def test_full_width_single_call_matches_port():
+    """C = 256 (the real channel count), MultiviewC full grid, one (view, scale) -- vs the float64 port."""
+    name = 'MultiviewC'
+    g = geometry.GEOMETRIES[name]
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g, n_views=1)
+    feats = synthetic.features(g, batch=1, n_views=1, seed=5, sizes=[g.feature_sizes()[1]])
+    params = synthetic.collapse_params(g, seed=5)[:1]
+    want = ref_port.vfa_forward(feats[0][0, 0].double(), calibs[0], grid, params[0][0].double(), params[0][1].double(),
+                                g.grid_height, g.cube_size, name, g.image_size).numpy()
+    args = SimpleNamespace(data=name, image_size=g.image_size)
+    m = vfa_b200.VFA(256, g.grid_height, g.cube_size, 1 / 16., args).cuda()
+    with torch.no_grad():
+        m.collapse.weight.copy_(params[0][0])
+        m.collapse.bias.copy_(params[0][1])
+        out = m(feats[0][0].cuda(), calibs[0].cuda(), grid[None].cuda())
+    ok, err = _within(out.cpu().numpy().astype(np.float64), want)
+    frac = 1.0 - ok.mean()
+    print(f'C=256 single call: outside tol {frac:.2e}, worst abs {err.max():.2e}, path {vfa_b200.last_kernel_path()}')
+    assert frac <= 1e-5, f'{frac:.3e} of elements outside tolerance (worst {err.max():.3e})'
+    assert err.max() < 2e-5
+
+
+def test_full_size_properties():
+    """BASELINE-size problem (MultiviewC, 7 views, 3 scales, C=256): properties that need no oracle."""
+    g = geometry.MULTIVIEWC
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g)
+    feats = [f.cuda() for f in synthetic.features(g, batch=2, seed=1)]
+    params = synthetic.collapse_params(g, seed=1)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    out = vfa_b200.aggregate(feats, table, ws, bs)
+    assert out.shape == (2, 256, 156, 156) and bool(torch.isfinite(out).all()) and float(out.min()) >= 0.0
+    # frames are independent: batch == per-frame calls (same kernel, same order -> same bits)
+    one = vfa_b200.aggregate([f[1:2] for f in feats], table, ws, bs)
+    assert torch.equal(one[0], out[1])
+    # summing over views is order-free up to fp32 rounding: permuting cameras permutes nothing else
+    perm = [3, 0, 6, 2, 5, 1, 4]
+    tperm = vfa_b200.ProjectionTable(table.geom, table.boxes[perm].contiguous())
+    outp = vfa_b200.aggregate([f[:1, perm] for f in feats], tperm, ws, bs)
+    torch.testing.assert_close(outp[0], out[0], rtol=1e-5, atol=1e-5)
+    # positive homogeneity with zero bias: relu(W (a x)) = a relu(W x)
+    zb = [torch.zeros_like(b) for b in bs]
+    o1 = vfa_b200.aggregate([f[:1] for f in feats], table, ws, zb)
+    o2 = vfa_b200.aggregate([f[:1] * 4.0 for f in feats], table, ws, zb)
+    torch.testing.assert_close(o2, o1 * 4.0, rtol=1e-5, atol=1e-5)
+    # a camera that sees nothing contributes relu(bias) per scale: all-zero features -> sum_v sum_s relu(b_s)
+    zf = [torch.zeros_like(f[:1]) for f in feats]
+    oz = vfa_b200.aggregate(zf, table, ws, bs)
+    want = sum(torch.relu(b) for b in bs) * calibs.shape[0]
+    torch.testing.assert_close(oz[0], want[:, None, None].expand_as(oz[0]), rtol=1e-6, atol=1e-6)
+
+
+def test_module_state_dict_and_errors():
+    g = geometry.MULTIVIEWC
+    args = SimpleNamespace(data=g.name, image_size=g.image_size)
+    m = vfa_b200.VFA(256, g.grid_height, np.array(g.cube_size), 1 / 8., args)
+    sd = m.state_dict()
+    assert {k: (tuple(v.shape), v.dtype) for k, v in sd.items()} == {
+        'z_corners': ((5, 1, 1, 3), torch.int64), 'corners_offset': ((1, 1, 1, 1, 8, 3), torch.float32),
+        'collapse.weight': ((256, 1280), torch.float32), 'collapse.bias': ((256,), torch.float32)}
+    grid = geometry.grid_for(g)[None]
+    feat = torch.zeros(1, 256, 90, 160)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m(feat, torch.zeros(3, 4), grid)
+    m = m.cuda()
+    calib = synthetic.ring_calibs(g, n_views=1)[0].cuda()
+    with pytest.raises(NotImplementedError):
+        m(feat.cuda(), calib, grid.cuda(), visualize=True)
+    with pytest.raises(vfa_b200.VFAError, match='crange'):
+        m(feat.cuda(), calib, grid.cuda(), crange=(-1, 1.0))
+    out = m(feat.cuda(), calib, grid.cuda())
+    assert out.shape == (1, 256, 156, 156)

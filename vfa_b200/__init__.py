@@ -1,0 +1,14 @@
+"""vfa_b200 -- B200-native voxelized 3D feature aggregation (the hot path of Jiahao-Ma/VFA).
+
+    from vfa_b200 import VFA, aggregate, build_table
+
+`VFA` is a drop-in for the reference module `vfa.model.vfa_op.VFA`; `aggregate` is the fused batched multi-view
+entry.  All arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of include/vfa_b200.h
+(libvfa_b200.so, loaded with ctypes); there is no CPU, Triton or PyTorch-op fallback.
+"""
+from . import geometry, synthetic                                    # noqa: F401
+from ._lib import VFAError, FLAG_BF16_MMA, FLAG_FORCE_SIMT, FLAG_FORCE_UMMA   # noqa: F401
+from .vfa_op import (VFA, ProjectionTable, aggregate, build_table, last_kernel_path, make_geometry,  # noqa: F401
+                     to_channels_last)
+
+__version__ = '0.1.0'

@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference aggregation module, backed by libvfa_b200.so.
+
+`VFA` keeps the constructor, forward signature, buffers and parameter names of the reference module (reference
+vfa/model/vfa_op.py:46-125) so `vfa.model.vfanet.VFANet` (reference vfa/model/vfanet.py:30-32, :76-78) and released
+checkpoints work unchanged.  `aggregate` is the fused multi-view / multi-scale entry that replaces the loop of
+reference vfa/model/vfanet.py:64-82 (minus the lateral convs) with one kernel launch per frame batch.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); all arithmetic runs in hand-written sm_100a
+kernels behind the C ABI.  Nothing in this file computes on the CPU or falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .geometry import convert_descriptor
+
+__all__ = ['VFA', 'ProjectionTable', 'build_table', 'aggregate', 'to_channels_last', 'last_kernel_path']
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor: vfa_b200 has no CPU path (got device {t.device})')
+
+
+def make_geometry(n_layers, cube_size, layer_z, grid_lw, dataset, image_size, crange=(-1.0, 0.95)) -> _lib.Geometry:
+    kind, scale, offset = convert_descriptor(dataset)
+    g = _lib.Geometry()
+    g.n_layers = int(n_layers)
+    g.grid_l, g.grid_w = int(grid_lw[0]), int(grid_lw[1])
+    g.convert_kind = kind
+    g.convert_scale = float(scale)
+    for a in range(3):
+        g.convert_offset[a] = float(offset[a])
+        g.cube[a] = float(cube_size[a])
+    if n_layers > _lib.VFA_MAX_LAYERS:
+        raise ValueError(f'{n_layers} height layers > supported maximum {_lib.VFA_MAX_LAYERS}')
+    for n in range(int(n_layers)):
+        g.layer_z[n] = float(layer_z[n])
+    g.image_h, g.image_w = float(image_size[0]), float(image_size[1])
+    g.clamp_lo, g.clamp_hi = float(crange[0]), float(crange[1])
+    return g
+
+
+class ProjectionTable:
+    """Boxes [V, nl, L*W, 4] fp32 for a set of cameras (bit-identical to the reference's `box_corners`)."""
+
+    def __init__(self, geom: _lib.Geometry, boxes: torch.Tensor):
+        self.geom = geom
+        self.boxes = boxes
+
+    @property
+    def n_views(self):
+        return self.boxes.shape[0]
+
+    def scale_table(self, feat_h: int, feat_w: int):
+        """(area fp32, visible bool, taps int32[...,4]) of one feature scale -- the parity-checked quantities."""
+        n = self.boxes.numel() // 4
+        area = torch.empty(self.boxes.shape[:-1], dtype=torch.float32, device=self.boxes.device)
+        vis = torch.empty(self.boxes.shape[:-1], dtype=torch.uint8, device=self.boxes.device)
+        taps = torch.empty(self.boxes.shape, dtype=torch.int32, device=self.boxes.device)
+        with torch.cuda.device(self.boxes.device):
+            _lib.check(_lib.lib().vfa_table_scale(self.boxes.data_ptr(), n, int(feat_h), int(feat_w), area.data_ptr(),
+                                                  vis.data_ptr(), taps.data_ptr(), _stream()))
+        return area, vis.bool(), taps
+
+
+def build_table(geom: _lib.Geometry, calibs: torch.Tensor, grid: torch.Tensor) -> ProjectionTable:
+    """calibs [V,3,4] (or [3,4]) fp32 CUDA, grid [L,W,3] / [1,L,W,3] fp32 CUDA."""
+    _require_cuda(calibs, 'calibs')
+    _require_cuda(grid, 'grid')
+    calibs = calibs.detach().reshape(-1, 3, 4).to(torch.float32).contiguous()
+    grid = grid.detach().reshape(-1, 3).to(torch.float32).contiguous()
+    if grid.shape[0] != geom.grid_l * geom.grid_w:
+        raise ValueError(f'grid has {grid.shape[0]} cells, geometry says {geom.grid_l}x{geom.grid_w}')
+    V = calibs.shape[0]
+    boxes = torch.empty(V, geom.n_layers, geom.grid_l * geom.grid_w, 4, dtype=torch.float32, device=calibs.device)
+    with torch.cuda.device(calibs.device):
+        _lib.check(_lib.lib().vfa_table_build(C.byref(geom), V, calibs.data_ptr(), grid.data_ptr(), boxes.data_ptr(),
+                                              _stream()))
+    return ProjectionTable(geom, boxes)
+
+
+class _ChannelsLast(torch.autograd.Function):
+    """[N, C, H, W] contiguous -> [N, H, W, C] contiguous with the library's tiled transpose (and back for grads)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, Cc, H, W = x.shape
+        out = torch.empty(N, H, W, Cc, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().vfa_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), N, Cc, H * W, _stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        N, H, W, Cc = g.shape
+        out = torch.empty(N, Cc, H, W, dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().vfa_nhwc_to_nchw(g.data_ptr(), out.data_ptr(), N, Cc, H * W, _stream()))
+        return out
+
+
+def to_channels_last(x: torch.Tensor) -> torch.Tensor:
+    """[..., C, H, W] fp32 CUDA -> contiguous [..., H, W, C].  Zero-copy when the tensor already has
+    channels-last strides (e.g. produced by a cuDNN conv in torch.channels_last memory format)."""
+    _require_cuda(x, 'feature')
+    if x.dtype != torch.float32:
+        raise TypeError(f'features must be float32, got {x.dtype}')
+    lead = x.shape[:-3]
+    Cc, H, W = x.shape[-3:]
+    perm = x.movedim(-3, -1)
+    if perm.is_contiguous():
+        return perm
+    x4 = x.reshape(-1, Cc, H, W).contiguous()
+    return _ChannelsLast.apply(x4).reshape(*lead, H, W, Cc)
+
+
+class _AggregateFn(torch.autograd.Function):
+    """out [B,C,L,W] = sum_v sum_s relu(collapse_s(pooled voxels)); tensors = feats(S) + weights(S) + biases(S)."""
+
+    @staticmethod
+    def forward(ctx, geom, boxes, flags, n_scales, *tensors):
+        S = n_scales
+        feats = [t.contiguous() for t in tensors[:S]]
+        weights = [t.contiguous() for t in tensors[S:2 * S]]
+        biases = [t.contiguous() for t in tensors[2 * S:3 * S]]
+        B, V, _, _, Cc = feats[0].shape
+        shape = _lib.Shape()
+        shape.batch, shape.n_views, shape.channels, shape.n_scales = B, V, Cc, S
+        for s in range(S):
+            if feats[s].shape[0] != B or feats[s].shape[1] != V or feats[s].shape[4] != Cc:
+                raise ValueError('feature tensors disagree on batch / views / channels')
+            shape.feat_h[s], shape.feat_w[s] = feats[s].shape[2], feats[s].shape[3]
+            if tuple(weights[s].shape) != (Cc, Cc * geom.n_layers) or tuple(biases[s].shape) != (Cc,):
+                raise ValueError(f'collapse parameters of scale {s} have shapes {tuple(weights[s].shape)}, '
+                                 f'{tuple(biases[s].shape)}; expected ({Cc}, {Cc * geom.n_layers}) and ({Cc},)')
+        if boxes.shape[0] != V:
+            raise ValueError(f'table holds {boxes.shape[0]} views, features hold {V}')
+        dev = feats[0].device
+        L = _lib.lib()
+        out = torch.empty(B, Cc, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
+        ws_bytes = L.vfa_aggregate_workspace_bytes(C.byref(geom), C.byref(shape), flags)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.vfa_aggregate_fwd(C.byref(geom), C.byref(shape), boxes.data_ptr(),
+                                           _lib.ptr_array([t.data_ptr() for t in feats]),
+                                           _lib.ptr_array([t.data_ptr() for t in weights]),
+                                           _lib.ptr_array([t.data_ptr() for t in biases]),
+                                           out.data_ptr(), ws.data_ptr(), ws.numel(), flags, _stream()))
+        ctx.geom, ctx.shape, ctx.flags, ctx.S = geom, shape, flags, S
+        ctx.save_for_backward(boxes, *feats, *weights, *biases)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        S = ctx.S
+        saved = ctx.saved_tensors
+        boxes, feats, weights, biases = saved[0], saved[1:1 + S], saved[1 + S:1 + 2 * S], saved[1 + 2 * S:1 + 3 * S]
+        grad_out = grad_out.contiguous()
+        dev = grad_out.device
+        L = _lib.lib()
+        need_f = [ctx.needs_input_grad[4 + s] for s in range(S)]
+        need_w = [ctx.needs_input_grad[4 + S + s] for s in range(S)]
+        need_b = [ctx.needs_input_grad[4 + 2 * S + s] for s in range(S)]
+        gf = [torch.zeros_like(feats[s]) if need_f[s] else None for s in range(S)]
+        gw = [torch.empty_like(weights[s]) if (need_w[s] or need_b[s]) else None for s in range(S)]
+        gb = [torch.empty_like(biases[s]) if (need_w[s] or need_b[s]) else None for s in range(S)]
+        ws_bytes = L.vfa_aggregate_workspace_bytes(C.byref(ctx.geom), C.byref(ctx.shape), ctx.flags)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.vfa_aggregate_bwd(C.byref(ctx.geom), C.byref(ctx.shape), boxes.data_ptr(),
+                                           _lib.ptr_array([t.data_ptr() for t in feats]),
+                                           _lib.ptr_array([t.data_ptr() for t in weights]),
+                                           _lib.ptr_array([t.data_ptr() for t in biases]),
+                                           grad_out.data_ptr(),
+                                           _lib.ptr_array([t.data_ptr() if t is not None else None for t in gf]),
+                                           _lib.ptr_array([t.data_ptr() if t is not None else None for t in gw]),
+                                           _lib.ptr_array([t.data_ptr() if t is not None else None for t in gb]),
+                                           ws.data_ptr(), ws.numel(), ctx.flags, _stream()))
+        grads = [g if n else None for g, n in zip(gf, need_f)]
+        grads += [g if n else None for g, n in zip(gw, need_w)]
+        grads += [g if n else None for g, n in zip(gb, need_b)]
+        return (None, None, None, None, *grads)
+
+
+def aggregate(feats, table: ProjectionTable, weights, biases, flags: int = 0, channels_last: bool | None = None):
+    """Fused aggregation of a frame batch.
+
+    feats    list of S tensors [B,V,C,fH,fW] fp32 CUDA (any strides; channels-last strides are consumed zero-copy),
+             or [B,V,fH,fW,C] when channels_last=True
+    table    ProjectionTable for the V cameras (build_table)
+    weights  list of S tensors [C, C*nl] (`collapse.weight`, column order c*nl+n), biases list of S tensors [C]
+    returns  [B,C,L,W] fp32 = sum over views and scales of relu(collapse(pooled voxels)), autograd-connected.
+    """
+    S = len(feats)
+    if not (1 <= S <= _lib.VFA_MAX_SCALES) or len(weights) != S or len(biases) != S:
+        raise ValueError('need 1..3 feature scales with one (weight, bias) pair each')
+    cl = []
+    for f in feats:
+        if f.dim() != 5:
+            raise ValueError(f'features must be 5-D [B,V,C,H,W], got {tuple(f.shape)}')
+        cl.append(f if channels_last else to_channels_last(f))
+    for t in list(weights) + list(biases):
+        _require_cuda(t, 'collapse parameter')
+    return _AggregateFn.apply(table.geom, table.boxes, int(flags), S, *cl, *weights, *biases)
+
+
+def last_kernel_path() -> str:
+    """Kernel family the most recent aggregate() on this thread dispatched to ('simt_fp32', 'umma_tf32x3', ...)."""
+    return _lib.last_path()
+
+
+class VFA(nn.Module):
+    """Drop-in for the reference `VFA` module (reference vfa/model/vfa_op.py:46-125).
+
+    Same constructor arguments, same buffers (`z_corners` int64 [nl,1,1,3], `corners_offset` fp32 [1,1,1,1,8,3]) and
+    parameters (`collapse.weight` [C, C*nl], `collapse.bias` [C]); `args` is any object with `.data` in
+    {'MultiviewC','MultiviewX','Wildtrack'} and `.image_size = (H, W)`.
+    """
+
+    def __init__(self, channel, grid_height=160, cube_size=(25, 25, 32), feat_scale=1, args=None):
+        super().__init__()
+        cube_size = [float(v) for v in np.asarray(cube_size).tolist()]
+        self.cube_size = tuple(cube_size)
+        self.cube_height = cube_size[2]
+        z_corners = torch.arange(0, grid_height, int(cube_size[2]) if float(cube_size[2]).is_integer() else cube_size[2])
+        z_corners = F.pad(z_corners.view(-1, 1, 1, 1), [2, 0])
+        l, w, h = cube_size
+        offs = torch.tensor([[-l / 2, -w / 2, 0], [l / 2, -w / 2, 0], [l / 2, w / 2, 0], [-l / 2, w / 2, 0],
+                             [-l / 2, -w / 2, h], [l / 2, -w / 2, h], [l / 2, w / 2, h], [-l / 2, w / 2, h]],
+                            dtype=torch.float32).view(1, 1, 1, 1, 8, 3)
+        self.register_buffer('z_corners', z_corners)
+        self.register_buffer('corners_offset', offs)
+        self.feat_scale = feat_scale          # accepted and unused, like the reference (vfa_op.py:57, :74)
+        self.args = args
+        self.channel = channel
+        self.num_grid_layer = z_corners.shape[0]
+        self.collapse = nn.Linear(channel * self.num_grid_layer, channel)
+        self.flags = 0
+
+    def geometry(self, grid_lw, crange=(-1.0, 0.95)) -> _lib.Geometry:
+        if self.args is None:
+            raise ValueError('VFA needs `args` with .data and .image_size (reference vfa_op.py:38-43, :75)')
+        layer_z = self.z_corners[:, 0, 0, 2].tolist()
+        return make_geometry(self.num_grid_layer, self.cube_size, layer_z, grid_lw, self.args.data, self.args.image_size,
+                             crange)
+
+    def forward(self, feature, calib, grid, crange=(-1, 0.95), visualize=False):
+        """feature [1,C,fH,fW], calib [3,4], grid [1,L,W,3] -> [1,C,L,W]   (reference vfa_op.py:61-125)."""
+        if visualize:
+            raise NotImplementedError('visualize=True is a matplotlib debugging aid of the reference and is not provided')
+        if feature.dim() != 4 or feature.shape[0] != 1:
+            raise ValueError(f'feature must be [1,C,fH,fW] (the reference is batch-1, vfa_op.py:64), got {tuple(feature.shape)}')
+        L, W = grid.shape[-3], grid.shape[-2]
+        geom = self.geometry((L, W), crange)
+        table = build_table(geom, calib, grid)
+        return aggregate([feature.unsqueeze(0)], table, [self.collapse.weight], [self.collapse.bias], self.flags)
