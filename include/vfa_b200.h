@@ -70,6 +70,7 @@ typedef struct {
 #define VFA_FLAG_FORCE_SIMT   1u     /* never take the tcgen05 path (generic fp32 FFMA kernel)         */
 #define VFA_FLAG_FORCE_UMMA   2u     /* fail with VFA_ERR_UNSUPPORTED instead of falling to SIMT       */
 #define VFA_FLAG_BF16_MMA     4u     /* single-pass bf16 tensor-core collapse (stated looser tolerance)*/
+#define VFA_FLAG_WEIGHTS_PREPARED 8u /* workspace already holds vfa_prepare_weights output for these flags */
 
 int vfa_version(void);
 const char* vfa_last_error(void);
@@ -97,6 +98,12 @@ int vfa_nhwc_to_nchw(const float* d_src, float* d_dst, int64_t n, int32_t channe
 
 /* Bytes of scratch vfa_aggregate_fwd / _bwd need for this problem (prepared weights etc.). */
 size_t vfa_aggregate_workspace_bytes(const vfa_geometry_t* geom, const vfa_shape_t* shape, uint32_t flags);
+
+/* Re-lays the collapse weights for the kernel family `flags` selects (column permutation c*nl+n -> n*C+c,
+ * operand splitting / swizzling for the tensor-core path) into the workspace.  vfa_aggregate_fwd does this
+ * itself unless VFA_FLAG_WEIGHTS_PREPARED is set; inference callers with frozen weights call it once. */
+int vfa_prepare_weights(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* const* d_weight,
+                        void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* Fused aggregation forward = the whole loop of reference vfanet.py:64-82 minus the lateral convs:
  *   out[b] = sum_v sum_s relu( collapse_s( pooled voxels of view v at scale s ) )       (vfa_op.py:104-124)

@@ -1,5 +1,6 @@
 """Scratch timing of the fused forward (not the bench): python scripts/quick_time.py [workload] [B] [flags]"""
-import sys, time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vfa_b200
 from vfa_b200 import geometry, synthetic

@@ -14,11 +14,12 @@ VFA_MAX_SCALES = 3
 FLAG_FORCE_SIMT = 1
 FLAG_FORCE_UMMA = 2
 FLAG_BF16_MMA = 4
+FLAG_WEIGHTS_PREPARED = 8
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libvfa_b200.so')
 
 EXPORTS = ['vfa_version', 'vfa_last_error', 'vfa_last_path', 'vfa_table_build', 'vfa_table_scale',
-           'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_workspace_bytes', 'vfa_aggregate_fwd',
+           'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_workspace_bytes', 'vfa_prepare_weights', 'vfa_aggregate_fwd',
            'vfa_aggregate_bwd']
 
 
@@ -63,10 +64,11 @@ def lib():
     L.vfa_aggregate_workspace_bytes.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), u32]
     L.vfa_aggregate_workspace_bytes.restype = sz
     PP = C.POINTER(C.c_void_p)
+    L.vfa_prepare_weights.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), PP, vp, sz, u32, vp]
     L.vfa_aggregate_fwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, PP, fp, vp, sz, u32, vp]
     L.vfa_aggregate_bwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, PP, fp, PP, PP, PP, vp, sz,
                                     u32, vp]
-    for name in ('vfa_table_build', 'vfa_table_scale', 'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_fwd',
+    for name in ('vfa_prepare_weights', 'vfa_table_build', 'vfa_table_scale', 'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_fwd',
                  'vfa_aggregate_bwd'):
         getattr(L, name).restype = C.c_int
     if L.vfa_version() != 1:

@@ -42,7 +42,9 @@ int launch_table_build(const vfa_geometry_t*, int, const float*, const float*, f
 int launch_table_scale(const float*, long long, int, int, float*, uint8_t*, int32_t*, cudaStream_t);
 int launch_transpose(const float*, float*, long long, int, long long, cudaStream_t);
 size_t simt_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*);
-int launch_fwd_simt(AggParams, const float* const*, void*, cudaStream_t);
+int prep_weights_simt(const AggParams&, const float* const*, void*, cudaStream_t);
+int launch_fwd_simt(AggParams, const float* const*, void*, uint32_t, cudaStream_t);
+int prep_weights_umma(const AggParams&, const float* const*, void*, cudaStream_t);
 size_t umma_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
 bool umma_supported(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
 int launch_fwd_umma(AggParams, const float* const*, void*, uint32_t, cudaStream_t);
@@ -199,7 +201,28 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
   }
   VFA_REQUIRE(workspace_bytes >= simt_workspace_bytes(geom, shape), VFA_ERR_WORKSPACE, "workspace %zu < required %zu",
               workspace_bytes, simt_workspace_bytes(geom, shape));
-  return launch_fwd_simt(p, d_weight, d_workspace, (cudaStream_t)stream);
+  return launch_fwd_simt(p, d_weight, d_workspace, flags, (cudaStream_t)stream);
+}
+
+int vfa_prepare_weights(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* const* d_weight,
+                        void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (int rc = validate_geometry(geom)) return rc;
+  if (int rc = validate_shape(geom, shape)) return rc;
+  VFA_REQUIRE(d_weight != nullptr, VFA_ERR_INVALID_ARGUMENT, "NULL weight array");
+  for (int s = 0; s < shape->n_scales; ++s)
+    VFA_REQUIRE(d_weight[s] != nullptr, VFA_ERR_INVALID_ARGUMENT, "scale %d: NULL weight", s);
+  VFA_REQUIRE(d_workspace != nullptr && (reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, VFA_ERR_WORKSPACE,
+              "workspace must be a 256-byte aligned device pointer");
+  if (int rc = check_device()) return rc;
+  AggParams p;
+  p.C = shape->channels;
+  p.nl = geom->n_layers;
+  p.S = shape->n_scales;
+  const bool use_umma = !(flags & VFA_FLAG_FORCE_SIMT) && umma_supported(geom, shape, flags);
+  const size_t need = use_umma ? umma_workspace_bytes(geom, shape, flags) : simt_workspace_bytes(geom, shape);
+  VFA_REQUIRE(workspace_bytes >= need, VFA_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  return use_umma ? prep_weights_umma(p, d_weight, d_workspace, (cudaStream_t)stream)
+                  : prep_weights_simt(p, d_weight, d_workspace, (cudaStream_t)stream);
 }
 
 int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,

@@ -147,7 +147,7 @@ size_t simt_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh) {
   return (size_t)sh->n_scales * sh->channels * sh->channels * g->n_layers * sizeof(float);
 }
 
-int launch_fwd_simt(AggParams p, const float* const* d_weight, void* ws, cudaStream_t st) {
+int prep_weights_simt(const AggParams& p, const float* const* d_weight, void* ws, cudaStream_t st) {
   float* wp = reinterpret_cast<float*>(ws);
   const size_t per_scale = (size_t)p.C * p.C * p.nl;
   for (int s = 0; s < p.S; ++s) {
@@ -155,8 +155,16 @@ int launch_fwd_simt(AggParams p, const float* const* d_weight, void* ws, cudaStr
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     prep_weight_simt_kernel<<<blocks, 256, 0, st>>>(d_weight[s], wp + s * per_scale, p.C, p.nl);
     VFA_LAUNCH_CHECK("prep_weight_simt_kernel");
-    p.wprep[s] = wp + s * per_scale;
   }
+  return VFA_OK;
+}
+
+int launch_fwd_simt(AggParams p, const float* const* d_weight, void* ws, uint32_t flags, cudaStream_t st) {
+  if (!(flags & VFA_FLAG_WEIGHTS_PREPARED)) {
+    if (int rc = prep_weights_simt(p, d_weight, ws, st)) return rc;
+  }
+  const size_t per_scale = (size_t)p.C * p.C * p.nl;
+  for (int s = 0; s < p.S; ++s) p.wprep[s] = reinterpret_cast<const float*>(ws) + s * per_scale;
   dim3 grid((p.LW + TM - 1) / TM, p.B);
   aggregate_fwd_simt_kernel<<<grid, THREADS, 0, st>>>(p);
   VFA_LAUNCH_CHECK("aggregate_fwd_simt_kernel");
