@@ -19,6 +19,8 @@
 // acc_empty (epilogue).  The [L*W, C*nl] matrix of the reference (vfa_op.py:118-120) only ever exists as
 // 16 KB operand tiles; the collapse (vfa_op.py:123) is the tensor-core contraction; ReLU and the sums over
 // scales and views (vfa_op.py:124, vfanet.py:79-82) are the epilogue.
+#include <stdlib.h>
+
 #include "vfa_common.cuh"
 
 namespace vfa {
@@ -33,13 +35,14 @@ constexpr int A_BYTES = TILE_M * KCH * 4;          // 16 KB per hi / lo tile
 constexpr int B_BYTES = CH * KCH * 4;              // 32 KB per hi / lo slab
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
 constexpr int NUM_PRODUCER_WARPS = 8;
-constexpr int FIRST_PRODUCER_WARP = 2;
-constexpr int FIRST_EPILOGUE_WARP = 10;
-constexpr int THREADS = 14 * 32;
+constexpr int FIRST_PRODUCER_WARP = 4;     // warpgroup 0 = {loader, MMA, 2 idle warps} gives its registers away
+constexpr int FIRST_EPILOGUE_WARP = 12;
+constexpr int NUM_EPILOGUE_WARPS = 8;
+constexpr int THREADS = 20 * 32;
 constexpr int TMEM_COLS = 512;
 
 struct __align__(8) SmemTail {
-  BoxTaps taps[2][TILE_M];
+  BoxTaps taps[NUM_PRODUCER_WARPS][16];
   float bias[VFA_MAX_SCALES][CH];
   unsigned long long full[STAGES];
   unsigned long long empty[STAGES];
@@ -176,7 +179,113 @@ struct UmmaArgs {
   const uint8_t* wprep[VFA_MAX_SCALES];
   int n_groups;        // view groups (grid.x = tiles * n_groups); > 1 -> atomic accumulation into a zeroed output
   int views_per_group;
+  int variant;         // debug: 0 = 3xTF32, 1 = hi*hi only (single-pass tf32)
 };
+
+// One producer work item = 4 cells (one per quarter-warp) x 32 channels of one K chunk.  The loads of an item are
+// issued into registers DEPTH items ahead of their use, so a warp keeps DEPTH * T * T 128-bit loads in flight.
+template <int T>
+struct GatherBuf {
+  float4 v[T][T];
+};
+
+template <int T>
+__device__ __forceinline__ void issue_item(GatherBuf<T>& buf, const BoxTaps& t, const float* __restrict__ feat, int fw,
+                                           int coff) {
+  const float* base = feat + ((size_t)t.y0 * fw + t.x0) * CH + coff;
+#pragma unroll
+  for (int ty = 0; ty < T; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < T; ++tx) {
+      const bool on = (ty < t.ny) && (tx < t.nx);
+      buf.v[ty][tx] = on ? __ldg(reinterpret_cast<const float4*>(base + ((size_t)ty * fw + tx) * CH))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int T>
+__device__ __forceinline__ float4 reduce_item(const GatherBuf<T>& buf, const BoxTaps& t, const float* __restrict__ feat,
+                                              int fw, int coff) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t.nx <= T && t.ny <= T) {
+#pragma unroll
+    for (int ty = 0; ty < T; ++ty) {
+      const float wy = (ty < t.ny) ? tap_wy(t, ty) : 0.f;
+#pragma unroll
+      for (int tx = 0; tx < T; ++tx) {
+        const float w = (tx < t.nx) ? wy * tap_wx(t, tx) : 0.f;
+        acc.x = fmaf(w, buf.v[ty][tx].x, acc.x);
+        acc.y = fmaf(w, buf.v[ty][tx].y, acc.y);
+        acc.z = fmaf(w, buf.v[ty][tx].z, acc.z);
+        acc.w = fmaf(w, buf.v[ty][tx].w, acc.w);
+      }
+    }
+  } else {  // rare large box (near-camera voxel): plain loops, not prefetched
+    const float* base = feat + ((size_t)t.y0 * fw + t.x0) * CH + coff;
+    for (int ty = 0; ty < t.ny; ++ty) {
+      const float wy = tap_wy(t, ty);
+      float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int tx = 0; tx < t.nx; ++tx) {
+        const float wx = tap_wx(t, tx);
+        const float4 f4 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)ty * fw + tx) * CH));
+        rs.x = fmaf(wx, f4.x, rs.x);
+        rs.y = fmaf(wx, f4.y, rs.y);
+        rs.z = fmaf(wx, f4.z, rs.z);
+        rs.w = fmaf(wx, f4.w, rs.w);
+      }
+      acc.x = fmaf(wy, rs.x, acc.x);
+      acc.y = fmaf(wy, rs.y, acc.y);
+      acc.z = fmaf(wy, rs.z, acc.z);
+      acc.w = fmaf(wy, rs.w, acc.w);
+    }
+  }
+  return acc;
+}
+
+// All 8 K chunks of one height layer for the 16 rows of one producer warp: 32 items, DEPTH in flight.
+template <int T, int DEPTH>
+__device__ __forceinline__ void produce_layer(uint8_t* smem, SmemTail* tail, const BoxTaps* __restrict__ wtaps,
+                                              const float* __restrict__ feat, int fw, int pw, int lane, int& it) {
+  constexpr int ITEMS = (CH / KCH) * 4;
+  const int q = lane >> 3, j = lane & 7;
+  GatherBuf<T> buf[DEPTH];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) issue_item<T>(buf[d], wtaps[(d & 3) * 4 + q], feat, fw, (d >> 2) * KCH + j * 4);
+#pragma unroll 1
+  for (int base = 0; base < ITEMS; base += DEPTH) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      const int item = base + d;
+      const int cc = item >> 2, round = item & 3;
+      const int st = it % STAGES;
+      if (round == 0) mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+      const int lr = round * 4 + q;                     // row within the warp's 16
+      const BoxTaps t = wtaps[lr];
+      const float4 acc = reduce_item<T>(buf[d], t, feat, fw, cc * KCH + j * 4);
+      const int nxt = item + DEPTH;
+      if (nxt < ITEMS) issue_item<T>(buf[d], wtaps[(nxt & 3) * 4 + q], feat, fw, (nxt >> 2) * KCH + j * 4);
+      uint4 hi, lo;
+      hi.x = to_tf32(acc.x);
+      hi.y = to_tf32(acc.y);
+      hi.z = to_tf32(acc.z);
+      hi.w = to_tf32(acc.w);
+      lo.x = to_tf32(acc.x - __uint_as_float(hi.x));
+      lo.y = to_tf32(acc.y - __uint_as_float(hi.y));
+      lo.z = to_tf32(acc.z - __uint_as_float(hi.z));
+      lo.w = to_tf32(acc.w - __uint_as_float(hi.w));
+      uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
+      const uint32_t off = swz((uint32_t)(pw * 16 + lr), (uint32_t)j);
+      *reinterpret_cast<uint4*>(a_hi + off) = hi;
+      *reinterpret_cast<uint4*>(a_hi + A_BYTES + off) = lo;
+      if (round == 3) {
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->full[st]);
+        ++it;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -191,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
   const int v_begin = group * a.views_per_group;
   const int v_end = min(p.V, v_begin + a.views_per_group);
   const int n_vs = (v_end - v_begin) * p.S;          // (view, scale) iterations of this CTA
-  const int chunks_per_vs = p.nl * (CH / KCH);
+  constexpr int CHUNKS_PER_LAYER = CH / KCH;
 
   // ---- one-time setup ----
   for (int i = tid; i < p.S * CH; i += THREADS) tail->bias[i / CH][i % CH] = __ldg(p.bias[i / CH] + (i % CH));
@@ -201,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
       mbar_init(&tail->empty[s], 1);
     }
     mbar_init(&tail->acc_full, 1);
-    mbar_init(&tail->acc_empty, 4);
+    mbar_init(&tail->acc_empty, NUM_EPILOGUE_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -215,16 +324,18 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
 
+  if (warp < FIRST_PRODUCER_WARP) {
+    // warpgroup 0 (loader, MMA issuer, two idle warps) hands registers to the producer warpgroups
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == 0) {
     // ================= weight loader =================
     if (lane == 0) {
       int it = 0;
       for (int v = v_begin; v < v_end; ++v)
         for (int s = 0; s < p.S; ++s)
-          for (int kc = 0; kc < chunks_per_vs; ++kc, ++it) {
+          for (int kc = 0; kc < p.nl * CHUNKS_PER_LAYER; ++kc, ++it) {
             const int st = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&tail->empty[st], ph ^ 1);
+            mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
             uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
             mbar_arrive_expect_tx(&tail->full[st], 2 * B_BYTES);
             bulk_g2s(dst, a.wprep[s] + (size_t)kc * (2 * B_BYTES), 2 * B_BYTES, &tail->full[st]);
@@ -232,46 +343,55 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    // The TMEM accumulator is only trusted for ONE height layer (32 k-steps): the tensor core truncates every
+    // accumulation (measured: error grows linearly in K, biased toward zero), so layer partials are summed by the
+    // epilogue warps with round-to-nearest FADDs (drain) instead of inside the tensor core.
     if (lane == 0) {
-      int it = 0;
+      int it = 0, drain = 0;
       for (int vs = 0; vs < n_vs; ++vs) {
-        mbar_wait(&tail->acc_empty, (vs & 1) ^ 1);
-        tc_fence_after();
-        for (int kc = 0; kc < chunks_per_vs; ++kc, ++it) {
-          const int st = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&tail->full[st], ph);
+        for (int n = 0; n < p.nl; ++n, ++drain) {
+          mbar_wait(&tail->acc_empty, (drain & 1) ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
-          const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES);
+          for (int cc = 0; cc < CHUNKS_PER_LAYER; ++cc, ++it) {
+            const int st = it % STAGES;
+            mbar_wait(&tail->full[st], (it / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+            const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+            const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < KCH / 8; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // 8 tf32 = 32 bytes along K inside the swizzle row
-            // small cross terms first, the dominant hi*hi product last
-            tc_mma_tf32(tmem, a_lo + adv, b_hi + adv, IDESC, (kc | ks) ? 1u : 0u);
-            tc_mma_tf32(tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-            tc_mma_tf32(tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+            for (int ks = 0; ks < KCH / 8; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // 8 tf32 = 32 bytes along K inside the swizzle row
+              if (a.variant == 1) {
+                tc_mma_tf32(tmem, a_hi + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
+              } else {
+                tc_mma_tf32(tmem, a_lo + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
+                tc_mma_tf32(tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+                tc_mma_tf32(tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+              }
+            }
+            tc_commit(&tail->empty[st]);          // frees the stage when these MMAs have read it
           }
-          tc_commit(&tail->empty[st]);          // frees the stage when these MMAs have read it
+          tc_commit(&tail->acc_full);             // this layer's partial sum is complete
         }
-        tc_commit(&tail->acc_full);             // accumulator of this (view, scale) is complete
       }
     }
+  }
   } else if (warp < FIRST_EPILOGUE_WARP) {
     // ================= pool producers =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     const int pw = warp - FIRST_PRODUCER_WARP;       // 0..7 -> rows pw*16 .. pw*16+15
-    const int ptid = tid - FIRST_PRODUCER_WARP * 32;  // 0..255
-    const int q = lane >> 3, j = lane & 7;            // quarter-warp = one cell, 8 lanes x float4 = 32 channels
+    BoxTaps* wtaps = tail->taps[pw];
     int it = 0;
-    int nbuf = 0;
     for (int v = v_begin; v < v_end; ++v) {
       for (int s = 0; s < p.S; ++s) {
         const ScaleConst sc = p.sc[s];
         const float* __restrict__ feat = p.feats[s] + ((size_t)(b * p.V + v) * sc.fh * sc.fw) * CH;
-        for (int n = 0; n < p.nl; ++n, nbuf ^= 1) {
-          if (ptid < TILE_M) {
-            const int cell = cell0 + ptid;
+        for (int n = 0; n < p.nl; ++n) {
+          __syncwarp();                              // everyone is done with the previous layer's taps
+          int extent = 0;
+          if (lane < 16) {
+            const int cell = cell0 + pw * 16 + lane;
             BoxTaps t;
             if (cell < p.LW) {
               t = derive_taps(reinterpret_cast<const float4*>(p.boxes)[((size_t)v * p.nl + n) * p.LW + cell], sc);
@@ -279,118 +399,56 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
               t.x0 = t.y0 = t.nx = t.ny = 0;
               t.wx_first = t.wx_last = t.wy_first = t.wy_last = t.wy_mid = 0.f;
             }
-            tail->taps[nbuf][ptid] = t;
+            wtaps[lane] = t;
+            extent = max(t.nx, t.ny);
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");        // producers only
-          for (int cc = 0; cc < CH / KCH; ++cc, ++it) {
-            const int st = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&tail->empty[st], ph ^ 1);
-            uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
-            uint8_t* a_lo = a_hi + A_BYTES;
-            const int coff = cc * KCH + j * 4;
-#pragma unroll 1
-            for (int round = 0; round < 4; ++round) {
-              const int r = pw * 16 + round * 4 + q;
-              const BoxTaps t = tail->taps[nbuf][r];
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              const float* base = feat + ((size_t)t.y0 * sc.fw + t.x0) * CH + coff;
-              const bool small = (t.nx <= 3) && (t.ny <= 3);
-              if (__all_sync(0xffffffffu, small)) {
-                float4 val[3][3];
-                float wgt[3][3];
-#pragma unroll
-                for (int ty = 0; ty < 3; ++ty)
-#pragma unroll
-                  for (int tx = 0; tx < 3; ++tx) {
-                    const bool on = (ty < t.ny) && (tx < t.nx);
-                    wgt[ty][tx] = on ? tap_wy(t, ty) * tap_wx(t, tx) : 0.f;
-                    val[ty][tx] = on ? __ldg(reinterpret_cast<const float4*>(base + ((size_t)ty * sc.fw + tx) * CH))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                  }
-#pragma unroll
-                for (int ty = 0; ty < 3; ++ty)
-#pragma unroll
-                  for (int tx = 0; tx < 3; ++tx) {
-                    acc.x = fmaf(wgt[ty][tx], val[ty][tx].x, acc.x);
-                    acc.y = fmaf(wgt[ty][tx], val[ty][tx].y, acc.y);
-                    acc.z = fmaf(wgt[ty][tx], val[ty][tx].z, acc.z);
-                    acc.w = fmaf(wgt[ty][tx], val[ty][tx].w, acc.w);
-                  }
-              } else {
-                for (int ty = 0; ty < t.ny; ++ty) {
-                  const float wy = tap_wy(t, ty);
-                  float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-                  for (int tx = 0; tx < t.nx; ++tx) {
-                    const float wx = tap_wx(t, tx);
-                    const float4 f4 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)ty * sc.fw + tx) * CH));
-                    rs.x = fmaf(wx, f4.x, rs.x);
-                    rs.y = fmaf(wx, f4.y, rs.y);
-                    rs.z = fmaf(wx, f4.z, rs.z);
-                    rs.w = fmaf(wx, f4.w, rs.w);
-                  }
-                  acc.x = fmaf(wy, rs.x, acc.x);
-                  acc.y = fmaf(wy, rs.y, acc.y);
-                  acc.z = fmaf(wy, rs.z, acc.z);
-                  acc.w = fmaf(wy, rs.w, acc.w);
-                }
-              }
-              uint4 hi, lo;
-              hi.x = to_tf32(acc.x);
-              hi.y = to_tf32(acc.y);
-              hi.z = to_tf32(acc.z);
-              hi.w = to_tf32(acc.w);
-              lo.x = to_tf32(acc.x - __uint_as_float(hi.x));
-              lo.y = to_tf32(acc.y - __uint_as_float(hi.y));
-              lo.z = to_tf32(acc.z - __uint_as_float(hi.z));
-              lo.w = to_tf32(acc.w - __uint_as_float(hi.w));
-              const uint32_t off = swz((uint32_t)r, (uint32_t)j);
-              *reinterpret_cast<uint4*>(a_hi + off) = hi;
-              *reinterpret_cast<uint4*>(a_lo + off) = lo;
-            }
-            fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tail->full[st]);
-          }
+          extent = __reduce_max_sync(0xffffffffu, extent);   // also orders the taps writes before the reads below
+          __syncwarp();
+          if (extent <= 2)
+            produce_layer<2, 4>(smem, tail, wtaps, feat, sc.fw, pw, lane, it);
+          else
+            produce_layer<3, 2>(smem, tail, wtaps, feat, sc.fw, pw, lane, it);
         }
       }
     }
   } else {
-    // ================= epilogue =================
-    const int ew = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = ew * 32 + lane;
+    // ================= epilogue: layer drains + per-(view, scale) finalisation =================
+    const int e = warp - FIRST_EPILOGUE_WARP;      // 0..7
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int col_begin = (e >> 2) * (CH / 2);     // two warps per quarter split the 256 columns
+    const int row = quarter * 32 + lane;
     const int cell = cell0 + row;
-    const uint32_t lane_addr = tmem + ((uint32_t)(ew * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     float* outp = p.out + (size_t)b * CH * p.LW + cell;
-    int vs = 0;
-    for (int v = v_begin; v < v_end; ++v) {
-      for (int s = 0; s < p.S; ++s, ++vs) {
-        mbar_wait(&tail->acc_full, vs & 1);
+    int drain = 0;
+    for (int vs = 0; vs < n_vs; ++vs) {
+      const int s = vs % p.S;
+      for (int n = 0; n < p.nl; ++n, ++drain) {
+        mbar_wait(&tail->acc_full, drain & 1);
         tc_fence_after();
-        const bool first = (vs == 0), last = (vs == n_vs - 1);
+        const bool first_layer = (n == 0), last_layer = (n == p.nl - 1);
 #pragma unroll 1
-        for (int c0 = 0; c0 < CH; c0 += 32) {
-          float acc[32], sum[32];
+        for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
+          float acc[32], pre[32];
           tc_ld32(lane_addr + c0, acc);
-          if (!first) tc_ld32(lane_addr + CH + c0, sum);
+          if (!first_layer) tc_ld32(lane_addr + CH + c0, pre);
           tc_wait_ld();
+          if (!first_layer) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float y = fmaxf(acc[i] + tail->bias[s][c0 + i], 0.f);      // vfa_op.py:123-124
-            sum[i] = first ? y : sum[i] + y;                                 // vfanet.py:79, :82
+            for (int i = 0; i < 32; ++i) acc[i] += pre[i];                   // round-to-nearest layer sum
           }
-          if (last) {
-            if (cell < p.LW) {
-              if (a.n_groups == 1) {
+          if (!last_layer) {
+            tc_st32(lane_addr + CH + c0, acc);
+          } else if (cell < p.LW) {
+            // + bias, ReLU (vfa_op.py:123-124), then the sum over scales and views (vfanet.py:79, :82)
+            if (a.n_groups == 1 && vs == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) outp[(size_t)(c0 + i) * p.LW] = sum[i];
-              } else {
+              for (int i = 0; i < 32; ++i) outp[(size_t)(c0 + i) * p.LW] = fmaxf(acc[i] + tail->bias[s][c0 + i], 0.f);
+            } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(outp + (size_t)(c0 + i) * p.LW, sum[i]);
-              }
+              for (int i = 0; i < 32; ++i)
+                atomicAdd(outp + (size_t)(c0 + i) * p.LW, fmaxf(acc[i] + tail->bias[s][c0 + i], 0.f));
             }
-          } else {
-            tc_st32(lane_addr + CH + c0, sum);
           }
         }
         tc_wait_st();
@@ -441,6 +499,8 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, uint32_
   }
   UmmaArgs a;
   a.p = p;
+  const char* var = getenv("VFA_UMMA_VARIANT");
+  a.variant = var ? atoi(var) : 0;
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   for (int s = 0; s < VFA_MAX_SCALES; ++s) a.wprep[s] = reinterpret_cast<const uint8_t*>(ws) + (s < p.S ? s : 0) * per_scale;
   const int tiles = (p.LW + TILE_M - 1) / TILE_M;
