@@ -28,4 +28,4 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(f'{name} B={B} flags={flags} path={vfa_b200.last_kernel_path()}: {ms:.3f} ms/step, {B / ms * 1e3:.1f} frames/s, mean={float(out.mean()):.5f}')
+print(f'var={os.environ.get("VFA_UMMA_VARIANT","0")} {name} B={B} flags={flags} path={vfa_b200.last_kernel_path()}: {ms:.3f} ms/step, {B / ms * 1e3:.1f} frames/s, mean={float(out.mean()):.5f}')

@@ -41,8 +41,24 @@ constexpr int NUM_EPILOGUE_WARPS = 8;
 constexpr int THREADS = 20 * 32;
 constexpr int TMEM_COLS = 512;
 
-struct __align__(8) SmemTail {
-  BoxTaps taps[NUM_PRODUCER_WARPS][16];
+// Gather recipe of one (cell, layer) row at one scale, prepared once per (view, scale, layer) in shared memory:
+// element offset of the first texel, tap counts and the separable edge weights (1/area and visibility folded
+// into the row weights; interior taps weigh 1 resp. wy_mid), plus the nine products of a <= 3x3 box.  80 bytes.
+struct __align__(16) RowDesc {
+  int base;        // ((y0 * fw) + x0) * CH
+  int nx, ny;      // tap counts (0 = not visible)
+  float wx_first, wx_last, wy_first, wy_last, wy_mid;
+  float w9[12];    // wy(ty) * wx(tx) at [ty*3+tx], ty,tx in {0,1,2} (0 = tap not used); last 3 are padding
+};
+__device__ __forceinline__ float desc_wx(const RowDesc& d, int i) {
+  return i >= d.nx ? 0.f : (i == 0 ? d.wx_first : (i == d.nx - 1 ? d.wx_last : 1.0f));
+}
+__device__ __forceinline__ float desc_wy(const RowDesc& d, int i) {
+  return i >= d.ny ? 0.f : (i == 0 ? d.wy_first : (i == d.ny - 1 ? d.wy_last : d.wy_mid));
+}
+
+struct __align__(16) SmemTail {
+  RowDesc desc[NUM_PRODUCER_WARPS][16];
   float bias[VFA_MAX_SCALES][CH];
   unsigned long long full[STAGES];
   unsigned long long empty[STAGES];
@@ -51,6 +67,13 @@ struct __align__(8) SmemTail {
   uint32_t tmem_base;
 };
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
+
+constexpr int TRACE_N = 2048;
+#define TRACE(role, idx)                                                                          \
+  do {                                                                                            \
+    if (a.trace != nullptr && blockIdx.x == a.trace_block && blockIdx.y == 0 && (idx) < TRACE_N)  \
+      a.trace[(role) * TRACE_N + (idx)] = clock64();                                              \
+  } while (0)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +100,24 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
       "}\n" ::"r"(addr),
       "r"(parity)
       : "memory");
+}
+// same, with a back-off between probes: for warps that wait long and must not steal issue slots
+__device__ __forceinline__ void mbar_wait_sleep(void* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(128);
+  }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -179,117 +220,210 @@ struct UmmaArgs {
   const uint8_t* wprep[VFA_MAX_SCALES];
   int n_groups;        // view groups (grid.x = tiles * n_groups); > 1 -> atomic accumulation into a zeroed output
   int views_per_group;
-  int variant;         // debug: 0 = 3xTF32, 1 = hi*hi only (single-pass tf32)
+  long long* trace;    // debug: timestamps of CTA (trace_block,0) when non-null: [role 0..3][TRACE_N]
+  int trace_block;
+  int variant;         // debug bits: 1 = hi*hi only, 2 = no gather loads, 4 = no MMA, 8 = no weight loads
 };
 
-// One producer work item = 4 cells (one per quarter-warp) x 32 channels of one K chunk.  The loads of an item are
-// issued into registers DEPTH items ahead of their use, so a warp keeps DEPTH * T * T 128-bit loads in flight.
-template <int T>
-struct GatherBuf {
-  float4 v[T][T];
-};
+// ---- pooling producers ----------------------------------------------------------------------------------------
+// One work item = 4 cells (one per quarter-warp) x 32 channels of one K chunk; 8 lanes x float4 read one 128-byte
+// row of a texel, so every load instruction moves 4 full cache lines.  A producer warp owns the tile rows
+// 32*round + 4*pw + {0,1,2,3}, round = 0..3: the 4 cells of one instruction are adjacent (their boxes overlap, so
+// their loads coalesce / hit L1) while the rounds are spread over the tile (box sizes vary smoothly along a BEV
+// row, so every warp gets the same mix of cheap and expensive rows).  Loads are predicated on the tap weight (taps with weight 0 are never
+// fetched) and issued ahead of their use so several items / windows are in flight per warp.
 
-template <int T>
-__device__ __forceinline__ void issue_item(GatherBuf<T>& buf, const BoxTaps& t, const float* __restrict__ feat, int fw,
-                                           int coff) {
-  const float* base = feat + ((size_t)t.y0 * fw + t.x0) * CH + coff;
-#pragma unroll
-  for (int ty = 0; ty < T; ++ty)
-#pragma unroll
-    for (int tx = 0; tx < T; ++tx) {
-      const bool on = (ty < t.ny) && (tx < t.nx);
-      buf.v[ty][tx] = on ? __ldg(reinterpret_cast<const float4*>(base + ((size_t)ty * fw + tx) * CH))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+// @(w != 0) ld.global.nc.v4.f32 v, [ptr + IMM]   -- v keeps its old (finite) contents when the tap is off
+template <int IMM>
+__device__ __forceinline__ void ldg_if(float4& v, const float* ptr, float w) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.neu.f32 p, %5, 0f00000000;\n\t"
+      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t"
+      "}\n"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(ptr), "f"(w), "n"(IMM));
+}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  if (w != 0.f) {        // predicated, so a stale Inf/NaN left in an unused slot can never leak in
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  }
 }
 
-template <int T>
-__device__ __forceinline__ float4 reduce_item(const GatherBuf<T>& buf, const BoxTaps& t, const float* __restrict__ feat,
-                                              int fw, int coff) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (t.nx <= T && t.ny <= T) {
+// Store one item's pooled values as the tf32 hi/lo pair into the swizzled operand tiles.
+__device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const float4& acc) {
+  uint4 hi, lo;
+  hi.x = to_tf32(acc.x);
+  hi.y = to_tf32(acc.y);
+  hi.z = to_tf32(acc.z);
+  hi.w = to_tf32(acc.w);
+  lo.x = to_tf32(acc.x - __uint_as_float(hi.x));
+  lo.y = to_tf32(acc.y - __uint_as_float(hi.y));
+  lo.z = to_tf32(acc.z - __uint_as_float(hi.z));
+  lo.w = to_tf32(acc.w - __uint_as_float(hi.w));
+  *reinterpret_cast<uint4*>(a_hi + off) = hi;
+  *reinterpret_cast<uint4*>(a_hi + A_BYTES + off) = lo;
+}
+
+struct ProducerCtx {
+  uint8_t* smem;
+  SmemTail* tail;
+  const RowDesc* wdesc;     // this warp's 16 recipes (shared memory)
+  const float* feat;        // [fh, fw, CH] map of this (frame, view, scale); nullptr = debug knock-out
+  size_t row_stride;        // fw * CH
+  int pw, lane, q, j;
+  long long* trace;
+};
+
+// Called when an item is complete: waits for the stage slot (first round only), stores, signals (last round).
+__device__ __forceinline__ void finish_item(const ProducerCtx& c, int round, float4& acc, int& it) {
+  const int st = it & (STAGES - 1);
+  if (round == 0) {
+    mbar_wait(&c.tail->empty[st], ((it / STAGES) & 1) ^ 1);
+    if (c.trace != nullptr && c.lane == 0 && 8 * it + c.pw < TRACE_N) c.trace[1 * TRACE_N + 8 * it + c.pw] = clock64();
+  }
+  const int row = 32 * round + 4 * c.pw + c.q;
+  store_split(c.smem + (size_t)st * STAGE_BYTES, swz((uint32_t)row, (uint32_t)c.j), acc);
+  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (round == 3) {
+    fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.tail->full[st]);
+    if (c.trace != nullptr && c.lane == 0 && 8 * it + c.pw < TRACE_N) c.trace[2 * TRACE_N + 8 * it + c.pw] = clock64();
+    ++it;
+  }
+}
+
+// Layers where every row of the warp has at most TxT taps (T = 2: the common case at strides 16 and 32; T = 3:
+// most of stride 8): 32 items, DEPTH in flight, tap weights precomputed in the recipe.
+template <int T, int DEPTH>
+__device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, int& it) {
+  constexpr int ITEMS = (CH / KCH) * 4;
+  float4 buf[DEPTH][T][T];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+    for (int ty = 0; ty < T; ++ty)
+#pragma unroll
+      for (int tx = 0; tx < T; ++tx) buf[d][ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto issue = [&](float4(&v)[T][T], int item) {
+    if (c.feat == nullptr) return;
+    const RowDesc& d = c.wdesc[(item & 3) * 4 + c.q];
+    const float* r = c.feat + d.base + (item >> 2) * KCH + c.j * 4;
 #pragma unroll
     for (int ty = 0; ty < T; ++ty) {
-      const float wy = (ty < t.ny) ? tap_wy(t, ty) : 0.f;
-#pragma unroll
-      for (int tx = 0; tx < T; ++tx) {
-        const float w = (tx < t.nx) ? wy * tap_wx(t, tx) : 0.f;
-        acc.x = fmaf(w, buf.v[ty][tx].x, acc.x);
-        acc.y = fmaf(w, buf.v[ty][tx].y, acc.y);
-        acc.z = fmaf(w, buf.v[ty][tx].z, acc.z);
-        acc.w = fmaf(w, buf.v[ty][tx].w, acc.w);
-      }
+      ldg_if<0>(v[ty][0], r, d.w9[ty * 3 + 0]);
+      ldg_if<CH * 4>(v[ty][1], r, d.w9[ty * 3 + 1]);
+      if (T > 2) ldg_if<2 * CH * 4>(v[ty][T - 1], r, d.w9[ty * 3 + 2]);
+      r += c.row_stride;
     }
-  } else {  // rare large box (near-camera voxel): plain loops, not prefetched
-    const float* base = feat + ((size_t)t.y0 * fw + t.x0) * CH + coff;
-    for (int ty = 0; ty < t.ny; ++ty) {
-      const float wy = tap_wy(t, ty);
-      float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int tx = 0; tx < t.nx; ++tx) {
-        const float wx = tap_wx(t, tx);
-        const float4 f4 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)ty * fw + tx) * CH));
-        rs.x = fmaf(wx, f4.x, rs.x);
-        rs.y = fmaf(wx, f4.y, rs.y);
-        rs.z = fmaf(wx, f4.z, rs.z);
-        rs.w = fmaf(wx, f4.w, rs.w);
-      }
-      acc.x = fmaf(wy, rs.x, acc.x);
-      acc.y = fmaf(wy, rs.y, acc.y);
-      acc.z = fmaf(wy, rs.z, acc.z);
-      acc.w = fmaf(wy, rs.w, acc.w);
-    }
-  }
-  return acc;
-}
-
-// All 8 K chunks of one height layer for the 16 rows of one producer warp: 32 items, DEPTH in flight.
-template <int T, int DEPTH>
-__device__ __forceinline__ void produce_layer(uint8_t* smem, SmemTail* tail, const BoxTaps* __restrict__ wtaps,
-                                              const float* __restrict__ feat, int fw, int pw, int lane, int& it) {
-  constexpr int ITEMS = (CH / KCH) * 4;
-  const int q = lane >> 3, j = lane & 7;
-  GatherBuf<T> buf[DEPTH];
+  };
 #pragma unroll
-  for (int d = 0; d < DEPTH; ++d) issue_item<T>(buf[d], wtaps[(d & 3) * 4 + q], feat, fw, (d >> 2) * KCH + j * 4);
+  for (int d = 0; d < DEPTH; ++d) issue(buf[d], d);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int base = 0; base < ITEMS; base += DEPTH) {
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) {
-      const int item = base + d;
-      const int cc = item >> 2, round = item & 3;
-      const int st = it % STAGES;
-      if (round == 0) mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
-      const int lr = round * 4 + q;                     // row within the warp's 16
-      const BoxTaps t = wtaps[lr];
-      const float4 acc = reduce_item<T>(buf[d], t, feat, fw, cc * KCH + j * 4);
-      const int nxt = item + DEPTH;
-      if (nxt < ITEMS) issue_item<T>(buf[d], wtaps[(nxt & 3) * 4 + q], feat, fw, (nxt >> 2) * KCH + j * 4);
-      uint4 hi, lo;
-      hi.x = to_tf32(acc.x);
-      hi.y = to_tf32(acc.y);
-      hi.z = to_tf32(acc.z);
-      hi.w = to_tf32(acc.w);
-      lo.x = to_tf32(acc.x - __uint_as_float(hi.x));
-      lo.y = to_tf32(acc.y - __uint_as_float(hi.y));
-      lo.z = to_tf32(acc.z - __uint_as_float(hi.z));
-      lo.w = to_tf32(acc.w - __uint_as_float(hi.w));
-      uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
-      const uint32_t off = swz((uint32_t)(pw * 16 + lr), (uint32_t)j);
-      *reinterpret_cast<uint4*>(a_hi + off) = hi;
-      *reinterpret_cast<uint4*>(a_hi + A_BYTES + off) = lo;
-      if (round == 3) {
-        fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->full[st]);
-        ++it;
-      }
+      const int item = base + d, round = item & 3;
+      const RowDesc& rd = c.wdesc[round * 4 + c.q];
+#pragma unroll
+      for (int ty = 0; ty < T; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < T; ++tx) fma4(acc, rd.w9[ty * 3 + tx], buf[d][ty][tx]);
+      if (item + DEPTH < ITEMS) issue(buf[d], item + DEPTH);
+      finish_item(c, round, acc, it);
     }
   }
 }
 
+// General layers: every item walks its box in 3x3 windows (boxes grow to 8x8 texels and beyond for voxels close
+// to a camera before the reference's area cap hides them); the next window's 9 predicated loads are in flight
+// while the current one is reduced.  nwx / nwy hold the per-round window counts (8 bits per round, warp-uniform).
+struct WinPos {
+  int cc, rd, sy, sx;
+};
+
+__device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx, uint32_t nwy, int* it_io) {
+  int it = *it_io;
+  float4 bufA[3][3], bufB[3][3];
+  float wA[3][3], wB[3][3];
+#pragma unroll
+  for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < 3; ++tx) bufA[ty][tx] = bufB[ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto issue = [&](float4(&v)[3][3], float(&w)[3][3], const WinPos& p) {
+    const RowDesc& d = c.wdesc[p.rd * 4 + c.q];
+    float wx[3], wy[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      wx[k] = desc_wx(d, 3 * p.sx + k);
+      wy[k] = desc_wy(d, 3 * p.sy + k);
+    }
+    const float* r = (c.feat == nullptr ? nullptr : c.feat + d.base) + (size_t)(3 * p.sy) * c.row_stride +
+                     (size_t)(3 * p.sx) * CH + p.cc * KCH + c.j * 4;
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) {
+      w[ty][0] = wy[ty] * wx[0];
+      w[ty][1] = wy[ty] * wx[1];
+      w[ty][2] = wy[ty] * wx[2];
+      if (c.feat != nullptr) {
+        ldg_if<0>(v[ty][0], r, w[ty][0]);
+        ldg_if<CH * 4>(v[ty][1], r, w[ty][1]);
+        ldg_if<2 * CH * 4>(v[ty][2], r, w[ty][2]);
+      }
+      r += c.row_stride;
+    }
+  };
+  auto advance = [&](WinPos p, bool& valid) {
+    valid = true;
+    if (++p.sx < (int)((nwx >> (8 * p.rd)) & 255u)) return p;
+    p.sx = 0;
+    if (++p.sy < (int)((nwy >> (8 * p.rd)) & 255u)) return p;
+    p.sy = 0;
+    if (++p.rd < 4) return p;
+    p.rd = 0;
+    if (++p.cc < CH / KCH) return p;
+    valid = false;
+    return p;
+  };
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto consume = [&](const float4(&v)[3][3], const float(&w)[3][3], const WinPos& p) {
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+      for (int tx = 0; tx < 3; ++tx) fma4(acc, w[ty][tx], v[ty][tx]);
+    if (p.sx + 1 == (int)((nwx >> (8 * p.rd)) & 255u) && p.sy + 1 == (int)((nwy >> (8 * p.rd)) & 255u))
+      finish_item(c, p.rd, acc, it);
+  };
+
+  WinPos cur{0, 0, 0, 0}, nxt;
+  bool more;
+  issue(bufA, wA, cur);
+  while (true) {
+    nxt = advance(cur, more);
+    if (more) issue(bufB, wB, nxt);
+    consume(bufA, wA, cur);
+    if (!more) break;
+    cur = nxt;
+    nxt = advance(cur, more);
+    if (more) issue(bufA, wA, nxt);
+    consume(bufB, wB, cur);
+    if (!more) break;
+    cur = nxt;
+  }
+  *it_io = it;
+}
+
 __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align by pointer arithmetic on the __shared__ array (keeps the shared address space visible to the compiler)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
   const AggParams& p = a.p;
 
@@ -337,8 +471,13 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
             const int st = it % STAGES;
             mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
             uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
-            mbar_arrive_expect_tx(&tail->full[st], 2 * B_BYTES);
-            bulk_g2s(dst, a.wprep[s] + (size_t)kc * (2 * B_BYTES), 2 * B_BYTES, &tail->full[st]);
+            TRACE(3, 1024 + it);
+            if (a.variant & 8) {   // debug knock-out: no weight traffic
+              mbar_arrive(&tail->full[st]);
+            } else {
+              mbar_arrive_expect_tx(&tail->full[st], 2 * B_BYTES);
+              bulk_g2s(dst, a.wprep[s] + (size_t)kc * (2 * B_BYTES), 2 * B_BYTES, &tail->full[st]);
+            }
           }
     }
   } else if (warp == 1) {
@@ -354,7 +493,9 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           tc_fence_after();
           for (int cc = 0; cc < CHUNKS_PER_LAYER; ++cc, ++it) {
             const int st = it % STAGES;
+            TRACE(0, 2 * it);
             mbar_wait(&tail->full[st], (it / STAGES) & 1);
+            TRACE(0, 2 * it + 1);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
             const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
@@ -362,7 +503,9 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
 #pragma unroll
             for (int ks = 0; ks < KCH / 8; ++ks) {
               const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // 8 tf32 = 32 bytes along K inside the swizzle row
-              if (a.variant == 1) {
+              if (a.variant & 4) {
+                // debug knock-out: no MMA
+              } else if (a.variant & 1) {
                 tc_mma_tf32(tmem, a_hi + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
               } else {
                 tc_mma_tf32(tmem, a_lo + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
@@ -380,34 +523,74 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
   } else if (warp < FIRST_EPILOGUE_WARP) {
     // ================= pool producers =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-    const int pw = warp - FIRST_PRODUCER_WARP;       // 0..7 -> rows pw*16 .. pw*16+15
-    BoxTaps* wtaps = tail->taps[pw];
+    const int pw = warp - FIRST_PRODUCER_WARP;       // 0..7 -> tile rows 32*round + 4*pw + {0..3}
+    RowDesc* wdesc = tail->desc[pw];
+    ProducerCtx c;
+    c.smem = smem;
+    c.tail = tail;
+    c.wdesc = wdesc;
+    c.pw = pw;
+    c.lane = lane;
+    c.q = lane >> 3;
+    c.j = lane & 7;
+    c.trace = (blockIdx.x == a.trace_block && blockIdx.y == 0) ? a.trace : nullptr;
     int it = 0;
     for (int v = v_begin; v < v_end; ++v) {
       for (int s = 0; s < p.S; ++s) {
         const ScaleConst sc = p.sc[s];
-        const float* __restrict__ feat = p.feats[s] + ((size_t)(b * p.V + v) * sc.fh * sc.fw) * CH;
+        c.feat = (a.variant & 2) ? nullptr : p.feats[s] + ((size_t)(b * p.V + v) * sc.fh * sc.fw) * CH;
+        c.row_stride = (size_t)sc.fw * CH;
         for (int n = 0; n < p.nl; ++n) {
-          __syncwarp();                              // everyone is done with the previous layer's taps
-          int extent = 0;
+          __syncwarp();                              // everyone is done with the previous layer's recipes
+          int nx = 0, ny = 0;
           if (lane < 16) {
-            const int cell = cell0 + pw * 16 + lane;
-            BoxTaps t;
+            const int cell = cell0 + 32 * (lane >> 2) + 4 * pw + (lane & 3);
+            RowDesc d;
+            d.base = 0;
+            d.nx = d.ny = 0;
+            d.wx_first = d.wx_last = d.wy_first = d.wy_last = d.wy_mid = 0.f;
             if (cell < p.LW) {
-              t = derive_taps(reinterpret_cast<const float4*>(p.boxes)[((size_t)v * p.nl + n) * p.LW + cell], sc);
-            } else {
-              t.x0 = t.y0 = t.nx = t.ny = 0;
-              t.wx_first = t.wx_last = t.wy_first = t.wy_last = t.wy_mid = 0.f;
+              const BoxTaps t =
+                  derive_taps(reinterpret_cast<const float4*>(p.boxes)[((size_t)v * p.nl + n) * p.LW + cell], sc);
+              d.base = (t.y0 * sc.fw + t.x0) * CH;
+              d.nx = t.nx;
+              d.ny = t.ny;
+              d.wx_first = t.wx_first;
+              d.wx_last = t.wx_last;
+              d.wy_first = t.wy_first;
+              d.wy_last = t.wy_last;
+              d.wy_mid = t.wy_mid;
             }
-            wtaps[lane] = t;
-            extent = max(t.nx, t.ny);
+#pragma unroll
+            for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+              for (int tx = 0; tx < 3; ++tx) d.w9[ty * 3 + tx] = desc_wy(d, ty) * desc_wx(d, tx);
+            d.w9[9] = d.w9[10] = d.w9[11] = 0.f;
+            wdesc[lane] = d;
+            nx = d.nx;
+            ny = d.ny;
           }
-          extent = __reduce_max_sync(0xffffffffu, extent);   // also orders the taps writes before the reads below
+          // per-round (4 consecutive lanes) maxima, then the window counts of the 4 rounds packed 8 bits each
+          nx = max(nx, __shfl_xor_sync(0xffffffffu, nx, 1));
+          nx = max(nx, __shfl_xor_sync(0xffffffffu, nx, 2));
+          ny = max(ny, __shfl_xor_sync(0xffffffffu, ny, 1));
+          ny = max(ny, __shfl_xor_sync(0xffffffffu, ny, 2));
+          uint32_t nwx = 0, nwy = 0;
+          int extent = 0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int mx = __shfl_sync(0xffffffffu, nx, 4 * r), my = __shfl_sync(0xffffffffu, ny, 4 * r);
+            extent = max(extent, max(mx, my));
+            nwx |= (uint32_t)min(255, max(1, (mx + 2) / 3)) << (8 * r);
+            nwy |= (uint32_t)min(255, max(1, (my + 2) / 3)) << (8 * r);
+          }
           __syncwarp();
           if (extent <= 2)
-            produce_layer<2, 4>(smem, tail, wtaps, feat, sc.fw, pw, lane, it);
+            produce_layer_small<2, 4>(c, it);
+          else if (extent <= 3)
+            produce_layer_small<3, 2>(c, it);
           else
-            produce_layer<3, 2>(smem, tail, wtaps, feat, sc.fw, pw, lane, it);
+            produce_layer_win(c, nwx, nwy, &it);
         }
       }
     }
@@ -424,9 +607,11 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     for (int vs = 0; vs < n_vs; ++vs) {
       const int s = vs % p.S;
       for (int n = 0; n < p.nl; ++n, ++drain) {
-        mbar_wait(&tail->acc_full, drain & 1);
+        mbar_wait_sleep(&tail->acc_full, drain & 1);
+        if (e == 0 && lane == 0) TRACE(3, 2 * drain);
         tc_fence_after();
         const bool first_layer = (n == 0), last_layer = (n == p.nl - 1);
+        // pass 1: fold this layer's partial into the fp32 running sum kept in TMEM columns [256, 512)
 #pragma unroll 1
         for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
           float acc[32], pre[32];
@@ -437,24 +622,33 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] += pre[i];                   // round-to-nearest layer sum
           }
-          if (!last_layer) {
-            tc_st32(lane_addr + CH + c0, acc);
-          } else if (cell < p.LW) {
-            // + bias, ReLU (vfa_op.py:123-124), then the sum over scales and views (vfanet.py:79, :82)
-            if (a.n_groups == 1 && vs == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) outp[(size_t)(c0 + i) * p.LW] = fmaxf(acc[i] + tail->bias[s][c0 + i], 0.f);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                atomicAdd(outp + (size_t)(c0 + i) * p.LW, fmaxf(acc[i] + tail->bias[s][c0 + i], 0.f));
-            }
-          }
+          tc_st32(lane_addr + CH + c0, acc);
         }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->acc_empty);      // accumulator columns may be overwritten
+        if (lane == 0) mbar_arrive(&tail->acc_empty);      // accumulator columns may be overwritten by the next layer
+        if (e == 0 && lane == 0) TRACE(3, 2 * drain + 1);
+        if (last_layer) {
+          // pass 2 (overlaps the next layer's MMAs): + bias, ReLU (vfa_op.py:123-124), then the sum over scales and
+          // views (vfanet.py:79, :82) straight into the [B, C, L*W] output
+#pragma unroll 1
+          for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
+            float y[32];
+            tc_ld32(lane_addr + CH + c0, y);
+            tc_wait_ld();
+            if (cell < p.LW) {
+              if (a.n_groups == 1 && vs == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) outp[(size_t)(c0 + i) * p.LW] = fmaxf(y[i] + tail->bias[s][c0 + i], 0.f);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  atomicAdd(outp + (size_t)(c0 + i) * p.LW, fmaxf(y[i] + tail->bias[s][c0 + i], 0.f));
+              }
+            }
+          }
+        }
       }
     }
   }
@@ -501,6 +695,13 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, uint32_
   a.p = p;
   const char* var = getenv("VFA_UMMA_VARIANT");
   a.variant = var ? atoi(var) : 0;
+  a.trace = nullptr;
+  const bool want_trace = getenv("VFA_UMMA_TRACE") != nullptr;   // debugging aid only (allocates, synchronises)
+  a.trace_block = want_trace ? atoi(getenv("VFA_UMMA_TRACE")) : 0;
+  if (want_trace) {
+    VFA_CUDA(cudaMalloc(&a.trace, 4 * TRACE_N * sizeof(long long)));
+    VFA_CUDA(cudaMemset(a.trace, 0, 4 * TRACE_N * sizeof(long long)));
+  }
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   for (int s = 0; s < VFA_MAX_SCALES; ++s) a.wprep[s] = reinterpret_cast<const uint8_t*>(ws) + (s < p.S ? s : 0) * per_scale;
   const int tiles = (p.LW + TILE_M - 1) / TILE_M;
@@ -511,6 +712,27 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, uint32_
   dim3 grid(tiles * a.n_groups, p.B);
   aggregate_fwd_umma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
   VFA_LAUNCH_CHECK("aggregate_fwd_umma_kernel");
+  if (want_trace) {
+    static long long host[4 * TRACE_N];
+    VFA_CUDA(cudaStreamSynchronize(st));
+    VFA_CUDA(cudaMemcpy(host, a.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(a.trace);
+    FILE* f = fopen("gpurun_out/umma_trace.txt", "w");
+    if (f) {
+      long long t0 = host[0];
+      for (int i = 0; i < 120; ++i) {
+        fprintf(f, "st %3d mma wait %7lld->%7lld | wload %7lld | empty seen/arrive:", i, host[2 * i] - t0,
+                host[2 * i + 1] - t0, host[3 * TRACE_N + 1024 + i] - t0);
+        for (int w = 0; w < 8; ++w)
+          fprintf(f, " %7lld/%7lld", host[TRACE_N + 8 * i + w] - t0, host[2 * TRACE_N + 8 * i + w] - t0);
+        fprintf(f, "\n");
+      }
+      for (int i = 0; i < 15; ++i)
+        fprintf(f, "layer %3d  epi: acc_full seen %8lld  drain done %8lld\n", i, host[3 * TRACE_N + 2 * i] - t0,
+                host[3 * TRACE_N + 2 * i + 1] - t0);
+      fclose(f);
+    }
+  }
   set_path("umma_tf32x3");
   return VFA_OK;
 }
