@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the aggregation hot path (BASELINE.json: aggregation frames/s and % of roofline at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference ...                     # the reference algorithm on the box's host cores
+
+One "step" = one pass of the hot path over one batch of synthetic frames:
+    projection table (1 launch) + weight re-layout (3 launches) + fused gather/collapse/ReLU/sum kernel (1 launch).
+Default workload: MultiviewC-shaped (7 views, 1280x720 source, stride-8/16/32 maps 90x160 / 45x80 / 23x40, C = 256,
+156x156x5 voxel grid = the shipped config-of-record of "37.5 m x 37.5 m"), B frames per GPU.
+Multi-GPU = batch data parallel (frames are independent: no data-path collective, weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same through the public
+API with pinned-host inputs and a device->host read of the result inside the timed region; `roofline` describes the
+fused kernel; `cpu_baseline` = the oracle's torch-CPU port of the reference timed on the host cores (N = 1 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch                      # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = 'aggregation_frames_per_s'
+UNIT = 'frames/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+    ap.add_argument('--workload', choices=['MultiviewC', 'MultiviewX', 'Wildtrack'], default='MultiviewC')
+    ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step')
+    ap.add_argument('--flags', type=int, default=0, help='vfa_aggregate_fwd flags (1 = force SIMT path)')
+    ap.add_argument('--cpu-views', type=int, default=2, help='views of one frame timed for cpu_baseline')
+    ap.add_argument('--ref-views', type=int, default=1, help='views of one frame per step of --impl reference')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p['hbm_gbs'], tflops=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    tflops_burst=p['bf16_tflops'], source='measured (MEASURED_PEAKS.json, sustained bf16 figure: kernel '
+                    'timed inside a long step)')
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source='fallback (B200_PROFILING.md)')
+
+
+def workload_numbers(geom, batch):
+    """Algorithmic bytes / flops of one step on one GPU."""
+    L, W = geom.grid_shape
+    C, nl, V = geom.channels, geom.n_layers, geom.n_views
+    px = sum(h * w for h, w in geom.feature_sizes())
+    feat_bytes = batch * V * px * C * 4
+    out_bytes = batch * C * L * W * 4
+    const_bytes = 3 * (C * C * nl + C) * 4 + V * nl * L * W * 16 + L * W * 12 + V * 48
+    flops = 2.0 * L * W * (C * nl) * C * 3 * V * batch          # collapse contraction, grid-side (as the reference)
+    return dict(bytes=feat_bytes + out_bytes + const_bytes, flops=flops, feat_bytes=feat_bytes, out_bytes=out_bytes)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(',')]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+def cpu_port_time(geom, views, threads_note=True):
+    """Seconds for `views` views x 3 scales of ONE frame through the oracle's torch-CPU port of the reference
+    (fp32, no_grad, boxes re-derived per call like the reference)."""
+    from oracle import ref_port
+    from vfa_b200 import geometry, synthetic
+    grid = geometry.grid_for(geom)
+    calibs = synthetic.ring_calibs(geom)[:views]
+    feats = synthetic.features(geom, batch=1, n_views=views, seed=0)
+    params = synthetic.collapse_params(geom, seed=0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        out = ref_port.aggregate(feats, calibs, grid, params, geom.grid_height, geom.cube_size, geom.name,
+                                 geom.image_size, cache_boxes=False)
+        dt = time.perf_counter() - t0
+    return dt, float(out.mean())
+
+
+def run_reference(args):
+    """`--impl reference`: the reference algorithm (oracle port: same torch operator sequence as reference
+    vfa_op.py:61-125 looped as vfanet.py:64-82) on the host cores; rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from vfa_b200 import geometry
+    geom = geometry.GEOMETRIES[args.workload]
+    views = max(1, min(args.ref_views, geom.n_views))
+    for _ in range(args.warmup):
+        cpu_port_time(geom, views)
+    times = [cpu_port_time(geom, views)[0] for _ in range(args.steps)]
+    per_step = sum(times) / len(times)
+    fps = 1.0 / (per_step * geom.n_views / views)
+    sample = (f'{views} of {geom.n_views} views x 3 scales of one {args.workload}-shaped frame per step, fp32 torch-CPU '
+              f'port of the reference operator sequence; frames/s = 1 / (step_s * {geom.n_views}/{views})')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}-shaped aggregation forward', 'batch_per_gpu': 1, 'views': geom.n_views,
+                   'channels': geom.channels, 'grid': list(geom.grid_shape) + [geom.n_layers]},
+        'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample,
+                         'host_cpus': os.cpu_count()},
+        'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f'--gpus {args.gpus} needs a torchrun launch with {args.gpus} ranks (WORLD_SIZE={world})')
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    import vfa_b200
+    from vfa_b200 import geometry
+    from vfa_b200 import synthetic
+    geom = geometry.GEOMETRIES[args.workload]
+    B, V, C = args.batch, geom.n_views, geom.channels
+    zs = list(range(0, geom.grid_height, geom.cube_size[2]))
+    grid = geometry.grid_for(geom).to(dev)
+    calibs = synthetic.ring_calibs(geom).to(dev)
+    cgeom = vfa_b200.make_geometry(len(zs), geom.cube_size, zs, grid.shape[:2], geom.name, geom.image_size)
+    params = synthetic.collapse_params(geom, seed=0)
+    weights, biases = [w.to(dev) for w, _ in params], [b.to(dev) for _, b in params]
+
+    # synthetic features, generated on the device (seed differs per rank: every GPU owns different frames);
+    # logical [B,V,C,fH,fW], stored channels-last = the layout the lateral convs emit in torch.channels_last
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feats_cl = [torch.randn(B, V, h, w, C, generator=gen, device=dev).relu_() for (h, w) in geom.feature_sizes()]
+    shape = vfa_b200.make_shape(feats_cl, cgeom.n_layers)
+    ws = vfa_b200.workspace_for(cgeom, shape, args.flags, dev)
+    out = torch.empty(B, C, grid.shape[0], grid.shape[1], device=dev)
+    nums = workload_numbers(geom, B)
+
+    kernel_ms = []
+
+    def step(timed_events=None):
+        table = vfa_b200.build_table(cgeom, calibs, grid)                           # 1 launch
+        vfa_b200.prepare_weights(cgeom, shape, weights, args.flags, workspace=ws)    # 3 launches
+        if timed_events is not None:
+            timed_events[0].record()
+        vfa_b200.aggregate_forward_raw(feats_cl, table, weights, biases, args.flags, out=out, workspace=ws,
+                                       prepared=True)                                # 1 launch (+1 memset if view-split)
+        if timed_events is not None:
+            timed_events[1].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    path = vfa_b200.last_kernel_path()
+    launches_per_step = 5        # table_build + 3 x prep_weight + fused aggregate kernel (memsets not counted)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(kev[i])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev0.elapsed_time(ev1)
+    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+    kern = sum(kernel_ms) / len(kernel_ms)
+
+    # ---- end to end through the public API: pinned host NCHW features -> device -> aggregate -> host ----
+    e2e = None
+    if not args.no_e2e:
+        host_feats = [f.permute(0, 1, 4, 2, 3).contiguous().cpu().pin_memory() for f in feats_cl]   # [B,V,C,fH,fW]
+        host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+
+        def e2e_step():
+            dfeats = [h.to(dev, non_blocking=True) for h in host_feats]
+            table = vfa_b200.build_table(cgeom, calibs, grid)
+            with torch.no_grad():
+                res = vfa_b200.aggregate(dfeats, table, weights, biases, flags=args.flags)
+            host_out.copy_(res, non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * B * n_e2e / (float(te.item()) * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': sum(h.numel() * 4 for h in host_feats),
+               'd2h_bytes_per_step': host_out.numel() * 4, 'steps': n_e2e,
+               'note': 'pinned-host [B,V,C,fH,fW] fp32 features copied H2D, NCHW->channels-last transpose, table, weight '
+                       're-layout, fused kernel, full [B,C,L,W] result copied D2H, every step'}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        views = max(1, min(args.cpu_views, V))
+        cpu_port_time(geom, 1)                                   # warm-up (thread pool, allocator)
+        dt, _ = cpu_port_time(geom, views)
+        cpu_baseline = {'value': 1.0 / (dt * V / views), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                        'host_cpus': os.cpu_count(),
+                        'sample': f'{views} of {V} views x 3 scales of one {args.workload}-shaped frame ({dt:.2f} s), fp32 '
+                                  f'torch-CPU port of the reference operator sequence (oracle/ref_port.py), extrapolated '
+                                  f'x{V}/{views} to a frame'}
+
+    if rank == 0:
+        peaks = load_peaks()
+        tflops = nums['flops'] / (kern * 1e-3) / 1e12
+        gbs = nums['bytes'] / (kern * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            per_frame = tj.get(args.workload, {}).get(path)
+            if per_frame is not None:
+                traffic = per_frame * B
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32' if path == 'simt_fp32' else 'f32 (3xTF32 tcgen05 contraction, fp32 pooling and sums)',
+            'data': 'synthetic',
+            'config': {'workload': f'{args.workload}-shaped aggregation forward', 'batch_per_gpu': B, 'views': V,
+                       'channels': C, 'grid': list(grid.shape[:2]) + [len(zs)],
+                       'feature_maps': [list(s) for s in geom.feature_sizes()], 'layout': 'channels_last',
+                       'parallelism': f'dp{world}', 'kernel_path': path, 'table': 'rebuilt every step',
+                       'l2': f'inputs {nums["feat_bytes"] / 1e6:.0f} MB/step/GPU exceed the 126 MB L2'},
+            'clocks': clocks,
+            'e2e': e2e,
+            'gpu_launches': launches_per_step * args.steps,
+            'roofline': {
+                'bound': 'tensor', 'achieved': tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                'frac': tflops / peaks['tflops'], 'traffic': traffic,
+                'kernel': 'aggregate_fwd_umma_kernel' if path.startswith('umma') else 'aggregate_fwd_simt_kernel',
+                'kernel_ms': kern, 'kernel_share_of_step': kern * args.steps / total_ms,
+                'algorithmic_flops_per_launch': nums['flops'], 'algorithmic_bytes_per_launch': nums['bytes'],
+                'hbm_achieved_gbs': gbs, 'hbm_peak_gbs': peaks['hbm_gbs'], 'hbm_frac': gbs / peaks['hbm_gbs'],
+                'peak_source': peaks['source'],
+                'note': 'collapse contraction counted grid-side (2*L*W*K*C per view and scale, as the reference computes '
+                        'it); it runs as 3 TF32 tensor-core passes, so executed tensor flops are 3x the algorithmic '
+                        'count and the TF32 hardware peak is half the bf16 figure used as denominator',
+            },
+            'cpu_baseline': cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

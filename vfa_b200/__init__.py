@@ -7,8 +7,9 @@ entry.  All arithmetic runs in hand-written sm_100a CUDA kernels behind the C AB
 (libvfa_b200.so, loaded with ctypes); there is no CPU, Triton or PyTorch-op fallback.
 """
 from . import geometry, synthetic                                    # noqa: F401
-from ._lib import VFAError, FLAG_BF16_MMA, FLAG_FORCE_SIMT, FLAG_FORCE_UMMA   # noqa: F401
-from .vfa_op import (VFA, ProjectionTable, aggregate, build_table, last_kernel_path, make_geometry,  # noqa: F401
-                     to_channels_last)
+from ._lib import (VFAError, FLAG_BF16_MMA, FLAG_FORCE_SIMT, FLAG_FORCE_UMMA,   # noqa: F401
+                   FLAG_WEIGHTS_PREPARED)
+from .vfa_op import (VFA, ProjectionTable, aggregate, aggregate_forward_raw, build_table, last_kernel_path,  # noqa: F401
+                     make_geometry, make_shape, prepare_weights, to_channels_last, workspace_for)
 
 __version__ = '0.1.0'

@@ -20,7 +20,8 @@ import torch.nn.functional as F
 from . import _lib
 from .geometry import convert_descriptor
 
-__all__ = ['VFA', 'ProjectionTable', 'build_table', 'aggregate', 'to_channels_last', 'last_kernel_path']
+__all__ = ['VFA', 'ProjectionTable', 'build_table', 'aggregate', 'aggregate_forward_raw', 'prepare_weights',
+           'make_shape', 'to_channels_last', 'last_kernel_path']
 
 
 def _stream():
@@ -124,6 +125,56 @@ def to_channels_last(x: torch.Tensor) -> torch.Tensor:
         return perm
     x4 = x.reshape(-1, Cc, H, W).contiguous()
     return _ChannelsLast.apply(x4).reshape(*lead, H, W, Cc)
+
+
+def make_shape(feats_cl, n_layers: int) -> _lib.Shape:
+    """vfa_shape_t of a list of channels-last feature tensors [B,V,fH,fW,C]."""
+    B, V, _, _, Cc = feats_cl[0].shape
+    shape = _lib.Shape()
+    shape.batch, shape.n_views, shape.channels, shape.n_scales = B, V, Cc, len(feats_cl)
+    for s, f in enumerate(feats_cl):
+        if f.dim() != 5 or f.shape[0] != B or f.shape[1] != V or f.shape[4] != Cc:
+            raise ValueError('feature tensors disagree on batch / views / channels')
+        if f.dtype != torch.float32 or not f.is_contiguous():
+            raise ValueError('features must be contiguous float32 [B,V,fH,fW,C]')
+        shape.feat_h[s], shape.feat_w[s] = f.shape[2], f.shape[3]
+    return shape
+
+
+def workspace_for(geom, shape, flags, device) -> torch.Tensor:
+    n = _lib.lib().vfa_aggregate_workspace_bytes(C.byref(geom), C.byref(shape), int(flags))
+    return torch.empty(max(n, 256), dtype=torch.uint8, device=device)
+
+
+def prepare_weights(geom, shape, weights, flags=0, workspace=None) -> torch.Tensor:
+    """Re-lay the collapse weights for the kernel family `flags` selects; returns the workspace holding them
+    (pass it back to aggregate_forward_raw(..., prepared=True)).  Inference callers do this once."""
+    weights = [w.detach().contiguous() for w in weights]
+    dev = weights[0].device
+    ws = workspace if workspace is not None else workspace_for(geom, shape, flags, dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vfa_prepare_weights(C.byref(geom), C.byref(shape),
+                                                  _lib.ptr_array([w.data_ptr() for w in weights]), ws.data_ptr(),
+                                                  ws.numel(), int(flags), _stream()))
+    return ws
+
+
+def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, workspace=None, prepared=False):
+    """No-autograd forward on channels-last features [B,V,fH,fW,C]: one C-ABI call on the current stream."""
+    geom = table.geom
+    shape = make_shape(feats_cl, geom.n_layers)
+    dev = feats_cl[0].device
+    if out is None:
+        out = torch.empty(shape.batch, shape.channels, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
+    ws = workspace if workspace is not None else workspace_for(geom, shape, flags, dev)
+    f = int(flags) | (_lib.FLAG_WEIGHTS_PREPARED if prepared else 0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().vfa_aggregate_fwd(C.byref(geom), C.byref(shape), table.boxes.data_ptr(),
+                                                _lib.ptr_array([t.data_ptr() for t in feats_cl]),
+                                                _lib.ptr_array([t.data_ptr() for t in weights]),
+                                                _lib.ptr_array([t.data_ptr() for t in biases]),
+                                                out.data_ptr(), ws.data_ptr(), ws.numel(), f, _stream()))
+    return out
 
 
 class _AggregateFn(torch.autograd.Function):
