@@ -111,17 +111,21 @@ int vfa_prepare_weights(const vfa_geometry_t* geom, const vfa_shape_t* shape, co
  *   d_feats[s] [B, V, fH_s, fW_s, C] fp32 channels-last
  *   d_weight[s] [C, C*nl] fp32 with the reference's column order c*nl + n, d_bias[s] [C]   (vfa_op.py:59, :120)
  *   d_out     [B, C, L, W] fp32 (fully overwritten)
+ *   d_relu_mask  NULL, or [B, V, S, ceil(C/32), L*W] u32 (fully overwritten): bit (o % 32) of word o/32 is set iff
+ *             output channel o of that (frame, view, scale, cell) passed the ReLU -- what the backward needs
  * With batch = n_views = n_scales = 1 this is exactly one reference `VFA.forward`. */
 int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,
                       const float* const* d_feats, const float* const* d_weight, const float* const* d_bias,
-                      float* d_out, void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+                      float* d_out, uint32_t* d_relu_mask, void* d_workspace, size_t workspace_bytes, uint32_t flags,
+                      void* stream);
 
 /* Backward of vfa_aggregate_fwd (what autograd derives for reference vfa_op.py:110-124): given d_grad_out
  * [B,C,L,W] accumulates into d_grad_feats[s] [B,V,fH,fW,C] (must be zero-initialised by the caller),
  * d_grad_weight[s] [C, C*nl] and d_grad_bias[s] [C] (both fully overwritten).  Any gradient pointer array
- * entry may be NULL to skip it.  Recomputes the pooled voxels instead of saving them. */
+ * entry may be NULL to skip it.  Needs the ReLU mask the forward wrote; recomputes the pooled voxels instead of
+ * saving them (the reference keeps 0.6-1.8 GB of intermediates per call for autograd). */
 int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,
-                      const float* const* d_feats, const float* const* d_weight, const float* const* d_bias,
+                      const float* const* d_feats, const float* const* d_weight, const uint32_t* d_relu_mask,
                       const float* d_grad_out, float* const* d_grad_feats, float* const* d_grad_weight,
                       float* const* d_grad_bias, void* d_workspace, size_t workspace_bytes, uint32_t flags,
                       void* stream);

@@ -65,8 +65,8 @@ def lib():
     L.vfa_aggregate_workspace_bytes.restype = sz
     PP = C.POINTER(C.c_void_p)
     L.vfa_prepare_weights.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), PP, vp, sz, u32, vp]
-    L.vfa_aggregate_fwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, PP, fp, vp, sz, u32, vp]
-    L.vfa_aggregate_bwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, PP, fp, PP, PP, PP, vp, sz,
+    L.vfa_aggregate_fwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, PP, fp, vp, vp, sz, u32, vp]
+    L.vfa_aggregate_bwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, vp, fp, PP, PP, PP, vp, sz,
                                     u32, vp]
     for name in ('vfa_prepare_weights', 'vfa_table_build', 'vfa_table_scale', 'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_fwd',
                  'vfa_aggregate_bwd'):

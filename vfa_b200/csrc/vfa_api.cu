@@ -110,11 +110,12 @@ static int fill_params(const vfa_geometry_t* g, const vfa_shape_t* sh, const flo
     p.sc[s] = make_scale_const(2, 2);
   }
   for (int s = 0; s < sh->n_scales; ++s) {
-    VFA_REQUIRE(d_feats[s] != nullptr && d_bias[s] != nullptr, VFA_ERR_INVALID_ARGUMENT, "scale %d: NULL tensor", s);
+    VFA_REQUIRE(d_feats[s] != nullptr && (d_bias == nullptr || d_bias[s] != nullptr), VFA_ERR_INVALID_ARGUMENT,
+                "scale %d: NULL tensor", s);
     VFA_REQUIRE((reinterpret_cast<uintptr_t>(d_feats[s]) & 15) == 0, VFA_ERR_INVALID_ARGUMENT,
                 "scale %d: feature pointer not 16-byte aligned", s);
     p.feats[s] = d_feats[s];
-    p.bias[s] = d_bias[s];
+    p.bias[s] = d_bias ? d_bias[s] : nullptr;
     p.sc[s] = make_scale_const(sh->feat_h[s], sh->feat_w[s]);
   }
   return VFA_OK;
@@ -174,7 +175,8 @@ size_t vfa_aggregate_workspace_bytes(const vfa_geometry_t* geom, const vfa_shape
 
 int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,
                       const float* const* d_feats, const float* const* d_weight, const float* const* d_bias,
-                      float* d_out, void* d_workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+                      float* d_out, uint32_t* d_relu_mask, void* d_workspace, size_t workspace_bytes, uint32_t flags,
+                      void* stream) {
   if (int rc = validate_geometry(geom)) return rc;
   if (int rc = validate_shape(geom, shape)) return rc;
   VFA_REQUIRE(d_boxes && d_feats && d_weight && d_bias && d_out, VFA_ERR_INVALID_ARGUMENT, "NULL device pointer");
@@ -187,6 +189,7 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
   AggParams p;
   if (int rc = fill_params(geom, shape, d_boxes, d_feats, d_bias, p)) return rc;
   p.out = d_out;
+  p.mask = d_relu_mask;
   VFA_REQUIRE(d_workspace != nullptr && (reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, VFA_ERR_WORKSPACE,
               "workspace must be a 256-byte aligned device pointer");
   const bool use_umma = !(flags & VFA_FLAG_FORCE_SIMT) && umma_supported(geom, shape, flags);
@@ -226,21 +229,23 @@ int vfa_prepare_weights(const vfa_geometry_t* geom, const vfa_shape_t* shape, co
 }
 
 int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,
-                      const float* const* d_feats, const float* const* d_weight, const float* const* d_bias,
+                      const float* const* d_feats, const float* const* d_weight, const uint32_t* d_relu_mask,
                       const float* d_grad_out, float* const* d_grad_feats, float* const* d_grad_weight,
                       float* const* d_grad_bias, void* d_workspace, size_t workspace_bytes, uint32_t flags,
                       void* stream) {
   (void)flags;
   if (int rc = validate_geometry(geom)) return rc;
   if (int rc = validate_shape(geom, shape)) return rc;
-  VFA_REQUIRE(d_boxes && d_feats && d_weight && d_bias && d_grad_out, VFA_ERR_INVALID_ARGUMENT, "NULL device pointer");
+  VFA_REQUIRE(d_boxes && d_feats && d_weight && d_relu_mask && d_grad_out, VFA_ERR_INVALID_ARGUMENT,
+              "NULL device pointer");
   VFA_REQUIRE(d_grad_feats && d_grad_weight && d_grad_bias, VFA_ERR_INVALID_ARGUMENT, "NULL gradient pointer array");
   for (int s = 0; s < shape->n_scales; ++s)
     VFA_REQUIRE(d_weight[s] != nullptr, VFA_ERR_INVALID_ARGUMENT, "scale %d: NULL weight", s);
   if (int rc = check_device()) return rc;
   AggParams p;
-  if (int rc = fill_params(geom, shape, d_boxes, d_feats, d_bias, p)) return rc;
+  if (int rc = fill_params(geom, shape, d_boxes, d_feats, nullptr, p)) return rc;
   p.out = nullptr;
+  p.mask = const_cast<uint32_t*>(d_relu_mask);
   VFA_REQUIRE(d_workspace != nullptr && (reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, VFA_ERR_WORKSPACE,
               "workspace must be a 256-byte aligned device pointer");
   VFA_REQUIRE(workspace_bytes >= bwd_workspace_bytes(geom, shape), VFA_ERR_WORKSPACE, "workspace %zu < required %zu",

@@ -164,6 +164,7 @@ struct AggParams {
   const float* bias[VFA_MAX_SCALES];     // [C]
   const float* boxes;                    // [V, nl, LW, 4]
   float* out;                            // [B, C, L, W]
+  uint32_t* mask;                        // nullptr or [B, V, S, ceil(C/32), LW]: ReLU pass bits (word o/32, bit o%32)
 };
 
 }  // namespace vfa

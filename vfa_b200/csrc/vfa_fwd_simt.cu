@@ -124,7 +124,17 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_simt_kernel(AggParam
           const int o = ob + og + 32 * j;
           const float bs = o < p.C ? __ldg(p.bias[s] + o) : 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bev[i][j] += fmaxf(acc[i][j] + bs, 0.f);
+          for (int i = 0; i < 8; ++i) {
+            const float y = acc[i][j] + bs;
+            bev[i][j] += fmaxf(y, 0.f);
+            if (p.mask != nullptr) {      // lanes = 32 consecutive output channels of word (ob/32 + j)
+              const unsigned bits = __ballot_sync(0xffffffffu, o < p.C && y > 0.f);
+              const int cell = cell0 + cg * 8 + i;
+              const int word = ob / 32 + j;
+              if (lane == 0 && cell < p.LW && word * 32 < p.C)
+                p.mask[((((size_t)b * p.V + v) * p.S + s) * ((p.C + 31) / 32) + word) * p.LW + cell] = bits;
+            }
+          }
         }
       }
     }

@@ -638,6 +638,13 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
             tc_ld32(lane_addr + CH + c0, y);
             tc_wait_ld();
             if (cell < p.LW) {
+              if (p.mask != nullptr) {      // ReLU pass bits of channels c0 .. c0+31 for the backward
+                uint32_t bits = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) bits |= (y[i] + tail->bias[s][c0 + i] > 0.f ? 1u : 0u) << i;
+                const int v_cur = v_begin + vs / p.S;
+                p.mask[((((size_t)b * p.V + v_cur) * p.S + s) * (CH / 32) + c0 / 32) * p.LW + cell] = bits;
+              }
               if (a.n_groups == 1 && vs == 0) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) outp[(size_t)(c0 + i) * p.LW] = fmaxf(y[i] + tail->bias[s][c0 + i], 0.f);

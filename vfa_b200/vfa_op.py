@@ -159,8 +159,10 @@ def prepare_weights(geom, shape, weights, flags=0, workspace=None) -> torch.Tens
     return ws
 
 
-def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, workspace=None, prepared=False):
-    """No-autograd forward on channels-last features [B,V,fH,fW,C]: one C-ABI call on the current stream."""
+def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, workspace=None, prepared=False,
+                          relu_mask=None):
+    """No-autograd forward on channels-last features [B,V,fH,fW,C]: one C-ABI call on the current stream.
+    relu_mask: optional int32 tensor [B,V,S,ceil(C/32),L*W] receiving the ReLU pass bits for the backward."""
     geom = table.geom
     shape = make_shape(feats_cl, geom.n_layers)
     dev = feats_cl[0].device
@@ -173,7 +175,8 @@ def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, w
                                                 _lib.ptr_array([t.data_ptr() for t in feats_cl]),
                                                 _lib.ptr_array([t.data_ptr() for t in weights]),
                                                 _lib.ptr_array([t.data_ptr() for t in biases]),
-                                                out.data_ptr(), ws.data_ptr(), ws.numel(), f, _stream()))
+                                                out.data_ptr(), relu_mask.data_ptr() if relu_mask is not None else None,
+                                                ws.data_ptr(), ws.numel(), f, _stream()))
     return out
 
 
@@ -186,38 +189,30 @@ class _AggregateFn(torch.autograd.Function):
         feats = [t.contiguous() for t in tensors[:S]]
         weights = [t.contiguous() for t in tensors[S:2 * S]]
         biases = [t.contiguous() for t in tensors[2 * S:3 * S]]
-        B, V, _, _, Cc = feats[0].shape
-        shape = _lib.Shape()
-        shape.batch, shape.n_views, shape.channels, shape.n_scales = B, V, Cc, S
+        shape = make_shape(feats, geom.n_layers)
+        B, V, Cc = shape.batch, shape.n_views, shape.channels
         for s in range(S):
-            if feats[s].shape[0] != B or feats[s].shape[1] != V or feats[s].shape[4] != Cc:
-                raise ValueError('feature tensors disagree on batch / views / channels')
-            shape.feat_h[s], shape.feat_w[s] = feats[s].shape[2], feats[s].shape[3]
             if tuple(weights[s].shape) != (Cc, Cc * geom.n_layers) or tuple(biases[s].shape) != (Cc,):
                 raise ValueError(f'collapse parameters of scale {s} have shapes {tuple(weights[s].shape)}, '
                                  f'{tuple(biases[s].shape)}; expected ({Cc}, {Cc * geom.n_layers}) and ({Cc},)')
         if boxes.shape[0] != V:
             raise ValueError(f'table holds {boxes.shape[0]} views, features hold {V}')
         dev = feats[0].device
-        L = _lib.lib()
-        out = torch.empty(B, Cc, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
-        ws_bytes = L.vfa_aggregate_workspace_bytes(C.byref(geom), C.byref(shape), flags)
-        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(L.vfa_aggregate_fwd(C.byref(geom), C.byref(shape), boxes.data_ptr(),
-                                           _lib.ptr_array([t.data_ptr() for t in feats]),
-                                           _lib.ptr_array([t.data_ptr() for t in weights]),
-                                           _lib.ptr_array([t.data_ptr() for t in biases]),
-                                           out.data_ptr(), ws.data_ptr(), ws.numel(), flags, _stream()))
+        need_grad = any(ctx.needs_input_grad[4:])
+        mask = None
+        if need_grad:
+            mask = torch.empty(B, V, S, (Cc + 31) // 32, geom.grid_l * geom.grid_w, dtype=torch.int32, device=dev)
+        out = aggregate_forward_raw(feats, ProjectionTable(geom, boxes), weights, biases, flags, relu_mask=mask)
         ctx.geom, ctx.shape, ctx.flags, ctx.S = geom, shape, flags, S
-        ctx.save_for_backward(boxes, *feats, *weights, *biases)
+        if need_grad:
+            ctx.save_for_backward(boxes, mask, *feats, *weights)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         S = ctx.S
         saved = ctx.saved_tensors
-        boxes, feats, weights, biases = saved[0], saved[1:1 + S], saved[1 + S:1 + 2 * S], saved[1 + 2 * S:1 + 3 * S]
+        boxes, mask, feats, weights = saved[0], saved[1], saved[2:2 + S], saved[2 + S:2 + 2 * S]
         grad_out = grad_out.contiguous()
         dev = grad_out.device
         L = _lib.lib()
@@ -225,16 +220,16 @@ class _AggregateFn(torch.autograd.Function):
         need_w = [ctx.needs_input_grad[4 + S + s] for s in range(S)]
         need_b = [ctx.needs_input_grad[4 + 2 * S + s] for s in range(S)]
         gf = [torch.zeros_like(feats[s]) if need_f[s] else None for s in range(S)]
-        gw = [torch.empty_like(weights[s]) if (need_w[s] or need_b[s]) else None for s in range(S)]
-        gb = [torch.empty_like(biases[s]) if (need_w[s] or need_b[s]) else None for s in range(S)]
-        ws_bytes = L.vfa_aggregate_workspace_bytes(C.byref(ctx.geom), C.byref(ctx.shape), ctx.flags)
-        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        want_wb = [need_w[s] or need_b[s] for s in range(S)]
+        gw = [torch.empty_like(weights[s]) if want_wb[s] else None for s in range(S)]
+        gb = [torch.empty(weights[s].shape[0], dtype=torch.float32, device=dev) if want_wb[s] else None
+              for s in range(S)]
+        ws = workspace_for(ctx.geom, ctx.shape, ctx.flags, dev)
         with torch.cuda.device(dev):
             _lib.check(L.vfa_aggregate_bwd(C.byref(ctx.geom), C.byref(ctx.shape), boxes.data_ptr(),
                                            _lib.ptr_array([t.data_ptr() for t in feats]),
                                            _lib.ptr_array([t.data_ptr() for t in weights]),
-                                           _lib.ptr_array([t.data_ptr() for t in biases]),
-                                           grad_out.data_ptr(),
+                                           mask.data_ptr(), grad_out.data_ptr(),
                                            _lib.ptr_array([t.data_ptr() if t is not None else None for t in gf]),
                                            _lib.ptr_array([t.data_ptr() if t is not None else None for t in gw]),
                                            _lib.ptr_array([t.data_ptr() if t is not None else None for t in gb]),
