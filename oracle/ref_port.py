@@ -74,6 +74,16 @@ def pooled_voxels(feature, boxes):
     return vox.permute(0, 3, 1, 2).flatten(0, 1).flatten(1, 2)
 
 
+def preactivation(feature, calib, grid, weight, bias, grid_height, cube_size, dataset, image_size,
+                  crange=(-1.0, 0.95), boxes=None):
+    """The linear part of one (view, scale), before the ReLU of reference vfa_op.py:124: [1, C, L, W]."""
+    L, W = grid.shape[-3], grid.shape[-2]
+    if boxes is None:
+        boxes = boxes_fp32(calib, grid, grid_height, cube_size, dataset, image_size, crange)
+    vox = pooled_voxels(feature, boxes)
+    return F.linear(vox, weight, bias).view(1, L, W, -1).permute(0, 3, 1, 2)
+
+
 def vfa_forward(feature, calib, grid, weight, bias, grid_height, cube_size, dataset, image_size,
                 crange=(-1.0, 0.95), boxes=None):
     """One (view, scale): -> [1, C, L, W] in feature.dtype.  With feature/weight/bias in float64 this is the

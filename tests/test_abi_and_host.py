@@ -1,0 +1,103 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/vfa_b200.h declares (no compute calls
+without a GPU), ctypes structs match the header layout, and the host mirror fails loudly off-GPU."""
+import ctypes
+import os
+import re
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import vfa_b200
+from vfa_b200 import _lib, geometry, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header():
+    with open(os.path.join(ROOT, 'include', 'vfa_b200.h')) as f:
+        return f.read()
+
+
+def test_library_exports_every_declared_symbol():
+    declared = set(re.findall(r'^(?:int|size_t|const char\*)\s+(vfa_\w+)\s*\(', _header(), flags=re.M))
+    assert declared, 'no prototypes found in include/vfa_b200.h'
+    L = _lib.lib()
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, f'libvfa_b200.so does not export {missing}'
+    assert declared == set(_lib.EXPORTS), 'vfa_b200/_lib.py EXPORTS is out of sync with the header'
+    assert L.vfa_version() == int(re.search(r'#define VFA_ABI_VERSION (\d+)', _header()).group(1))
+
+
+def test_struct_layouts_match_header():
+    # vfa_geometry_t: 4 int32 + 1 float + 3 + 3 + 16 floats + 4 floats ; vfa_shape_t: 4 + 3 + 3 int32
+    assert ctypes.sizeof(_lib.Geometry) == 4 * 4 + 4 * (1 + 3 + 3 + 16 + 4)
+    assert ctypes.sizeof(_lib.Shape) == 4 * 10
+    h = _header()
+    assert int(re.search(r'#define VFA_MAX_LAYERS (\d+)', h).group(1)) == _lib.VFA_MAX_LAYERS
+    assert int(re.search(r'#define VFA_MAX_SCALES (\d+)', h).group(1)) == _lib.VFA_MAX_SCALES
+    for name, val in (('FORCE_SIMT', _lib.FLAG_FORCE_SIMT), ('FORCE_UMMA', _lib.FLAG_FORCE_UMMA),
+                      ('BF16_MMA', _lib.FLAG_BF16_MMA), ('WEIGHTS_PREPARED', _lib.FLAG_WEIGHTS_PREPARED)):
+        assert int(re.search(rf'#define VFA_FLAG_{name}\s+(\d+)u', h).group(1)) == val
+
+
+def test_argument_validation_needs_no_gpu():
+    """Invalid arguments are rejected before any CUDA call, with a message."""
+    L = _lib.lib()
+    g = vfa_b200.make_geometry(5, (25, 25, 32), [0, 32, 64, 96, 128], (156, 156), 'MultiviewC', (720, 1280))
+    assert L.vfa_table_build(ctypes.byref(g), 0, None, None, None, None) == -1
+    assert b'n_views' in L.vfa_last_error()
+    g.n_layers = 99
+    assert L.vfa_table_build(ctypes.byref(g), 1, None, None, None, None) == -1
+    assert b'n_layers' in L.vfa_last_error()
+    assert L.vfa_table_scale(None, 10, 90, 160, None, None, None, None) == -1
+    if not torch.cuda.is_available():
+        # with valid arguments and no device the library reports NO_DEVICE instead of computing anything
+        g.n_layers = 5
+        buf = (ctypes.c_float * 64)()
+        rc = L.vfa_table_build(ctypes.byref(g), 1, ctypes.addressof(buf), ctypes.addressof(buf), ctypes.addressof(buf), None)
+        assert rc == -5 and b'no CPU fallback' in L.vfa_last_error() or rc == -5
+
+
+def test_module_mirrors_reference_interface():
+    g = geometry.MULTIVIEWC
+    args = SimpleNamespace(data=g.name, image_size=g.image_size)
+    m = vfa_b200.VFA(256, g.grid_height, np.array(g.cube_size), 1 / 8., args)
+    sd = m.state_dict()
+    assert list(sd) == ['z_corners', 'corners_offset', 'collapse.weight', 'collapse.bias']
+    assert sd['z_corners'].dtype == torch.int64 and sd['z_corners'][:, 0, 0, 2].tolist() == [0, 32, 64, 96, 128]
+    assert tuple(sd['corners_offset'].shape) == (1, 1, 1, 1, 8, 3)
+    assert sd['corners_offset'][0, 0, 0, 0, 0].tolist() == [-12.5, -12.5, 0.0]
+    assert sd['corners_offset'][0, 0, 0, 0, 6].tolist() == [12.5, 12.5, 32.0]
+    assert [n for n, _ in m.named_parameters()] == ['collapse.weight', 'collapse.bias']
+    # no CPU path: loud failure instead of a silent fallback
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m(torch.zeros(1, 256, 90, 160), torch.zeros(3, 4), geometry.grid_for(g)[None])
+    with pytest.raises(ValueError, match='unknown dataset'):
+        vfa_b200.VFA(8, 160, (25, 25, 32), 1, SimpleNamespace(data='KITTI', image_size=(1, 1))).geometry((4, 4))
+
+
+def test_geometries_match_configs_of_record():
+    assert geometry.MULTIVIEWC.grid_shape == (156, 156) and geometry.MULTIVIEWC.n_layers == 5
+    assert geometry.MULTIVIEWX.grid_shape == (160, 250) and geometry.MULTIVIEWX.n_layers == 8
+    assert geometry.WILDTRACK.grid_shape == (120, 360) and geometry.WILDTRACK.n_layers == 8
+    for g in geometry.GEOMETRIES.values():
+        assert g.feature_sizes() == [(90, 160), (45, 80), (23, 40)]
+        assert tuple(geometry.grid_for(g).shape) == g.grid_shape + (3,)
+    # Wildtrack grid has its axes swapped (reference utils.py:24-25, :33-34)
+    wt = geometry.grid_for(geometry.WILDTRACK)
+    assert wt[1, 0].tolist() == [4.0, 0.0, 0.0] and wt[0, 1].tolist() == [0.0, 4.0, 0.0]
+    mc = geometry.grid_for(geometry.MULTIVIEWC)
+    assert mc[0, 1].tolist() == [25.0, 0.0, 0.0] and mc[1, 0].tolist() == [0.0, 25.0, 0.0]
+
+
+def test_synthetic_inputs_are_deterministic():
+    g = geometry.MULTIVIEWC
+    a, b = synthetic.ring_calibs(g), synthetic.ring_calibs(g)
+    assert torch.equal(a, b) and a.shape == (7, 3, 4) and a.dtype == torch.float32
+    f1 = synthetic.features(g, channels=4, seed=3)
+    f2 = synthetic.features(g, channels=4, seed=3)
+    assert all(torch.equal(x, y) for x, y in zip(f1, f2)) and float(f1[0].min()) >= 0.0
+    p = synthetic.collapse_params(g, channels=4)
+    assert p[0][0].shape == (4, 20) and p[0][1].shape == (4,)
