@@ -44,6 +44,10 @@ def parse():
     ap.add_argument('--flags', type=int, default=0, help='vfa_aggregate_fwd flags (1 = force SIMT path)')
     ap.add_argument('--cpu-views', type=int, default=2, help='views of one frame timed for cpu_baseline')
     ap.add_argument('--ref-views', type=int, default=1, help='views of one frame per step of --impl reference')
+    ap.add_argument('--mode', choices=['dp', 'slab'], default='dp',
+                    help='dp: frames sharded over GPUs, no data-path collective (weak scaling, default); slab: BEV row '
+                         'slabs over GPUs, features broadcast from rank 0 + output all-gather per step (strong scaling)')
+    ap.add_argument('--backward', action='store_true', help='time forward + backward (BASELINE config 4)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -194,8 +198,42 @@ def main():
     nums = workload_numbers(geom, B)
 
     kernel_ms = []
+    from vfa_b200 import distributed as vd
+    zs_geom = lambda lw: vfa_b200.make_geometry(len(zs), geom.cube_size, zs, lw, geom.name, geom.image_size)  # noqa: E731
+    if args.backward:
+        for t in feats_cl + weights + biases:
+            t.requires_grad_(True)
+        gout = torch.randn(out.shape, generator=gen, device=dev)
+    slab_compute = None
+    if args.mode == 'slab':
+        def slab_compute(f, c, grid_slab, w, b_):
+            table = vfa_b200.build_table(zs_geom(grid_slab.shape[:2]), c, grid_slab)
+            if args.backward:
+                return vfa_b200.aggregate(f, table, w, b_, flags=args.flags, channels_last=True)
+            return vfa_b200.aggregate_forward_raw(f, table, w, b_, args.flags)
+
+    def step_general(timed_events=None):
+        """slab mode and/or backward: through the autograd-capable public entry points."""
+        if timed_events is not None:
+            timed_events[0].record()
+        if args.mode == 'slab':
+            vd.broadcast_features([f.detach() for f in feats_cl], src=0)
+            res = vd.aggregate_slab(feats_cl, calibs, grid, weights, biases, slab_compute)
+        else:
+            table = vfa_b200.build_table(cgeom, calibs, grid)
+            res = vfa_b200.aggregate(feats_cl, table, weights, biases, flags=args.flags, channels_last=True)
+        if args.backward:
+            for t in feats_cl + weights + biases:
+                t.grad = None
+            res.backward(gout)
+            if world > 1 and args.mode == 'dp':
+                vd.allreduce_collapse_grads(weights + biases)
+        if timed_events is not None:
+            timed_events[1].record()
 
     def step(timed_events=None):
+        if args.mode == 'slab' or args.backward:
+            return step_general(timed_events)
         table = vfa_b200.build_table(cgeom, calibs, grid)                           # 1 launch
         vfa_b200.prepare_weights(cgeom, shape, weights, args.flags, workspace=ws)    # 3 launches
         if timed_events is not None:
@@ -233,12 +271,13 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * B * args.steps / (total_ms * 1e-3)
+    frames_per_step = B if args.mode == 'slab' else world * B
+    value = frames_per_step * args.steps / (total_ms * 1e-3)
     kern = sum(kernel_ms) / len(kernel_ms)
 
     # ---- end to end through the public API: pinned host NCHW features -> device -> aggregate -> host ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.mode == 'dp' and not args.backward:
         host_feats = [f.permute(0, 1, 4, 2, 3).contiguous().cpu().pin_memory() for f in feats_cl]   # [B,V,C,fH,fW]
         host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
 
@@ -281,7 +320,8 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        tflops = nums['flops'] / (kern * 1e-3) / 1e12
+        work_scale = (3.0 if args.backward else 1.0) / (world if args.mode == 'slab' else 1)
+        tflops = nums['flops'] * work_scale / (kern * 1e-3) / 1e12
         gbs = nums['bytes'] / (kern * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -293,13 +333,14 @@ def main():
                 traffic = per_frame * B
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'strong' if args.mode == 'slab' else 'weak', 'vs_baseline': None,
             'dtype': 'f32' if path == 'simt_fp32' else 'f32 (3xTF32 tcgen05 contraction, fp32 pooling and sums)',
             'data': 'synthetic',
-            'config': {'workload': f'{args.workload}-shaped aggregation forward', 'batch_per_gpu': B, 'views': V,
-                       'channels': C, 'grid': list(grid.shape[:2]) + [len(zs)],
+            'config': {'workload': f'{args.workload}-shaped aggregation forward' + ('+backward' if args.backward else ''),
+                       'batch_per_gpu': B, 'views': V, 'channels': C, 'grid': list(grid.shape[:2]) + [len(zs)],
                        'feature_maps': [list(s) for s in geom.feature_sizes()], 'layout': 'channels_last',
-                       'parallelism': f'dp{world}', 'kernel_path': path, 'table': 'rebuilt every step',
+                       'parallelism': f'{args.mode}{world}', 'kernel_path': path, 'table': 'rebuilt every step',
                        'l2': f'inputs {nums["feat_bytes"] / 1e6:.0f} MB/step/GPU exceed the 126 MB L2'},
             'clocks': clocks,
             'e2e': e2e,

@@ -109,7 +109,7 @@ def aggregate(feats, calibs, grid, params, grid_height, cube_size, dataset, imag
         ortho = 0
         for v in range(V):
             per_view = 0
-            for s in range(3):
+            for s in range(len(feats)):
                 per_view = per_view + vfa_forward(feats[s][b, v], calibs[v], grid, params[s][0], params[s][1],
                                                   grid_height, cube_size, dataset, image_size, boxes=boxes[v])
             ortho = ortho + per_view

@@ -1,0 +1,66 @@
+"""Two-GPU checks (skipped on a 1-GPU box): BEV row-slab sharding over NCCL reproduces the single-GPU result and
+gradients; data-parallel ranks reduce the collapse gradients."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, results):
+    import torch.distributed as dist
+    import vfa_b200
+    from vfa_b200 import distributed as vd
+    from vfa_b200 import geometry, synthetic
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        g = geometry.MULTIVIEWC
+        zs = list(range(0, g.grid_height, g.cube_size[2]))
+        geom_of = lambda lw: vfa_b200.make_geometry(len(zs), g.cube_size, zs, lw, g.name, g.image_size)  # noqa: E731
+        grid = geometry.grid_for(g).to(dev)
+        calibs = synthetic.ring_calibs(g, n_views=3).to(dev)
+        feats = [f.to(dev) for f in synthetic.features(g, batch=2, n_views=3, seed=13)]
+        if rank != 0:
+            feats = [torch.zeros_like(f) for f in feats]
+        vd.broadcast_features(feats, src=0)
+        params = synthetic.collapse_params(g, seed=13)
+        ws = [w.to(dev).requires_grad_(True) for w, _ in params]
+        bs = [b.to(dev).requires_grad_(True) for _, b in params]
+        feats = [f.requires_grad_(True) for f in feats]
+        full = vd.aggregate_slab(feats, calibs, grid, ws, bs, vd.cuda_compute(geom_of))
+        gout = torch.randn(full.shape, generator=torch.Generator(device=dev).manual_seed(1), device=dev)
+        full.backward(gout)
+        # single-GPU truth on every rank
+        f2 = [f.detach().clone().requires_grad_(True) for f in feats]
+        w2 = [w.detach().clone().requires_grad_(True) for w in ws]
+        b2 = [b.detach().clone().requires_grad_(True) for b in bs]
+        table = vfa_b200.build_table(geom_of(grid.shape[:2]), calibs, grid)
+        want = vfa_b200.aggregate(f2, table, w2, b2)
+        want.backward(gout)
+        ok = torch.allclose(full, want, rtol=1e-5, atol=1e-5)
+        for a, b in zip(feats + ws + bs, f2 + w2 + b2):
+            scale = float(b.grad.abs().max()) + 1e-30
+            ok = ok and float((a.grad - b.grad).abs().max()) / scale < 1e-4
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_slab_sharding_two_gpus_matches_single_gpu():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}

@@ -1,0 +1,127 @@
+"""Multi-GPU execution of the aggregation path on one NVLink/NVSwitch box.
+
+The reference is single-GPU, batch-1 (reference train.py:57-59, :245-246); both modes here are new functionality:
+
+* batch data parallel -- frames are independent, every rank aggregates its own frames with no forward collective;
+  `allreduce_collapse_grads` sums dWeight / dBias over ranks after the backward (the only exchange).
+* BEV row-slab sharding -- rank g owns rows [r0, r1) of the L x W ground grid for all views and scales: it builds
+  the projection table of its slab only, aggregates it, and the slabs are all-gathered (NCCL over NVLink) into
+  the full [B, C, L, W] map.  View features must be present on every rank (`broadcast_features`, or replicated
+  backbones); in the backward each slab yields a partial dFeature over the whole image, summed by all-reduce.
+
+One process per GPU, `torch.distributed` (backend "nccl") for the plumbing.  The functions take the per-rank
+compute as a callable so the partition / collective logic is testable on CPU ranks (gloo) with the oracle.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(n_rows: int, world: int, rank: int):
+    """Rows [r0, r1) of rank `rank`: as even as possible, the first n_rows % world ranks hold one extra row."""
+    base, extra = divmod(n_rows, world)
+    r0 = rank * base + min(rank, extra)
+    return r0, r0 + base + (1 if rank < extra else 0)
+
+
+class _GatherSlabs(torch.autograd.Function):
+    """local [B, C, rows_g, W] -> full [B, C, L, W]; backward hands every rank its own rows of the gradient."""
+
+    @staticmethod
+    def forward(ctx, local, n_rows, group):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B, C, rows, W = local.shape
+        r0, r1 = slab_bounds(n_rows, world, rank)
+        assert rows == r1 - r0, f'rank {rank} holds {rows} rows, plan says {r1 - r0}'
+        max_rows = slab_bounds(n_rows, world, 0)[1]
+        # equal-sized NCCL messages: pad the (at most one row) shorter slabs
+        send = local.new_zeros(B, C, max_rows, W)
+        send[:, :, :rows] = local
+        recv = local.new_empty(world * B, C, max_rows, W)          # concatenated along dim 0 (gloo and nccl agree)
+        dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+        recv = recv.view(world, B, C, max_rows, W)
+        full = local.new_empty(B, C, n_rows, W)
+        for g in range(world):
+            a, b = slab_bounds(n_rows, world, g)
+            full[:, :, a:b] = recv[g, :, :, :b - a]
+        ctx.bounds = (r0, r1)
+        return full
+
+    @staticmethod
+    def backward(ctx, grad_full):
+        r0, r1 = ctx.bounds
+        return grad_full[:, :, r0:r1].contiguous(), None, None
+
+
+class _ReplicatedInput(torch.autograd.Function):
+    """Identity on a tensor that is replicated on every rank; backward sums the per-rank partial gradients."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def broadcast_features(feats, src: int = 0, group=None):
+    """In-place broadcast of the view features from rank `src` (one NCCL broadcast per scale)."""
+    for f in feats:
+        dist.broadcast(f, src=src, group=group)
+    return feats
+
+
+def aggregate_slab(feats, calibs, grid, weights, biases, compute, group=None, replicated_grads: bool = True):
+    """BEV row-slab sharded aggregation.
+
+    feats / weights / biases  replicated on every rank (see broadcast_features); calibs [V,3,4]; grid [L,W,3]
+    compute(feats, calibs, grid_slab, weights, biases) -> [B, C, rows, W]   the single-GPU aggregation of a grid slab
+    returns the full [B, C, L, W] on every rank.  With replicated_grads=True gradients w.r.t. feats / weights /
+    biases are all-reduced so every rank ends up with the gradient of the full map.
+    """
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    L = grid.shape[-3]
+    r0, r1 = slab_bounds(L, world, rank)
+    if replicated_grads:
+        feats = [_ReplicatedInput.apply(f, group) if f.requires_grad else f for f in feats]
+        weights = [_ReplicatedInput.apply(w, group) if w.requires_grad else w for w in weights]
+        biases = [_ReplicatedInput.apply(b, group) if b.requires_grad else b for b in biases]
+    grid_slab = grid.reshape(L, grid.shape[-2], 3)[r0:r1].contiguous()
+    local = compute(feats, calibs, grid_slab, weights, biases)
+    return _GatherSlabs.apply(local, L, group)
+
+
+def shard_frames(n_frames: int, world: int, rank: int):
+    """Frames [f0, f1) of rank `rank` for batch data parallelism (same even split as slab_bounds)."""
+    return slab_bounds(n_frames, world, rank)
+
+
+def allreduce_collapse_grads(params, group=None, average: bool = False):
+    """Sum (or average) .grad of the collapse parameters over the data-parallel ranks in one flat all-reduce."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def cuda_compute(geom_of, flags: int = 0):
+    """The default `compute` of aggregate_slab: table + fused kernels of this repo for a grid slab.
+    geom_of(grid_lw) -> vfa_geometry_t for a slab of that many rows (see vfa_b200.make_geometry)."""
+    from . import vfa_op
+
+    def compute(feats, calibs, grid_slab, weights, biases):
+        table = vfa_op.build_table(geom_of(grid_slab.shape[:2]), calibs, grid_slab)
+        return vfa_op.aggregate(feats, table, weights, biases, flags=flags)
+    return compute
