@@ -34,21 +34,35 @@ constexpr int STAGES = 2;
 constexpr int A_BYTES = TILE_M * KCH * 4;          // 16 KB per hi / lo tile
 constexpr int B_BYTES = CH * KCH * 4;              // 32 KB per hi / lo slab
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
-constexpr int NUM_PRODUCER_WARPS = 8;
+#ifndef VFA_PRODUCER_WARPS
+#define VFA_PRODUCER_WARPS 8
+#endif
+constexpr int NUM_PRODUCER_WARPS = VFA_PRODUCER_WARPS;   // 8 (deep per-warp prefetch) or 16 (more warps, shallower)
+constexpr int ROUNDS = TILE_M / (4 * NUM_PRODUCER_WARPS);  // items (4 cells each) per producer warp and K chunk
+constexpr int ROWS_PER_WARP = 4 * ROUNDS;
 constexpr int FIRST_PRODUCER_WARP = 4;     // warpgroup 0 = {loader, MMA, 2 idle warps} gives its registers away
-constexpr int FIRST_EPILOGUE_WARP = 12;
+constexpr int FIRST_EPILOGUE_WARP = FIRST_PRODUCER_WARP + NUM_PRODUCER_WARPS;
 constexpr int NUM_EPILOGUE_WARPS = 8;
-constexpr int THREADS = 20 * 32;
+constexpr int THREADS = (FIRST_EPILOGUE_WARP + NUM_EPILOGUE_WARPS) * 32;
+// register redistribution (setmaxnreg): {warpgroup 0, producers, epilogue}; 0 = leave at the launch value
+constexpr int REGS_WG0 = NUM_PRODUCER_WARPS == 8 ? 32 : 24;
+constexpr int REGS_PRODUCER = NUM_PRODUCER_WARPS == 8 ? 128 : 0;
+constexpr int REGS_EPILOGUE = NUM_PRODUCER_WARPS == 8 ? 0 : 96;
+constexpr int DEPTH_2X2 = NUM_PRODUCER_WARPS == 8 ? 4 : 2;
+constexpr int DEPTH_3X3 = NUM_PRODUCER_WARPS == 8 ? 2 : 1;
+constexpr bool WINDOW_DOUBLE_BUFFER = NUM_PRODUCER_WARPS == 8;
 constexpr int TMEM_COLS = 512;
 
 // Gather recipe of one (cell, layer) row at one scale, prepared once per (view, scale, layer) in shared memory:
 // element offset of the first texel, tap counts and the separable edge weights (1/area and visibility folded
-// into the row weights; interior taps weigh 1 resp. wy_mid), plus the nine products of a <= 3x3 box.  80 bytes.
+// into the row weights; interior taps weigh 1 resp. wy_mid), plus the nine products of a <= 3x3 box and the first 8 weights per axis.  144 bytes.
 struct __align__(16) RowDesc {
   int base;        // ((y0 * fw) + x0) * CH
   int nx, ny;      // tap counts (0 = not visible)
   float wx_first, wx_last, wy_first, wy_last, wy_mid;
   float w9[12];    // wy(ty) * wx(tx) at [ty*3+tx], ty,tx in {0,1,2} (0 = tap not used); last 3 are padding
+  float wx8[8];    // wx(0..7), wy(0..7) (0 beyond the box): window weights without the select chain for boxes up to
+  float wy8[8];    // 8x8 taps; larger boxes fall back to desc_wx / desc_wy
 };
 __device__ __forceinline__ float desc_wx(const RowDesc& d, int i) {
   return i >= d.nx ? 0.f : (i == 0 ? d.wx_first : (i == d.nx - 1 ? d.wx_last : 1.0f));
@@ -58,7 +72,7 @@ __device__ __forceinline__ float desc_wy(const RowDesc& d, int i) {
 }
 
 struct __align__(16) SmemTail {
-  RowDesc desc[NUM_PRODUCER_WARPS][16];
+  RowDesc desc[NUM_PRODUCER_WARPS][ROWS_PER_WARP];
   float bias[VFA_MAX_SCALES][CH];
   unsigned long long full[STAGES];
   unsigned long long empty[STAGES];
@@ -228,7 +242,7 @@ struct UmmaArgs {
 // ---- pooling producers ----------------------------------------------------------------------------------------
 // One work item = 4 cells (one per quarter-warp) x 32 channels of one K chunk; 8 lanes x float4 read one 128-byte
 // row of a texel, so every load instruction moves 4 full cache lines.  A producer warp owns the tile rows
-// 32*round + 4*pw + {0,1,2,3}, round = 0..3: the 4 cells of one instruction are adjacent (their boxes overlap, so
+// (128/ROUNDS)*round + 4*pw + {0,1,2,3}: the 4 cells of one instruction are adjacent (their boxes overlap, so
 // their loads coalesce / hit L1) while the rounds are spread over the tile (box sizes vary smoothly along a BEV
 // row, so every warp gets the same mix of cheap and expensive rows).  Loads are predicated on the tap weight (taps with weight 0 are never
 // fetched) and issued ahead of their use so several items / windows are in flight per warp.
@@ -247,10 +261,10 @@ __device__ __forceinline__ void ldg_if(float4& v, const float* ptr, float w) {
 }
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   if (w != 0.f) {        // predicated, so a stale Inf/NaN left in an unused slot can never leak in
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+    const float2 w2 = make_float2(w, w);          // packed fp32x2 FMA (sm_100): 2 instead of 4 issue slots
+    const float2 lo = __ffma2_rn(w2, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(w2, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
   }
 }
 
@@ -261,10 +275,13 @@ __device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const f
   hi.y = to_tf32(acc.y);
   hi.z = to_tf32(acc.z);
   hi.w = to_tf32(acc.w);
-  lo.x = to_tf32(acc.x - __uint_as_float(hi.x));
-  lo.y = to_tf32(acc.y - __uint_as_float(hi.y));
-  lo.z = to_tf32(acc.z - __uint_as_float(hi.z));
-  lo.w = to_tf32(acc.w - __uint_as_float(hi.w));
+  // lo = a - hi is exact in fp32; the tensor core reads its top 19 bits (truncation error 2^-11 of lo = 2^-22 of a)
+  const float2 l01 = __fadd2_rn(make_float2(acc.x, acc.y), make_float2(-__uint_as_float(hi.x), -__uint_as_float(hi.y)));
+  const float2 l23 = __fadd2_rn(make_float2(acc.z, acc.w), make_float2(-__uint_as_float(hi.z), -__uint_as_float(hi.w)));
+  lo.x = __float_as_uint(l01.x);
+  lo.y = __float_as_uint(l01.y);
+  lo.z = __float_as_uint(l23.x);
+  lo.w = __float_as_uint(l23.y);
   *reinterpret_cast<uint4*>(a_hi + off) = hi;
   *reinterpret_cast<uint4*>(a_hi + A_BYTES + off) = lo;
 }
@@ -284,16 +301,16 @@ __device__ __forceinline__ void finish_item(const ProducerCtx& c, int round, flo
   const int st = it & (STAGES - 1);
   if (round == 0) {
     mbar_wait(&c.tail->empty[st], ((it / STAGES) & 1) ^ 1);
-    if (c.trace != nullptr && c.lane == 0 && 8 * it + c.pw < TRACE_N) c.trace[1 * TRACE_N + 8 * it + c.pw] = clock64();
+    if (c.trace != nullptr && c.lane == 0 && c.pw < 8 && 8 * it + c.pw < TRACE_N) c.trace[1 * TRACE_N + 8 * it + c.pw] = clock64();
   }
-  const int row = 32 * round + 4 * c.pw + c.q;
+  const int row = (TILE_M / ROUNDS) * round + 4 * c.pw + c.q;
   store_split(c.smem + (size_t)st * STAGE_BYTES, swz((uint32_t)row, (uint32_t)c.j), acc);
   acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (round == 3) {
+  if (round == ROUNDS - 1) {
     fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&c.tail->full[st]);
-    if (c.trace != nullptr && c.lane == 0 && 8 * it + c.pw < TRACE_N) c.trace[2 * TRACE_N + 8 * it + c.pw] = clock64();
+    if (c.trace != nullptr && c.lane == 0 && c.pw < 8 && 8 * it + c.pw < TRACE_N) c.trace[2 * TRACE_N + 8 * it + c.pw] = clock64();
     ++it;
   }
 }
@@ -302,7 +319,8 @@ __device__ __forceinline__ void finish_item(const ProducerCtx& c, int round, flo
 // most of stride 8): 32 items, DEPTH in flight, tap weights precomputed in the recipe.
 template <int T, int DEPTH>
 __device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, int& it) {
-  constexpr int ITEMS = (CH / KCH) * 4;
+  constexpr int ITEMS = (CH / KCH) * ROUNDS;
+  static_assert(ITEMS % DEPTH == 0, "depth must divide the item count");
   float4 buf[DEPTH][T][T];
 #pragma unroll
   for (int d = 0; d < DEPTH; ++d)
@@ -312,8 +330,8 @@ __device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, int& i
       for (int tx = 0; tx < T; ++tx) buf[d][ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
   auto issue = [&](float4(&v)[T][T], int item) {
     if (c.feat == nullptr) return;
-    const RowDesc& d = c.wdesc[(item & 3) * 4 + c.q];
-    const float* r = c.feat + d.base + (item >> 2) * KCH + c.j * 4;
+    const RowDesc& d = c.wdesc[(item % ROUNDS) * 4 + c.q];
+    const float* r = c.feat + d.base + (item / ROUNDS) * KCH + c.j * 4;
 #pragma unroll
     for (int ty = 0; ty < T; ++ty) {
       ldg_if<0>(v[ty][0], r, d.w9[ty * 3 + 0]);
@@ -329,7 +347,7 @@ __device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, int& i
   for (int base = 0; base < ITEMS; base += DEPTH) {
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) {
-      const int item = base + d, round = item & 3;
+      const int item = base + d, round = item % ROUNDS;
       const RowDesc& rd = c.wdesc[round * 4 + c.q];
 #pragma unroll
       for (int ty = 0; ty < T; ++ty)
@@ -350,33 +368,51 @@ struct WinPos {
 
 __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx, uint32_t nwy, int* it_io) {
   int it = *it_io;
-  float4 bufA[3][3], bufB[3][3];
+  float4 bufA[3][3], bufB[3][3];      // bufB is dead (eliminated) when WINDOW_DOUBLE_BUFFER is false
   float wA[3][3], wB[3][3];
 #pragma unroll
   for (int ty = 0; ty < 3; ++ty)
 #pragma unroll
-    for (int tx = 0; tx < 3; ++tx) bufA[ty][tx] = bufB[ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tx = 0; tx < 3; ++tx) {
+      bufA[ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (WINDOW_DOUBLE_BUFFER) bufB[ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
   auto issue = [&](float4(&v)[3][3], float(&w)[3][3], const WinPos& p) {
     const RowDesc& d = c.wdesc[p.rd * 4 + c.q];
-    float wx[3], wy[3];
+    const bool single = (((nwx >> (8 * p.rd)) & 255u) == 1u) && (((nwy >> (8 * p.rd)) & 255u) == 1u);   // warp-uniform
+    if (single) {            // all 4 boxes of this round fit one 3x3 window: precomputed products
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      wx[k] = desc_wx(d, 3 * p.sx + k);
-      wy[k] = desc_wy(d, 3 * p.sy + k);
+      for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) w[ty][tx] = d.w9[ty * 3 + tx];
+    } else {
+      float wx[3], wy[3];
+      if (3 * p.sx + 2 < 8 && 3 * p.sy + 2 < 8) {          // warp-uniform
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          wx[k] = d.wx8[3 * p.sx + k];
+          wy[k] = d.wy8[3 * p.sy + k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          wx[k] = desc_wx(d, 3 * p.sx + k);
+          wy[k] = desc_wy(d, 3 * p.sy + k);
+        }
+      }
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) w[ty][tx] = wy[ty] * wx[tx];
     }
-    const float* r = (c.feat == nullptr ? nullptr : c.feat + d.base) + (size_t)(3 * p.sy) * c.row_stride +
-                     (size_t)(3 * p.sx) * CH + p.cc * KCH + c.j * 4;
+    if (c.feat == nullptr) return;
+    const float* r = c.feat + d.base + (size_t)(3 * p.sy) * c.row_stride + (size_t)(3 * p.sx) * CH + p.cc * KCH + c.j * 4;
 #pragma unroll
     for (int ty = 0; ty < 3; ++ty) {
-      w[ty][0] = wy[ty] * wx[0];
-      w[ty][1] = wy[ty] * wx[1];
-      w[ty][2] = wy[ty] * wx[2];
-      if (c.feat != nullptr) {
-        ldg_if<0>(v[ty][0], r, w[ty][0]);
-        ldg_if<CH * 4>(v[ty][1], r, w[ty][1]);
-        ldg_if<2 * CH * 4>(v[ty][2], r, w[ty][2]);
-      }
+      ldg_if<0>(v[ty][0], r, w[ty][0]);
+      ldg_if<CH * 4>(v[ty][1], r, w[ty][1]);
+      ldg_if<2 * CH * 4>(v[ty][2], r, w[ty][2]);
       r += c.row_stride;
     }
   };
@@ -386,7 +422,7 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
     p.sx = 0;
     if (++p.sy < (int)((nwy >> (8 * p.rd)) & 255u)) return p;
     p.sy = 0;
-    if (++p.rd < 4) return p;
+    if (++p.rd < ROUNDS) return p;
     p.rd = 0;
     if (++p.cc < CH / KCH) return p;
     valid = false;
@@ -405,17 +441,27 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
   WinPos cur{0, 0, 0, 0}, nxt;
   bool more;
   issue(bufA, wA, cur);
-  while (true) {
-    nxt = advance(cur, more);
-    if (more) issue(bufB, wB, nxt);
-    consume(bufA, wA, cur);
-    if (!more) break;
-    cur = nxt;
-    nxt = advance(cur, more);
-    if (more) issue(bufA, wA, nxt);
-    consume(bufB, wB, cur);
-    if (!more) break;
-    cur = nxt;
+  if (WINDOW_DOUBLE_BUFFER) {
+    while (true) {
+      nxt = advance(cur, more);
+      if (more) issue(bufB, wB, nxt);
+      consume(bufA, wA, cur);
+      if (!more) break;
+      cur = nxt;
+      nxt = advance(cur, more);
+      if (more) issue(bufA, wA, nxt);
+      consume(bufB, wB, cur);
+      if (!more) break;
+      cur = nxt;
+    }
+  } else {
+    while (true) {
+      consume(bufA, wA, cur);
+      nxt = advance(cur, more);
+      if (!more) break;
+      cur = nxt;
+      issue(bufA, wA, cur);
+    }
   }
   *it_io = it;
 }
@@ -460,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
 
   if (warp < FIRST_PRODUCER_WARP) {
     // warpgroup 0 (loader, MMA issuer, two idle warps) hands registers to the producer warpgroups
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_WG0));
   if (warp == 0) {
     // ================= weight loader =================
     if (lane == 0) {
@@ -522,8 +568,8 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
   }
   } else if (warp < FIRST_EPILOGUE_WARP) {
     // ================= pool producers =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-    const int pw = warp - FIRST_PRODUCER_WARP;       // 0..7 -> tile rows 32*round + 4*pw + {0..3}
+    if (REGS_PRODUCER > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER > 0 ? REGS_PRODUCER : 128));
+    const int pw = warp - FIRST_PRODUCER_WARP;       // tile rows (128/ROUNDS)*round + 4*pw + {0..3}
     RowDesc* wdesc = tail->desc[pw];
     ProducerCtx c;
     c.smem = smem;
@@ -543,8 +589,8 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
         for (int n = 0; n < p.nl; ++n) {
           __syncwarp();                              // everyone is done with the previous layer's recipes
           int nx = 0, ny = 0;
-          if (lane < 16) {
-            const int cell = cell0 + 32 * (lane >> 2) + 4 * pw + (lane & 3);
+          if (lane < ROWS_PER_WARP) {
+            const int cell = cell0 + (TILE_M / ROUNDS) * (lane >> 2) + 4 * pw + (lane & 3);
             RowDesc d;
             d.base = 0;
             d.nx = d.ny = 0;
@@ -566,6 +612,11 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
 #pragma unroll
               for (int tx = 0; tx < 3; ++tx) d.w9[ty * 3 + tx] = desc_wy(d, ty) * desc_wx(d, tx);
             d.w9[9] = d.w9[10] = d.w9[11] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              d.wx8[k] = desc_wx(d, k);
+              d.wy8[k] = desc_wy(d, k);
+            }
             wdesc[lane] = d;
             nx = d.nx;
             ny = d.ny;
@@ -578,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           uint32_t nwx = 0, nwy = 0;
           int extent = 0;
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < ROUNDS; ++r) {
             const int mx = __shfl_sync(0xffffffffu, nx, 4 * r), my = __shfl_sync(0xffffffffu, ny, 4 * r);
             extent = max(extent, max(mx, my));
             nwx |= (uint32_t)min(255, max(1, (mx + 2) / 3)) << (8 * r);
@@ -586,9 +637,9 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           }
           __syncwarp();
           if (extent <= 2)
-            produce_layer_small<2, 4>(c, it);
+            produce_layer_small<2, DEPTH_2X2>(c, it);
           else if (extent <= 3)
-            produce_layer_small<3, 2>(c, it);
+            produce_layer_small<3, DEPTH_3X3>(c, it);
           else
             produce_layer_win(c, nwx, nwy, &it);
         }
@@ -596,6 +647,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     }
   } else {
     // ================= epilogue: layer drains + per-(view, scale) finalisation =================
+    if (REGS_EPILOGUE > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE > 0 ? REGS_EPILOGUE : 96));
     const int e = warp - FIRST_EPILOGUE_WARP;      // 0..7
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int col_begin = (e >> 2) * (CH / 2);     // two warps per quarter split the 256 columns
