@@ -15,7 +15,7 @@ build/%.o: $(SRC_DIR)/%.cu $(SRC_DIR)/vfa_common.cuh include/vfa_b200.h
 
 $(OUT): $(OBJS)
 	@mkdir -p vfa_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -ldl
 
 clean:
 	rm -rf build $(OUT)
