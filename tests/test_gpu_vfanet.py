@@ -1,0 +1,79 @@
+"""The fused camera/scale entry against the reference's own loop structure (reference vfanet.py:64-82), with the
+drop-in VFA modules called once per (camera, scale) as the reference does, and against the float64 port."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_port                        # noqa: E402
+import vfa_b200                                     # noqa: E402
+from vfa_b200 import geometry, synthetic, vfanet    # noqa: E402
+
+
+class _Stem(nn.Module):
+    """The attributes of reference VFANet that the loop touches (vfanet.py:30-43), at reduced width."""
+    def __init__(self, g, ch=32):
+        super().__init__()
+        args = SimpleNamespace(data=g.name, image_size=g.image_size)
+        self.vfa8 = vfa_b200.VFA(ch, g.grid_height, g.cube_size, 1 / 8., args)
+        self.vfa16 = vfa_b200.VFA(ch, g.grid_height, g.cube_size, 1 / 16., args)
+        self.vfa32 = vfa_b200.VFA(ch, g.grid_height, g.cube_size, 1 / 32., args)
+        self.lat8, self.lat16, self.lat32 = nn.Conv2d(16, ch, 1), nn.Conv2d(24, ch, 1), nn.Conv2d(40, ch, 1)
+        self.bn8, self.bn16, self.bn32 = nn.GroupNorm(8, ch), nn.GroupNorm(8, ch), nn.GroupNorm(8, ch)
+
+
+def test_fused_cameras_equal_reference_loop():
+    g = geometry.MULTIVIEWC
+    torch.manual_seed(0)
+    m = _Stem(g).cuda()
+    V = 3
+    grid = geometry.grid_for(g)[None].cuda()
+    calibs = synthetic.ring_calibs(g, n_views=V).cuda()
+    sizes = g.feature_sizes()
+    f8 = torch.randn(V, 16, *sizes[0], device='cuda')
+    f16 = torch.randn(V, 24, *sizes[1], device='cuda')
+    f32 = torch.randn(V, 40, *sizes[2], device='cuda')
+    with torch.no_grad():
+        fused = vfanet.aggregate_cameras(m, f8, f16, f32, calibs, grid)
+        # the reference's loop, one drop-in VFA.forward per (camera, scale)   (vfanet.py:64-82)
+        ortho = 0
+        for cam in range(V):
+            lat8 = F.relu(m.bn8(m.lat8(f8[[cam]])))
+            lat16 = F.relu(m.bn16(m.lat16(f16[[cam]])))
+            lat32 = F.relu(m.bn32(m.lat32(f32[[cam]])))
+            ortho = ortho + (m.vfa8(lat8, calibs[cam], grid) + m.vfa16(lat16, calibs[cam], grid)
+                             + m.vfa32(lat32, calibs[cam], grid))
+        # float64 port on the same lateral features
+        lats = vfanet.lateral_features(m, f8, f16, f32)
+        params = [(v.collapse.weight.detach().cpu(), v.collapse.bias.detach().cpu()) for v in (m.vfa8, m.vfa16, m.vfa32)]
+        want = ref_port.aggregate([x.cpu().double()[None] for x in lats], calibs.cpu(), grid[0].cpu(),
+                                  [(w.double(), b.double()) for w, b in params], g.grid_height, g.cube_size, g.name,
+                                  g.image_size, cache_boxes=True).numpy()
+    assert fused.shape == (1, 32, 156, 156)
+    torch.testing.assert_close(fused, ortho, rtol=1e-5, atol=2e-6)
+    err = np.abs(fused.cpu().numpy().astype(np.float64) - want)
+    assert (err <= 1e-6 + 1e-5 * np.abs(want)).all(), f'worst abs err {err.max():.2e}'
+
+
+def test_fused_cameras_train_step_updates_collapse_and_laterals():
+    g = geometry.WILDTRACK
+    torch.manual_seed(1)
+    m = _Stem(g, ch=16).cuda()
+    V, B = 2, 2
+    grid = geometry.grid_for(g)[::4, ::4].contiguous().cuda()
+    calibs = synthetic.ring_calibs(g, n_views=V).cuda()
+    sizes = g.feature_sizes()
+    f8 = torch.randn(B * V, 16, *sizes[0], device='cuda')
+    f16 = torch.randn(B * V, 24, *sizes[1], device='cuda')
+    f32 = torch.randn(B * V, 40, *sizes[2], device='cuda')
+    out = vfanet.aggregate_cameras(m, f8, f16, f32, calibs, grid, batch=B)
+    assert out.shape == (B, 16, 30, 90)
+    out.square().mean().backward()
+    for name, p in m.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+        assert float(p.grad.abs().max()) > 0, name

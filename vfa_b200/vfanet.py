@@ -1,0 +1,45 @@
+"""Caller-side glue for the reference network.
+
+`aggregate_cameras` replaces the per-camera / per-scale loop of reference `VFANet.forward`
+(reference vfa/model/vfanet.py:64-82) for any module that carries the reference's attribute names
+(`lat8/16/32`, `bn8/16/32`, `vfa8/16/32` -- the latter being `vfa_b200.VFA` modules): the three lateral
+1x1 conv + GroupNorm + ReLU stages run ONCE over all cameras (exact: GroupNorm statistics are per sample,
+reference vfanet.py:72-74) in channels-last memory format, and one fused kernel launch aggregates all
+cameras and scales.  INTEGRATION.md shows the two-line edit of the reference's forward.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .vfa_op import aggregate, build_table
+
+
+def lateral_features(model, feats8, feats16, feats32):
+    """relu(GN(conv1x1(.))) for all cameras at once, emitted channels-last (zero-copy hand-off to the gather)."""
+    outs = []
+    for conv, norm, f in ((model.lat8, model.bn8, feats8), (model.lat16, model.bn16, feats16),
+                          (model.lat32, model.bn32, feats32)):
+        x = f.contiguous(memory_format=torch.channels_last)
+        outs.append(F.relu(norm(conv(x))))
+    return outs
+
+
+def aggregate_cameras(model, feats8, feats16, feats32, calibs, grid, crange=(-1.0, 0.95), batch: int = 1):
+    """feats* [B*V, C_s, fH_s, fW_s] backbone maps (camera-major within a frame, as reference utils.py:43 collates),
+    calibs [V,3,4], grid [1,L,W,3] or [L,W,3]  ->  ortho [B, 256, L, W] = sum over cameras and scales (vfanet.py:79-82)."""
+    lats = lateral_features(model, feats8, feats16, feats32)
+    N = lats[0].shape[0]
+    if N % batch != 0:
+        raise ValueError(f'{N} feature maps do not split into {batch} frames')
+    V = N // batch
+    calibs = calibs.reshape(-1, 3, 4)
+    if calibs.shape[0] != V:
+        raise ValueError(f'{calibs.shape[0]} calibrations for {V} cameras')
+    L, W = grid.shape[-3], grid.shape[-2]
+    vfas = (model.vfa8, model.vfa16, model.vfa32)
+    geom = vfas[0].geometry((L, W), crange)
+    table = build_table(geom, calibs, grid)
+    feats = [x.reshape(batch, V, *x.shape[1:]) for x in lats]
+    return aggregate(feats, table, [m.collapse.weight for m in vfas], [m.collapse.bias for m in vfas],
+                     flags=vfas[0].flags)
