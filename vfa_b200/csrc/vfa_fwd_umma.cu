@@ -29,11 +29,26 @@ namespace umma {
 
 constexpr int CH = 256;                 // channels == MMA N
 constexpr int TILE_M = 128;             // cells per CTA == TMEM lanes
+// A tile is a compact TILE_H x TILE_W block of the BEV grid, not 128 consecutive cells: neighbouring cells in both
+// directions project to overlapping texel windows, so the texels one stage touches shrink ~3x (L1 / L2 reuse).
+constexpr int TILE_W = 16;
+constexpr int TILE_H = TILE_M / TILE_W;
 constexpr int KCH = 32;                 // K elements per stage (one 128-byte swizzle row of tf32)
-constexpr int STAGES = 2;
+#ifndef VFA_CTA_PAIR
+#define VFA_CTA_PAIR 1
+#endif
+// PAIR: two CTAs of a cluster (one TPC) run tcgen05.mma.cta_group::2 -- M = 256 cells across the pair, each CTA stages
+// its own pooled rows and only HALF of the weight slab (the tensor cores fetch the other half from the peer), which
+// halves the weight traffic from L2 and the operand reads from shared memory, and makes room for a third stage.
+constexpr bool PAIR = VFA_CTA_PAIR != 0;
+#ifndef VFA_STAGES
+#define VFA_STAGES (VFA_CTA_PAIR ? 3 : 2)
+#endif
+constexpr int STAGES = VFA_STAGES;
 constexpr int A_BYTES = TILE_M * KCH * 4;          // 16 KB per hi / lo tile
-constexpr int B_BYTES = CH * KCH * 4;              // 32 KB per hi / lo slab
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
+constexpr int B_BYTES = CH * KCH * 4;              // 32 KB per hi / lo slab (whole N = 256)
+constexpr int B_LOCAL_BYTES = PAIR ? B_BYTES / 2 : B_BYTES;   // rows of the slab this CTA stages
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_LOCAL_BYTES;  // 64 KB (pair) / 96 KB
 #ifndef VFA_PRODUCER_WARPS
 #define VFA_PRODUCER_WARPS 8
 #endif
@@ -74,10 +89,11 @@ __device__ __forceinline__ float desc_wy(const RowDesc& d, int i) {
 struct __align__(16) SmemTail {
   RowDesc desc[NUM_PRODUCER_WARPS][ROWS_PER_WARP];
   float bias[VFA_MAX_SCALES][CH];
-  unsigned long long full[STAGES];
-  unsigned long long empty[STAGES];
+  unsigned long long full[STAGES];       // 8 producer warps + weight loader (tx) of THIS CTA
+  unsigned long long empty[STAGES];      // tcgen05.commit (multicast to both CTAs of a pair)
+  unsigned long long peer_full[STAGES];  // pair leader only: the peer's relay thread reports the peer's full[st]
   unsigned long long acc_full;
-  unsigned long long acc_empty;
+  unsigned long long acc_empty;          // epilogue warps (of both CTAs of a pair, on the leader's barrier)
   uint32_t tmem_base;
 };
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
@@ -139,23 +155,77 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// wait on a barrier whose arrivals come from the other CTA of the pair (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(void* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE_C;\n\t"
+      "bra.uni WAIT_LOOP_C;\n\t"
+      "WAIT_DONE_C:\n\t"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(void* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(void* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  if (PAIR) {   // arrive on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (PAIR) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -198,7 +268,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
          ((uint64_t)2 << 61);
 }
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N=256, M=128
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CH >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CH >> 3) << 17) |
+                           ((uint32_t)((PAIR ? 2 * TILE_M : TILE_M) >> 4) << 24);
 
 // byte offset of (row, 16-byte chunk j) inside a [rows x 128 B] SWIZZLE_128B tile
 __device__ __host__ __forceinline__ uint32_t swz(uint32_t row, uint32_t j) { return row * 128u + ((j ^ (row & 7u)) << 4); }
@@ -232,7 +303,9 @@ __global__ void __launch_bounds__(256) prep_weight_umma_kernel(const float* __re
 struct UmmaArgs {
   AggParams p;
   const uint8_t* wprep[VFA_MAX_SCALES];
-  int n_groups;        // view groups (grid.x = tiles * n_groups); > 1 -> atomic accumulation into a zeroed output
+  int n_groups;        // view groups (grid.x = tiles_padded * n_groups); > 1 -> atomic accumulation into a zeroed output
+  int tiles_padded;    // cell tiles, rounded up to a multiple of the cluster size
+  int tiles_x;         // tiles are TILE_H x TILE_W blocks of BEV cells: tile -> (tile / tiles_x, tile % tiles_x)
   int views_per_group;
   long long* trace;    // debug: timestamps of CTA (trace_block,0) when non-null: [role 0..3][TRACE_N]
   int trace_block;
@@ -247,9 +320,26 @@ struct UmmaArgs {
 // row, so every warp gets the same mix of cheap and expensive rows).  Loads are predicated on the tap weight (taps with weight 0 are never
 // fetched) and issued ahead of their use so several items / windows are in flight per warp.
 
-// @(w != 0) ld.global.nc.v4.f32 v, [ptr + IMM]   -- v keeps its old (finite) contents when the tap is off
+// @(w != 0) ld.global.nc.v4.f32 v, [ptr + IMM]   -- v keeps its old (finite) contents when the tap is off.
+// With VFA_L1_PREFETCH the same predicate also issues prefetch.global.L1 of the NEXT 128-byte line of the texel: that is
+// exactly what the same rows will load for the next K chunk (32 channels further), one stage later, so 7 of 8 chunks
+// of a layer find their data in L1 instead of paying the L2 latency while holding registers.
+#ifndef VFA_L1_PREFETCH
+#define VFA_L1_PREFETCH 0
+#endif
 template <int IMM>
 __device__ __forceinline__ void ldg_if(float4& v, const float* ptr, float w) {
+#if VFA_L1_PREFETCH
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.neu.f32 p, %5, 0f00000000;\n\t"
+      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t"
+      "@p prefetch.global.L1 [%4+%7];\n\t"
+      "}\n"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(ptr), "f"(w), "n"(IMM), "n"(IMM + KCH * 4));
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -258,6 +348,7 @@ __device__ __forceinline__ void ldg_if(float4& v, const float* ptr, float w) {
       "}\n"
       : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
       : "l"(ptr), "f"(w), "n"(IMM));
+#endif
 }
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   if (w != 0.f) {        // predicated, so a stale Inf/NaN left in an unused slot can never leak in
@@ -298,7 +389,7 @@ struct ProducerCtx {
 
 // Called when an item is complete: waits for the stage slot (first round only), stores, signals (last round).
 __device__ __forceinline__ void finish_item(const ProducerCtx& c, int round, float4& acc, int& it) {
-  const int st = it & (STAGES - 1);
+  const int st = it % STAGES;
   if (round == 0) {
     mbar_wait(&c.tail->empty[st], ((it / STAGES) & 1) ^ 1);
     if (c.trace != nullptr && c.lane == 0 && c.pw < 8 && 8 * it + c.pw < TRACE_N) c.trace[1 * TRACE_N + 8 * it + c.pw] = clock64();
@@ -474,9 +565,16 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
   const AggParams& p = a.p;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x / a.n_groups, group = blockIdx.x % a.n_groups;
+  // grid.x = tiles_padded * n_groups; consecutive blockIdx.x (= the two CTAs of a pair) are adjacent tiles of a group
+  const int tile = blockIdx.x % a.tiles_padded, group = blockIdx.x / a.tiles_padded;
   const int b = blockIdx.y;
-  const int cell0 = tile * TILE_M;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // 0 = pair leader (issues the MMAs)
+  // cell index of tile row r (0..127), or -1 outside the grid (edge tiles, the padding tile of an odd pair)
+  const int tile_y0 = (tile / a.tiles_x) * TILE_H, tile_x0 = (tile % a.tiles_x) * TILE_W;
+  auto cell_of_row = [&](int r) -> int {
+    const int y = tile_y0 + r / TILE_W, x = tile_x0 + r % TILE_W;
+    return (y < p.L && x < p.W) ? y * p.W + x : -1;
+  };
   const int v_begin = group * a.views_per_group;
   const int v_end = min(p.V, v_begin + a.views_per_group);
   const int n_vs = (v_end - v_begin) * p.S;          // (view, scale) iterations of this CTA
@@ -488,19 +586,27 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&tail->full[s], NUM_PRODUCER_WARPS + 1);
       mbar_init(&tail->empty[s], 1);
+      mbar_init(&tail->peer_full[s], 1);
     }
     mbar_init(&tail->acc_full, 1);
-    mbar_init(&tail->acc_empty, NUM_EPILOGUE_WARPS);
+    mbar_init(&tail->acc_empty, PAIR ? 2 * NUM_EPILOGUE_WARPS : NUM_EPILOGUE_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {   // both CTAs of the pair, same warp, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // barriers + TMEM of both CTAs exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
 
@@ -521,8 +627,14 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
             if (a.variant & 8) {   // debug knock-out: no weight traffic
               mbar_arrive(&tail->full[st]);
             } else {
-              mbar_arrive_expect_tx(&tail->full[st], 2 * B_BYTES);
-              bulk_g2s(dst, a.wprep[s] + (size_t)kc * (2 * B_BYTES), 2 * B_BYTES, &tail->full[st]);
+              mbar_arrive_expect_tx(&tail->full[st], 2 * B_LOCAL_BYTES);
+              const uint8_t* src = a.wprep[s] + (size_t)kc * (2 * B_BYTES);
+              if (PAIR) {   // this CTA's half of the output-channel rows: rows [128*rank, 128*rank+128) of hi and of lo
+                bulk_g2s(dst, src + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+                bulk_g2s(dst + B_LOCAL_BYTES, src + B_BYTES + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+              } else {
+                bulk_g2s(dst, src, 2 * B_BYTES, &tail->full[st]);
+              }
             }
           }
     }
@@ -531,21 +643,31 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     // The TMEM accumulator is only trusted for ONE height layer (32 k-steps): the tensor core truncates every
     // accumulation (measured: error grows linearly in K, biased toward zero), so layer partials are summed by the
     // epilogue warps with round-to-nearest FADDs (drain) instead of inside the tensor core.
-    if (lane == 0) {
+    if (lane == 0 && cta_rank != 0) {
+      // pair follower: its tensor core is driven by the leader's instructions; this thread only relays "my stage is
+      // full" (own producers + own half of the weight slab) to the leader
+      const int total = n_vs * p.nl * CHUNKS_PER_LAYER;
+      for (int it = 0; it < total; ++it) {
+        const int st = it % STAGES;
+        mbar_wait(&tail->full[st], (it / STAGES) & 1);
+        mbar_arrive_remote(&tail->peer_full[st], 0);
+      }
+    } else if (lane == 0) {
       int it = 0, drain = 0;
       for (int vs = 0; vs < n_vs; ++vs) {
         for (int n = 0; n < p.nl; ++n, ++drain) {
-          mbar_wait(&tail->acc_empty, (drain & 1) ^ 1);
+          if (PAIR) mbar_wait_cluster(&tail->acc_empty, (drain & 1) ^ 1); else mbar_wait(&tail->acc_empty, (drain & 1) ^ 1);
           tc_fence_after();
           for (int cc = 0; cc < CHUNKS_PER_LAYER; ++cc, ++it) {
             const int st = it % STAGES;
             TRACE(0, 2 * it);
             mbar_wait(&tail->full[st], (it / STAGES) & 1);
+            if (PAIR) mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
             TRACE(0, 2 * it + 1);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
             const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
-            const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES);
+            const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_LOCAL_BYTES);
 #pragma unroll
             for (int ks = 0; ks < KCH / 8; ++ks) {
               const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // 8 tf32 = 32 bytes along K inside the swizzle row
@@ -590,12 +712,12 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           __syncwarp();                              // everyone is done with the previous layer's recipes
           int nx = 0, ny = 0;
           if (lane < ROWS_PER_WARP) {
-            const int cell = cell0 + (TILE_M / ROUNDS) * (lane >> 2) + 4 * pw + (lane & 3);
+            const int cell = cell_of_row((TILE_M / ROUNDS) * (lane >> 2) + 4 * pw + (lane & 3));
             RowDesc d;
             d.base = 0;
             d.nx = d.ny = 0;
             d.wx_first = d.wx_last = d.wy_first = d.wy_last = d.wy_mid = 0.f;
-            if (cell < p.LW) {
+            if (cell >= 0) {
               const BoxTaps t =
                   derive_taps(reinterpret_cast<const float4*>(p.boxes)[((size_t)v * p.nl + n) * p.LW + cell], sc);
               d.base = (t.y0 * sc.fw + t.x0) * CH;
@@ -652,7 +774,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int col_begin = (e >> 2) * (CH / 2);     // two warps per quarter split the 256 columns
     const int row = quarter * 32 + lane;
-    const int cell = cell0 + row;
+    const int cell = cell_of_row(row);
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     float* outp = p.out + (size_t)b * CH * p.LW + cell;
     int drain = 0;
@@ -679,7 +801,10 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->acc_empty);      // accumulator columns may be overwritten by the next layer
+        if (lane == 0) {                                   // accumulator columns may be overwritten by the next layer
+          if (PAIR && cta_rank != 0) mbar_arrive_remote(&tail->acc_empty, 0);
+          else mbar_arrive(&tail->acc_empty);
+        }
         if (e == 0 && lane == 0) TRACE(3, 2 * drain + 1);
         if (last_layer) {
           // pass 2 (overlaps the next layer's MMAs): + bias, ReLU (vfa_op.py:123-124), then the sum over scales and
@@ -689,7 +814,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
             float y[32];
             tc_ld32(lane_addr + CH + c0, y);
             tc_wait_ld();
-            if (cell < p.LW) {
+            if (cell >= 0) {
               if (p.mask != nullptr) {      // ReLU pass bits of channels c0 .. c0+31 for the backward
                 uint32_t bits = 0;
 #pragma unroll
@@ -714,9 +839,12 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // the peer's shared memory / TMEM stay valid until both are done
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -763,13 +891,26 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, uint32_
   }
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   for (int s = 0; s < VFA_MAX_SCALES; ++s) a.wprep[s] = reinterpret_cast<const uint8_t*>(ws) + (s < p.S ? s : 0) * per_scale;
-  const int tiles = (p.LW + TILE_M - 1) / TILE_M;
+  a.tiles_x = (p.W + TILE_W - 1) / TILE_W;
+  const int tiles = a.tiles_x * ((p.L + TILE_H - 1) / TILE_H);
+  a.tiles_padded = PAIR ? (tiles + 1) / 2 * 2 : tiles;
   // enough CTAs for >= ~4 waves over 148 SMs, otherwise split the views and accumulate atomically
   a.n_groups = ((long long)tiles * p.B >= 4 * 148 || p.V == 1) ? 1 : p.V;
   a.views_per_group = (p.V + a.n_groups - 1) / a.n_groups;
   if (a.n_groups > 1) VFA_CUDA(cudaMemsetAsync(p.out, 0, (size_t)p.B * CH * p.LW * sizeof(float), st));
-  dim3 grid(tiles * a.n_groups, p.B);
-  aggregate_fwd_umma_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.tiles_padded * a.n_groups, p.B);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VFA_CUDA(cudaLaunchKernelEx(&cfg, aggregate_fwd_umma_kernel, a));
   VFA_LAUNCH_CHECK("aggregate_fwd_umma_kernel");
   if (want_trace) {
     static long long host[4 * TRACE_N];
