@@ -377,41 +377,51 @@ __device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const f
   *reinterpret_cast<uint4*>(a_hi + A_BYTES + off) = lo;
 }
 
+// Position of a role in the ring of STAGES smem slots: slot index and the parity its barriers are at.
+struct Pipe {
+  uint32_t st, ph;
+  __device__ __forceinline__ void advance() {
+    if (++st == STAGES) {
+      st = 0;
+      ph ^= 1u;
+    }
+  }
+};
+
 struct ProducerCtx {
   uint8_t* smem;
   SmemTail* tail;
-  const RowDesc* wdesc;     // this warp's 16 recipes (shared memory)
-  const float* feat;        // [fh, fw, CH] map of this (frame, view, scale); nullptr = debug knock-out
+  const RowDesc* wdesc;     // this warp's recipes (shared memory), rows of round r at [4*r .. 4*r+3]
+  const float* feat;        // [fh, fw, CH] map of this (frame, view, scale), + this thread's channel offset j*4
   size_t row_stride;        // fw * CH
-  int pw, lane, q, j;
-  long long* trace;
+  uint32_t a_off[ROUNDS];   // swizzled byte offset of (this thread's row of round r, its 16-byte chunk) in an A tile
+  int lane, q;
+  bool no_gather;           // debug knock-out
 };
 
 // Called when an item is complete: waits for the stage slot (first round only), stores, signals (last round).
-__device__ __forceinline__ void finish_item(const ProducerCtx& c, int round, float4& acc, int& it) {
-  const int st = it % STAGES;
-  if (round == 0) {
-    mbar_wait(&c.tail->empty[st], ((it / STAGES) & 1) ^ 1);
-    if (c.trace != nullptr && c.lane == 0 && c.pw < 8 && 8 * it + c.pw < TRACE_N) c.trace[1 * TRACE_N + 8 * it + c.pw] = clock64();
-  }
-  const int row = (TILE_M / ROUNDS) * round + 4 * c.pw + c.q;
-  store_split(c.smem + (size_t)st * STAGE_BYTES, swz((uint32_t)row, (uint32_t)c.j), acc);
+__device__ __forceinline__ void finish_item(const ProducerCtx& c, int round, uint32_t a_off, float4& acc, Pipe& pipe) {
+  if (round == 0) mbar_wait(&c.tail->empty[pipe.st], pipe.ph ^ 1u);
+  store_split(c.smem + (size_t)pipe.st * STAGE_BYTES, a_off, acc);
   acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (round == ROUNDS - 1) {
     fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.tail->full[st]);
-    if (c.trace != nullptr && c.lane == 0 && c.pw < 8 && 8 * it + c.pw < TRACE_N) c.trace[2 * TRACE_N + 8 * it + c.pw] = clock64();
-    ++it;
+    if (c.lane == 0) mbar_arrive(&c.tail->full[pipe.st]);
+    pipe.advance();
   }
 }
 
 // Layers where every row of the warp has at most TxT taps (T = 2: the common case at strides 16 and 32; T = 3:
 // most of stride 8): 32 items, DEPTH in flight, tap weights precomputed in the recipe.
 template <int T, int DEPTH>
-__device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, int& it) {
+__device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, Pipe& pipe) {
   constexpr int ITEMS = (CH / KCH) * ROUNDS;
-  static_assert(ITEMS % DEPTH == 0, "depth must divide the item count");
+  static_assert(ROUNDS % DEPTH == 0, "DEPTH must divide ROUNDS");
+  static_assert(ITEMS % ROUNDS == 0, "");
+  const RowDesc* dq = c.wdesc + c.q;          // this quarter-warp's row of round 0; round r is dq[4*r]
+  const float* feat = c.feat;
+  const size_t rs = c.row_stride;
   float4 buf[DEPTH][T][T];
 #pragma unroll
   for (int d = 0; d < DEPTH; ++d)
@@ -419,33 +429,37 @@ __device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, int& i
     for (int ty = 0; ty < T; ++ty)
 #pragma unroll
       for (int tx = 0; tx < T; ++tx) buf[d][ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto issue = [&](float4(&v)[T][T], int item) {
-    if (c.feat == nullptr) return;
-    const RowDesc& d = c.wdesc[(item % ROUNDS) * 4 + c.q];
-    const float* r = c.feat + d.base + (item / ROUNDS) * KCH + c.j * 4;
+  auto issue = [&](float4(&v)[T][T], int round, int cc) {
+    if (c.no_gather) return;
+    const RowDesc& d = dq[4 * round];
+    const float* r = feat + (d.base + cc * KCH);
 #pragma unroll
     for (int ty = 0; ty < T; ++ty) {
       ldg_if<0>(v[ty][0], r, d.w9[ty * 3 + 0]);
       ldg_if<CH * 4>(v[ty][1], r, d.w9[ty * 3 + 1]);
       if (T > 2) ldg_if<2 * CH * 4>(v[ty][T - 1], r, d.w9[ty * 3 + 2]);
-      r += c.row_stride;
+      r += rs;
     }
   };
 #pragma unroll
-  for (int d = 0; d < DEPTH; ++d) issue(buf[d], d);
+  for (int d = 0; d < DEPTH; ++d) issue(buf[d], d % ROUNDS, d / ROUNDS);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // one outer iteration = one K chunk (= one stage); rounds unrolled so buffer slots, store offsets and the
+  // wait / arrive points are all compile-time
 #pragma unroll 1
-  for (int base = 0; base < ITEMS; base += DEPTH) {
+  for (int cc = 0; cc < CH / KCH; ++cc) {
 #pragma unroll
-    for (int d = 0; d < DEPTH; ++d) {
-      const int item = base + d, round = item % ROUNDS;
-      const RowDesc& rd = c.wdesc[round * 4 + c.q];
+    for (int r = 0; r < ROUNDS; ++r) {
+      constexpr int D = DEPTH;
+      const int slot = r % D;                     // (cc * ROUNDS + r) % DEPTH, as DEPTH divides ROUNDS (or is 4 = ROUNDS)
+      const RowDesc& rd = dq[4 * r];
 #pragma unroll
       for (int ty = 0; ty < T; ++ty)
 #pragma unroll
-        for (int tx = 0; tx < T; ++tx) fma4(acc, rd.w9[ty * 3 + tx], buf[d][ty][tx]);
-      if (item + DEPTH < ITEMS) issue(buf[d], item + DEPTH);
-      finish_item(c, round, acc, it);
+        for (int tx = 0; tx < T; ++tx) fma4(acc, rd.w9[ty * 3 + tx], buf[slot][ty][tx]);
+      const int nr = (r + D) % ROUNDS, ncc = cc + (r + D) / ROUNDS;
+      if (ncc < CH / KCH) issue(buf[slot], nr, ncc);
+      finish_item(c, r, c.a_off[r], acc, pipe);
     }
   }
 }
@@ -457,8 +471,8 @@ struct WinPos {
   int cc, rd, sy, sx;
 };
 
-__device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx, uint32_t nwy, int* it_io) {
-  int it = *it_io;
+__device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx, uint32_t nwy, Pipe* pipe_io) {
+  Pipe pipe = *pipe_io;
   float4 bufA[3][3], bufB[3][3];      // bufB is dead (eliminated) when WINDOW_DOUBLE_BUFFER is false
   float wA[3][3], wB[3][3];
 #pragma unroll
@@ -497,8 +511,8 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
 #pragma unroll
         for (int tx = 0; tx < 3; ++tx) w[ty][tx] = wy[ty] * wx[tx];
     }
-    if (c.feat == nullptr) return;
-    const float* r = c.feat + d.base + (size_t)(3 * p.sy) * c.row_stride + (size_t)(3 * p.sx) * CH + p.cc * KCH + c.j * 4;
+    if (c.no_gather) return;
+    const float* r = c.feat + d.base + (size_t)(3 * p.sy) * c.row_stride + (size_t)(3 * p.sx) * CH + p.cc * KCH;
 #pragma unroll
     for (int ty = 0; ty < 3; ++ty) {
       ldg_if<0>(v[ty][0], r, w[ty][0]);
@@ -526,7 +540,7 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
 #pragma unroll
       for (int tx = 0; tx < 3; ++tx) fma4(acc, w[ty][tx], v[ty][tx]);
     if (p.sx + 1 == (int)((nwx >> (8 * p.rd)) & 255u) && p.sy + 1 == (int)((nwy >> (8 * p.rd)) & 255u))
-      finish_item(c, p.rd, acc, it);
+      finish_item(c, p.rd, c.a_off[0] + (uint32_t)p.rd * ((TILE_M / ROUNDS) * 128u), acc, pipe);
   };
 
   WinPos cur{0, 0, 0, 0}, nxt;
@@ -554,7 +568,7 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
       issue(bufA, wA, cur);
     }
   }
-  *it_io = it;
+  *pipe_io = pipe;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const UmmaArgs a) {
@@ -697,16 +711,17 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     c.smem = smem;
     c.tail = tail;
     c.wdesc = wdesc;
-    c.pw = pw;
     c.lane = lane;
     c.q = lane >> 3;
-    c.j = lane & 7;
-    c.trace = (blockIdx.x == a.trace_block && blockIdx.y == 0) ? a.trace : nullptr;
-    int it = 0;
+    c.no_gather = (a.variant & 2) != 0;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r)
+      c.a_off[r] = swz((uint32_t)((TILE_M / ROUNDS) * r + 4 * pw + (lane >> 3)), (uint32_t)(lane & 7));
+    Pipe pipe{0u, 0u};
     for (int v = v_begin; v < v_end; ++v) {
       for (int s = 0; s < p.S; ++s) {
         const ScaleConst sc = p.sc[s];
-        c.feat = (a.variant & 2) ? nullptr : p.feats[s] + ((size_t)(b * p.V + v) * sc.fh * sc.fw) * CH;
+        c.feat = p.feats[s] + ((size_t)(b * p.V + v) * sc.fh * sc.fw) * CH + (lane & 7) * 4;
         c.row_stride = (size_t)sc.fw * CH;
         for (int n = 0; n < p.nl; ++n) {
           __syncwarp();                              // everyone is done with the previous layer's recipes
@@ -759,11 +774,11 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           }
           __syncwarp();
           if (extent <= 2)
-            produce_layer_small<2, DEPTH_2X2>(c, it);
+            produce_layer_small<2, DEPTH_2X2>(c, pipe);
           else if (extent <= 3)
-            produce_layer_small<3, DEPTH_3X3>(c, it);
+            produce_layer_small<3, DEPTH_3X3>(c, pipe);
           else
-            produce_layer_win(c, nwx, nwy, &it);
+            produce_layer_win(c, nwx, nwy, &pipe);
         }
       }
     }
