@@ -69,7 +69,7 @@ typedef struct {
 /* flags of vfa_aggregate_fwd / _bwd */
 #define VFA_FLAG_FORCE_SIMT   1u     /* never take the tcgen05 path (generic fp32 FFMA kernel)         */
 #define VFA_FLAG_FORCE_UMMA   2u     /* fail with VFA_ERR_UNSUPPORTED instead of falling to SIMT       */
-#define VFA_FLAG_BF16_MMA     4u     /* single-pass bf16 tensor-core collapse (stated looser tolerance)*/
+#define VFA_FLAG_BF16_MMA     4u     /* reserved: single-pass bf16 collapse; returns VFA_ERR_UNSUPPORTED */
 #define VFA_FLAG_WEIGHTS_PREPARED 8u /* workspace already holds vfa_prepare_weights output for these flags */
 
 int vfa_version(void);

@@ -183,6 +183,8 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
   VFA_REQUIRE((reinterpret_cast<uintptr_t>(d_boxes) & 15) == 0, VFA_ERR_INVALID_ARGUMENT, "d_boxes not 16-byte aligned");
   VFA_REQUIRE(!((flags & VFA_FLAG_FORCE_SIMT) && (flags & VFA_FLAG_FORCE_UMMA)), VFA_ERR_INVALID_ARGUMENT,
               "FORCE_SIMT and FORCE_UMMA are exclusive");
+  VFA_REQUIRE(!(flags & VFA_FLAG_BF16_MMA), VFA_ERR_UNSUPPORTED,
+              "VFA_FLAG_BF16_MMA (single-pass bf16 collapse) is reserved and not implemented in this build");
   for (int s = 0; s < shape->n_scales; ++s)
     VFA_REQUIRE(d_weight[s] != nullptr, VFA_ERR_INVALID_ARGUMENT, "scale %d: NULL weight", s);
   if (int rc = check_device()) return rc;

@@ -443,23 +443,37 @@ __device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, Pipe& 
   };
 #pragma unroll
   for (int d = 0; d < DEPTH; ++d) issue(buf[d], d % ROUNDS, d / ROUNDS);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // one outer iteration = one K chunk (= one stage); rounds unrolled so buffer slots, store offsets and the
-  // wait / arrive points are all compile-time
+  // The DEPTH resident items are processed phase-batched (all reductions, then all loads of the items DEPTH ahead,
+  // then all stores) so their dependency chains interleave instead of running back to back.
 #pragma unroll 1
   for (int cc = 0; cc < CH / KCH; ++cc) {
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-      constexpr int D = DEPTH;
-      const int slot = r % D;                     // (cc * ROUNDS + r) % DEPTH, as DEPTH divides ROUNDS (or is 4 = ROUNDS)
-      const RowDesc& rd = dq[4 * r];
+    for (int g = 0; g < ROUNDS; g += DEPTH) {
+      float4 accr[DEPTH];
 #pragma unroll
-      for (int ty = 0; ty < T; ++ty)
+      for (int d = 0; d < DEPTH; ++d) {
+        accr[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const RowDesc& rd = dq[4 * (g + d)];
 #pragma unroll
-        for (int tx = 0; tx < T; ++tx) fma4(acc, rd.w9[ty * 3 + tx], buf[slot][ty][tx]);
-      const int nr = (r + D) % ROUNDS, ncc = cc + (r + D) / ROUNDS;
-      if (ncc < CH / KCH) issue(buf[slot], nr, ncc);
-      finish_item(c, r, c.a_off[r], acc, pipe);
+        for (int ty = 0; ty < T; ++ty)
+#pragma unroll
+          for (int tx = 0; tx < T; ++tx) fma4(accr[d], rd.w9[ty * 3 + tx], buf[d][ty][tx]);
+      }
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) {
+        const int nr = (g + d + DEPTH) % ROUNDS, ncc = cc + (g + d + DEPTH) / ROUNDS;
+        if (ncc < CH / KCH) issue(buf[d], nr, ncc);
+      }
+      if (g == 0) mbar_wait(&c.tail->empty[pipe.st], pipe.ph ^ 1u);
+      uint8_t* a_hi = c.smem + (size_t)pipe.st * STAGE_BYTES;
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) store_split(a_hi, c.a_off[g + d], accr[d]);
+      if (g + DEPTH == ROUNDS) {
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.tail->full[pipe.st]);
+        pipe.advance();
+      }
     }
   }
 }
