@@ -12,4 +12,6 @@ from ._lib import (VFAError, FLAG_BF16_MMA, FLAG_FORCE_SIMT, FLAG_FORCE_UMMA,   
 from .vfa_op import (VFA, ProjectionTable, aggregate, aggregate_forward_raw, build_table, last_kernel_path,  # noqa: F401
                      make_geometry, make_shape, prepare_weights, to_channels_last, workspace_for)
 
+from .streaming import StreamingAggregator                          # noqa: F401
+
 __version__ = '0.1.0'
