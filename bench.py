@@ -77,38 +77,50 @@ def workload_numbers(geom, batch):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
-    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-              'clocks_event_reasons.sw_power_cap')
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs (NVML, 5 ms period; falls back to
+    polling nvidia-smi when the NVML binding is unavailable)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.mask, self.max_mhz, self._stop_evt = index, [], 0, None, threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(',')]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                if self.nvml is not None:
+                    self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                    self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self._stop_evt.wait(0.005)
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=clocks.sm,clocks.max.sm,'
+                                          'clocks_event_reasons.active', '--format=csv,noheader,nounits'],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                    self.sm.append(float(out[0]))
+                    self.max_mhz = float(out[1])
+                    self.mask |= int(out[2].strip(), 16)
             except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+                self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
-        if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(self.samples)}
+        if not self.sm:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
+        reasons = [name for bit, name in self.REASONS.items() if self.mask & bit]
+        return {'sm_mhz': statistics.median(self.sm), 'sm_min_mhz': min(self.sm), 'sm_max_mhz': self.max_mhz,
+                'reasons': reasons, 'samples': len(self.sm), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def cpu_port_time(geom, views, threads_note=True):
