@@ -128,6 +128,8 @@ def cpu_port_time(geom, views, threads_note=True):
     (fp32, no_grad, boxes re-derived per call like the reference)."""
     from oracle import ref_port
     from vfa_b200 import geometry, synthetic
+    if torch.get_num_threads() < (os.cpu_count() or 1):
+        torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core
     grid = geometry.grid_for(geom)
     calibs = synthetic.ring_calibs(geom)[:views]
     feats = synthetic.features(geom, batch=1, n_views=views, seed=0)
