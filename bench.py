@@ -48,6 +48,8 @@ def parse():
                     help='dp: frames sharded over GPUs, no data-path collective (weak scaling, default); slab: BEV row '
                          'slabs over GPUs, features broadcast from rank 0 + output all-gather per step (strong scaling)')
     ap.add_argument('--backward', action='store_true', help='time forward + backward (BASELINE config 4)')
+    ap.add_argument('--features', choices=['f32', 'bf16'], default='f32',
+                    help='feature-map storage: f32 (parity path, default) or bf16 (half the gather bytes, stated tolerance)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -64,12 +66,12 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source='fallback (B200_PROFILING.md)')
 
 
-def workload_numbers(geom, batch):
+def workload_numbers(geom, batch, esize=4):
     """Algorithmic bytes / flops of one step on one GPU."""
     L, W = geom.grid_shape
     C, nl, V = geom.channels, geom.n_layers, geom.n_views
     px = sum(h * w for h, w in geom.feature_sizes())
-    feat_bytes = batch * V * px * C * 4
+    feat_bytes = batch * V * px * C * esize
     out_bytes = batch * C * L * W * 4
     const_bytes = 3 * (C * C * nl + C) * 4 + V * nl * L * W * 16 + L * W * 12 + V * 48
     flops = 2.0 * L * W * (C * nl) * C * 3 * V * batch          # collapse contraction, grid-side (as the reference)
@@ -206,10 +208,13 @@ def main():
     # logical [B,V,C,fH,fW], stored channels-last = the layout the lateral convs emit in torch.channels_last
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     feats_cl = [torch.randn(B, V, h, w, C, generator=gen, device=dev).relu_() for (h, w) in geom.feature_sizes()]
+    if args.features == 'bf16':
+        feats_cl = [f.to(torch.bfloat16) for f in feats_cl]
+        args.no_e2e = True
     shape = vfa_b200.make_shape(feats_cl, cgeom.n_layers)
     ws = vfa_b200.workspace_for(cgeom, shape, args.flags, dev)
     out = torch.empty(B, C, grid.shape[0], grid.shape[1], device=dev)
-    nums = workload_numbers(geom, B)
+    nums = workload_numbers(geom, B, 2 if args.features == 'bf16' else 4)
 
     kernel_ms = []
     from vfa_b200 import distributed as vd
@@ -353,6 +358,7 @@ def main():
             'config': {'workload': f'{args.workload}-shaped aggregation forward' + ('+backward' if args.backward else ''),
                        'batch_per_gpu': B, 'views': V, 'channels': C, 'grid': list(grid.shape[:2]) + [len(zs)],
                        'feature_maps': [list(s) for s in geom.feature_sizes()], 'layout': 'channels_last',
+                       'feature_storage': args.features,
                        'parallelism': f'{args.mode}{world}', 'kernel_path': path, 'table': 'rebuilt every step',
                        'l2': f'inputs {nums["feat_bytes"] / 1e6:.0f} MB/step/GPU exceed the 126 MB L2'},
             'clocks': clocks,

@@ -71,6 +71,8 @@ typedef struct {
 #define VFA_FLAG_FORCE_UMMA   2u     /* fail with VFA_ERR_UNSUPPORTED instead of falling to SIMT       */
 #define VFA_FLAG_BF16_MMA     4u     /* reserved: single-pass bf16 collapse; returns VFA_ERR_UNSUPPORTED */
 #define VFA_FLAG_WEIGHTS_PREPARED 8u /* workspace already holds vfa_prepare_weights output for these flags */
+#define VFA_FLAG_BF16_FEATURES 16u  /* d_feats point to bf16 [B,V,fH,fW,C] maps (forward, C = 256 only): half the
+                                        gather bytes; pooling / collapse arithmetic is unchanged (fp32, 3xTF32)    */
 
 int vfa_version(void);
 const char* vfa_last_error(void);

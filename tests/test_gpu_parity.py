@@ -267,3 +267,33 @@ def test_streaming_aggregator_matches_direct_call():
     for hb, out in zip(batches, got):
         want = vfa_b200.aggregate([f.cuda() for f in hb], table, ws, bs)
         assert torch.equal(out.cuda(), want)
+
+
+def test_bf16_feature_storage():
+    """bf16 feature maps (VFA_FLAG_BF16_FEATURES): the kernel widens bf16 -> fp32 exactly, so against the float64 oracle
+    fed the SAME bf16-rounded features the fp32 tolerance holds; against the fp32-feature oracle the stated tolerance is
+    the input quantisation, 2^-9 relative per feature value -> 4e-3 of the output scale (measured ~1e-3)."""
+    name = 'MultiviewC'
+    g = geometry.GEOMETRIES[name]
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g, n_views=2)
+    feats = synthetic.features(g, batch=1, n_views=2, seed=9)
+    params = synthetic.collapse_params(g, seed=9)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    f16 = [f.cuda().permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16) for f in feats]       # [B,V,H,W,C] bf16
+    out = vfa_b200.aggregate(f16, table, ws, bs, channels_last=True)
+    assert vfa_b200.last_kernel_path() == 'umma_tf32x3_bf16feat' and out.dtype == torch.float32
+    # (a) same quantised inputs, fp32 path: identical arithmetic after the widening -> fp32 tolerance
+    fq = [t.float() for t in f16]
+    ref = vfa_b200.aggregate(fq, table, ws, bs, channels_last=True)
+    ok, err = _within(out.cpu().numpy().astype(np.float64), ref.cpu().numpy().astype(np.float64))
+    assert ok.all(), f'worst {err.max():.2e}'
+    # (b) stated tolerance against unquantised fp32 features
+    full = vfa_b200.aggregate([f.cuda() for f in feats], table, ws, bs)
+    scale = float(full.abs().max())
+    rel = float((out - full).abs().max()) / scale
+    print(f'bf16 feature storage: max |err| / max|out| = {rel:.2e}')
+    assert rel < 4e-3
+    with pytest.raises(RuntimeError, match='forward-only'):
+        vfa_b200.aggregate(f16, table, [w.requires_grad_(True) for w in ws], bs, channels_last=True)

@@ -195,6 +195,8 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
   VFA_REQUIRE(d_workspace != nullptr && (reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, VFA_ERR_WORKSPACE,
               "workspace must be a 256-byte aligned device pointer");
   const bool use_umma = !(flags & VFA_FLAG_FORCE_SIMT) && umma_supported(geom, shape, flags);
+  VFA_REQUIRE(!(flags & VFA_FLAG_BF16_FEATURES) || (use_umma && d_relu_mask == nullptr), VFA_ERR_UNSUPPORTED,
+              "bf16 feature maps are supported by the tcgen05 forward (C = 256) only, without the backward mask");
   if ((flags & VFA_FLAG_FORCE_UMMA) && !use_umma) {
     set_error("tcgen05 path requested but unsupported for channels=%d layers=%d", shape->channels, geom->n_layers);
     return VFA_ERR_UNSUPPORTED;

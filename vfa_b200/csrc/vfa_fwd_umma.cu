@@ -98,13 +98,6 @@ struct __align__(16) SmemTail {
 };
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
 
-constexpr int TRACE_N = 2048;
-#define TRACE(role, idx)                                                                          \
-  do {                                                                                            \
-    if (a.trace != nullptr && blockIdx.x == a.trace_block && blockIdx.y == 0 && (idx) < TRACE_N)  \
-      a.trace[(role) * TRACE_N + (idx)] = clock64();                                              \
-  } while (0)
-
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -307,8 +300,6 @@ struct UmmaArgs {
   int tiles_padded;    // cell tiles, rounded up to a multiple of the cluster size
   int tiles_x;         // tiles are TILE_H x TILE_W blocks of BEV cells: tile -> (tile / tiles_x, tile % tiles_x)
   int views_per_group;
-  long long* trace;    // debug: timestamps of CTA (trace_block,0) when non-null: [role 0..3][TRACE_N]
-  int trace_block;
   int variant;         // debug bits: 1 = hi*hi only, 2 = no gather loads, 4 = no MMA, 8 = no weight loads
 };
 
@@ -320,44 +311,85 @@ struct UmmaArgs {
 // row, so every warp gets the same mix of cheap and expensive rows).  Loads are predicated on the tap weight (taps with weight 0 are never
 // fetched) and issued ahead of their use so several items / windows are in flight per warp.
 
-// @(w != 0) ld.global.nc.v4.f32 v, [ptr + IMM]   -- v keeps its old (finite) contents when the tap is off.
-// With VFA_L1_PREFETCH the same predicate also issues prefetch.global.L1 of the NEXT 128-byte line of the texel: that is
-// exactly what the same rows will load for the next K chunk (32 channels further), one stage later, so 7 of 8 chunks
-// of a layer find their data in L1 instead of paying the L2 latency while holding registers.
+// Feature element type of the gather.  fp32: a thread's 4 channels are one 128-bit load (float4).  bf16 storage
+// (VFA_FLAG_BF16_FEATURES): one 64-bit load (4 x bf16), widened to fp32 in registers -- half the gather bytes and half
+// the registers per tap in flight; pooling, split and contraction stay fp32 / 3xTF32.
+//   ldg_if<TX>:  @(w != 0) load the tap TX texels to the right of ptr; the slot keeps its old (finite) contents when
+//                the tap is off.  With VFA_L1_PREFETCH the same predicate also prefetches the texel's next 128-byte
+//                line into L1 (what the same rows load for the next K chunk); measured slower, off by default.
+//   fma4:        acc += w * slot on 4 channels with two packed fp32x2 FMAs (sm_100), predicated on w != 0 so a stale
+//                Inf / NaN left in an unused slot can never leak in.
 #ifndef VFA_L1_PREFETCH
 #define VFA_L1_PREFETCH 0
 #endif
-template <int IMM>
-__device__ __forceinline__ void ldg_if(float4& v, const float* ptr, float w) {
+template <bool BF16>
+struct Feat;
+
+template <>
+struct Feat<false> {
+  using Slot = float4;
+  static constexpr int ES = 4;      // bytes per element
+  __device__ static __forceinline__ Slot zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  template <int TX>
+  __device__ static __forceinline__ void ldg_if(Slot& v, const uint8_t* ptr, float w) {
 #if VFA_L1_PREFETCH
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.neu.f32 p, %5, 0f00000000;\n\t"
-      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t"
-      "@p prefetch.global.L1 [%4+%7];\n\t"
-      "}\n"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "l"(ptr), "f"(w), "n"(IMM), "n"(IMM + KCH * 4));
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.neu.f32 p, %5, 0f00000000;\n\t"
+        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t"
+        "@p prefetch.global.L1 [%4+%7];\n\t"
+        "}\n"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "l"(ptr), "f"(w), "n"(TX * CH * ES), "n"(TX * CH * ES + KCH * ES));
 #else
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.neu.f32 p, %5, 0f00000000;\n\t"
-      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t"
-      "}\n"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "l"(ptr), "f"(w), "n"(IMM));
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.neu.f32 p, %5, 0f00000000;\n\t"
+        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+%6];\n\t"
+        "}\n"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "l"(ptr), "f"(w), "n"(TX * CH * ES));
 #endif
-}
-__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
-  if (w != 0.f) {        // predicated, so a stale Inf/NaN left in an unused slot can never leak in
-    const float2 w2 = make_float2(w, w);          // packed fp32x2 FMA (sm_100): 2 instead of 4 issue slots
-    const float2 lo = __ffma2_rn(w2, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
-    const float2 hi = __ffma2_rn(w2, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
-    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
   }
-}
+  __device__ static __forceinline__ void fma4(float4& acc, float w, const Slot& v) {
+    if (w != 0.f) {
+      const float2 w2 = make_float2(w, w);
+      const float2 lo = __ffma2_rn(w2, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
+      const float2 hi = __ffma2_rn(w2, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
+      acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+  }
+};
+
+template <>
+struct Feat<true> {
+  using Slot = uint2;               // 4 x bf16
+  static constexpr int ES = 2;
+  __device__ static __forceinline__ Slot zero() { return make_uint2(0u, 0u); }
+  template <int TX>
+  __device__ static __forceinline__ void ldg_if(Slot& v, const uint8_t* ptr, float w) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.neu.f32 p, %3, 0f00000000;\n\t"
+        "@p ld.global.nc.v2.b32 {%0, %1}, [%2+%4];\n\t"
+        "}\n"
+        : "+r"(v.x), "+r"(v.y)
+        : "l"(ptr), "f"(w), "n"(TX * CH * ES));
+  }
+  __device__ static __forceinline__ void fma4(float4& acc, float w, const Slot& v) {
+    if (w != 0.f) {
+      const float2 w2 = make_float2(w, w);      // bf16 -> fp32 is a 16-bit shift (exact)
+      const float2 a = make_float2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+      const float2 c = make_float2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+      const float2 lo = __ffma2_rn(w2, a, make_float2(acc.x, acc.y));
+      const float2 hi = __ffma2_rn(w2, c, make_float2(acc.z, acc.w));
+      acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+  }
+};
 
 // Store one item's pooled values as the tf32 hi/lo pair into the swizzled operand tiles.
 __device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const float4& acc) {
@@ -392,8 +424,8 @@ struct ProducerCtx {
   uint8_t* smem;
   SmemTail* tail;
   const RowDesc* wdesc;     // this warp's recipes (shared memory), rows of round r at [4*r .. 4*r+3]
-  const float* feat;        // [fh, fw, CH] map of this (frame, view, scale), + this thread's channel offset j*4
-  size_t row_stride;        // fw * CH
+  const uint8_t* feat;      // [fh, fw, CH] map of this (frame, view, scale), + this thread's channel offset (bytes)
+  size_t row_stride;        // fw * CH * element size (bytes)
   uint32_t a_off[ROUNDS];   // swizzled byte offset of (this thread's row of round r, its 16-byte chunk) in an A tile
   int lane, q;
   bool no_gather;           // debug knock-out
@@ -414,30 +446,32 @@ __device__ __forceinline__ void finish_item(const ProducerCtx& c, int round, uin
 
 // Layers where every row of the warp has at most TxT taps (T = 2: the common case at strides 16 and 32; T = 3:
 // most of stride 8): 32 items, DEPTH in flight, tap weights precomputed in the recipe.
-template <int T, int DEPTH>
+template <int T, int DEPTH, bool BF16>
 __device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, Pipe& pipe) {
+  using F = Feat<BF16>;
+  using Slot = typename F::Slot;
   constexpr int ITEMS = (CH / KCH) * ROUNDS;
   static_assert(ROUNDS % DEPTH == 0, "DEPTH must divide ROUNDS");
   static_assert(ITEMS % ROUNDS == 0, "");
   const RowDesc* dq = c.wdesc + c.q;          // this quarter-warp's row of round 0; round r is dq[4*r]
-  const float* feat = c.feat;
+  const uint8_t* feat = c.feat;
   const size_t rs = c.row_stride;
-  float4 buf[DEPTH][T][T];
+  Slot buf[DEPTH][T][T];
 #pragma unroll
   for (int d = 0; d < DEPTH; ++d)
 #pragma unroll
     for (int ty = 0; ty < T; ++ty)
 #pragma unroll
-      for (int tx = 0; tx < T; ++tx) buf[d][ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto issue = [&](float4(&v)[T][T], int round, int cc) {
+      for (int tx = 0; tx < T; ++tx) buf[d][ty][tx] = F::zero();
+  auto issue = [&](Slot(&v)[T][T], int round, int cc) {
     if (c.no_gather) return;
     const RowDesc& d = dq[4 * round];
-    const float* r = feat + (d.base + cc * KCH);
+    const uint8_t* r = feat + (size_t)(d.base + cc * KCH) * F::ES;
 #pragma unroll
     for (int ty = 0; ty < T; ++ty) {
-      ldg_if<0>(v[ty][0], r, d.w9[ty * 3 + 0]);
-      ldg_if<CH * 4>(v[ty][1], r, d.w9[ty * 3 + 1]);
-      if (T > 2) ldg_if<2 * CH * 4>(v[ty][T - 1], r, d.w9[ty * 3 + 2]);
+      F::template ldg_if<0>(v[ty][0], r, d.w9[ty * 3 + 0]);
+      F::template ldg_if<1>(v[ty][1], r, d.w9[ty * 3 + 1]);
+      if (T > 2) F::template ldg_if<2>(v[ty][T - 1], r, d.w9[ty * 3 + 2]);
       r += rs;
     }
   };
@@ -457,7 +491,7 @@ __device__ __forceinline__ void produce_layer_small(const ProducerCtx& c, Pipe& 
 #pragma unroll
         for (int ty = 0; ty < T; ++ty)
 #pragma unroll
-          for (int tx = 0; tx < T; ++tx) fma4(accr[d], rd.w9[ty * 3 + tx], buf[d][ty][tx]);
+          for (int tx = 0; tx < T; ++tx) F::fma4(accr[d], rd.w9[ty * 3 + tx], buf[d][ty][tx]);
       }
 #pragma unroll
       for (int d = 0; d < DEPTH; ++d) {
@@ -485,19 +519,22 @@ struct WinPos {
   int cc, rd, sy, sx;
 };
 
-__device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx, uint32_t nwy, Pipe* pipe_io) {
+template <bool BF16>
+__device__ __forceinline__ void produce_layer_win(const ProducerCtx& c, uint32_t nwx, uint32_t nwy, Pipe* pipe_io) {
+  using F = Feat<BF16>;
+  using Slot = typename F::Slot;
   Pipe pipe = *pipe_io;
-  float4 bufA[3][3], bufB[3][3];      // bufB is dead (eliminated) when WINDOW_DOUBLE_BUFFER is false
+  Slot bufA[3][3], bufB[3][3];      // bufB is dead (eliminated) when WINDOW_DOUBLE_BUFFER is false
   float wA[3][3], wB[3][3];
 #pragma unroll
   for (int ty = 0; ty < 3; ++ty)
 #pragma unroll
     for (int tx = 0; tx < 3; ++tx) {
-      bufA[ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (WINDOW_DOUBLE_BUFFER) bufB[ty][tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bufA[ty][tx] = F::zero();
+      if (WINDOW_DOUBLE_BUFFER) bufB[ty][tx] = F::zero();
     }
 
-  auto issue = [&](float4(&v)[3][3], float(&w)[3][3], const WinPos& p) {
+  auto issue = [&](Slot(&v)[3][3], float(&w)[3][3], const WinPos& p) {
     const RowDesc& d = c.wdesc[p.rd * 4 + c.q];
     const bool single = (((nwx >> (8 * p.rd)) & 255u) == 1u) && (((nwy >> (8 * p.rd)) & 255u) == 1u);   // warp-uniform
     if (single) {            // all 4 boxes of this round fit one 3x3 window: precomputed products
@@ -526,12 +563,13 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
         for (int tx = 0; tx < 3; ++tx) w[ty][tx] = wy[ty] * wx[tx];
     }
     if (c.no_gather) return;
-    const float* r = c.feat + d.base + (size_t)(3 * p.sy) * c.row_stride + (size_t)(3 * p.sx) * CH + p.cc * KCH;
+    const uint8_t* r = c.feat + (size_t)(3 * p.sy) * c.row_stride +
+                       ((size_t)d.base + (size_t)(3 * p.sx) * CH + p.cc * KCH) * F::ES;
 #pragma unroll
     for (int ty = 0; ty < 3; ++ty) {
-      ldg_if<0>(v[ty][0], r, w[ty][0]);
-      ldg_if<CH * 4>(v[ty][1], r, w[ty][1]);
-      ldg_if<2 * CH * 4>(v[ty][2], r, w[ty][2]);
+      F::template ldg_if<0>(v[ty][0], r, w[ty][0]);
+      F::template ldg_if<1>(v[ty][1], r, w[ty][1]);
+      F::template ldg_if<2>(v[ty][2], r, w[ty][2]);
       r += c.row_stride;
     }
   };
@@ -548,11 +586,11 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
     return p;
   };
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto consume = [&](const float4(&v)[3][3], const float(&w)[3][3], const WinPos& p) {
+  auto consume = [&](const Slot(&v)[3][3], const float(&w)[3][3], const WinPos& p) {
 #pragma unroll
     for (int ty = 0; ty < 3; ++ty)
 #pragma unroll
-      for (int tx = 0; tx < 3; ++tx) fma4(acc, w[ty][tx], v[ty][tx]);
+      for (int tx = 0; tx < 3; ++tx) F::fma4(acc, w[ty][tx], v[ty][tx]);
     if (p.sx + 1 == (int)((nwx >> (8 * p.rd)) & 255u) && p.sy + 1 == (int)((nwy >> (8 * p.rd)) & 255u))
       finish_item(c, p.rd, c.a_off[0] + (uint32_t)p.rd * ((TILE_M / ROUNDS) * 128u), acc, pipe);
   };
@@ -585,6 +623,7 @@ __device__ __noinline__ void produce_layer_win(const ProducerCtx c, uint32_t nwx
   *pipe_io = pipe;
 }
 
+template <bool BF16>
 __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const UmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // align by pointer arithmetic on the __shared__ array (keeps the shared address space visible to the compiler)
@@ -651,7 +690,6 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
             const int st = it % STAGES;
             mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
             uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
-            TRACE(3, 1024 + it);
             if (a.variant & 8) {   // debug knock-out: no weight traffic
               mbar_arrive(&tail->full[st]);
             } else {
@@ -688,10 +726,8 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           tc_fence_after();
           for (int cc = 0; cc < CHUNKS_PER_LAYER; ++cc, ++it) {
             const int st = it % STAGES;
-            TRACE(0, 2 * it);
             mbar_wait(&tail->full[st], (it / STAGES) & 1);
             if (PAIR) mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
-            TRACE(0, 2 * it + 1);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
             const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
@@ -735,8 +771,9 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
     for (int v = v_begin; v < v_end; ++v) {
       for (int s = 0; s < p.S; ++s) {
         const ScaleConst sc = p.sc[s];
-        c.feat = p.feats[s] + ((size_t)(b * p.V + v) * sc.fh * sc.fw) * CH + (lane & 7) * 4;
-        c.row_stride = (size_t)sc.fw * CH;
+        c.feat = reinterpret_cast<const uint8_t*>(p.feats[s]) +
+                 (((size_t)(b * p.V + v) * sc.fh * sc.fw) * CH + (lane & 7) * 4) * Feat<BF16>::ES;
+        c.row_stride = (size_t)sc.fw * CH * Feat<BF16>::ES;
         for (int n = 0; n < p.nl; ++n) {
           __syncwarp();                              // everyone is done with the previous layer's recipes
           int nx = 0, ny = 0;
@@ -788,11 +825,11 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           }
           __syncwarp();
           if (extent <= 2)
-            produce_layer_small<2, DEPTH_2X2>(c, pipe);
+            produce_layer_small<2, DEPTH_2X2, BF16>(c, pipe);
           else if (extent <= 3)
-            produce_layer_small<3, DEPTH_3X3>(c, pipe);
+            produce_layer_small<3, (BF16 ? 4 : DEPTH_3X3), BF16>(c, pipe);
           else
-            produce_layer_win(c, nwx, nwy, &pipe);
+            produce_layer_win<BF16>(c, nwx, nwy, &pipe);
         }
       }
     }
@@ -811,7 +848,6 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
       const int s = vs % p.S;
       for (int n = 0; n < p.nl; ++n, ++drain) {
         mbar_wait_sleep(&tail->acc_full, drain & 1);
-        if (e == 0 && lane == 0) TRACE(3, 2 * drain);
         tc_fence_after();
         const bool first_layer = (n == 0), last_layer = (n == p.nl - 1);
         // pass 1: fold this layer's partial into the fp32 running sum kept in TMEM columns [256, 512)
@@ -834,7 +870,6 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           if (PAIR && cta_rank != 0) mbar_arrive_remote(&tail->acc_empty, 0);
           else mbar_arrive(&tail->acc_empty);
         }
-        if (e == 0 && lane == 0) TRACE(3, 2 * drain + 1);
         if (last_layer) {
           // pass 2 (overlaps the next layer's MMAs): + bias, ReLU (vfa_op.py:123-124), then the sum over scales and
           // views (vfanet.py:79, :82) straight into the [B, C, L*W] output
@@ -902,22 +937,19 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, uint32_
   if (!(flags & VFA_FLAG_WEIGHTS_PREPARED)) {
     if (int rc = prep_weights_umma(p, d_weight, ws, st)) return rc;
   }
+  const bool bf16 = (flags & VFA_FLAG_BF16_FEATURES) != 0;
   static bool attr_set = false;
   if (!attr_set) {
-    VFA_CUDA(cudaFuncSetAttribute(aggregate_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(aggregate_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(aggregate_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)SMEM_BYTES));
     attr_set = true;
   }
   UmmaArgs a;
   a.p = p;
   const char* var = getenv("VFA_UMMA_VARIANT");
   a.variant = var ? atoi(var) : 0;
-  a.trace = nullptr;
-  const bool want_trace = getenv("VFA_UMMA_TRACE") != nullptr;   // debugging aid only (allocates, synchronises)
-  a.trace_block = want_trace ? atoi(getenv("VFA_UMMA_TRACE")) : 0;
-  if (want_trace) {
-    VFA_CUDA(cudaMalloc(&a.trace, 4 * TRACE_N * sizeof(long long)));
-    VFA_CUDA(cudaMemset(a.trace, 0, 4 * TRACE_N * sizeof(long long)));
-  }
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   for (int s = 0; s < VFA_MAX_SCALES; ++s) a.wprep[s] = reinterpret_cast<const uint8_t*>(ws) + (s < p.S ? s : 0) * per_scale;
   a.tiles_x = (p.W + TILE_W - 1) / TILE_W;
@@ -939,30 +971,12 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, uint32_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VFA_CUDA(cudaLaunchKernelEx(&cfg, aggregate_fwd_umma_kernel, a));
+  if (bf16)
+    VFA_CUDA(cudaLaunchKernelEx(&cfg, aggregate_fwd_umma_kernel<true>, a));
+  else
+    VFA_CUDA(cudaLaunchKernelEx(&cfg, aggregate_fwd_umma_kernel<false>, a));
   VFA_LAUNCH_CHECK("aggregate_fwd_umma_kernel");
-  if (want_trace) {
-    static long long host[4 * TRACE_N];
-    VFA_CUDA(cudaStreamSynchronize(st));
-    VFA_CUDA(cudaMemcpy(host, a.trace, sizeof(host), cudaMemcpyDeviceToHost));
-    cudaFree(a.trace);
-    FILE* f = fopen("gpurun_out/umma_trace.txt", "w");
-    if (f) {
-      long long t0 = host[0];
-      for (int i = 0; i < 120; ++i) {
-        fprintf(f, "st %3d mma wait %7lld->%7lld | wload %7lld | empty seen/arrive:", i, host[2 * i] - t0,
-                host[2 * i + 1] - t0, host[3 * TRACE_N + 1024 + i] - t0);
-        for (int w = 0; w < 8; ++w)
-          fprintf(f, " %7lld/%7lld", host[TRACE_N + 8 * i + w] - t0, host[2 * TRACE_N + 8 * i + w] - t0);
-        fprintf(f, "\n");
-      }
-      for (int i = 0; i < 15; ++i)
-        fprintf(f, "layer %3d  epi: acc_full seen %8lld  drain done %8lld\n", i, host[3 * TRACE_N + 2 * i] - t0,
-                host[3 * TRACE_N + 2 * i + 1] - t0);
-      fclose(f);
-    }
-  }
-  set_path("umma_tf32x3");
+  set_path(bf16 ? "umma_tf32x3_bf16feat" : "umma_tf32x3");
   return VFA_OK;
 }
 

@@ -116,13 +116,16 @@ def to_channels_last(x: torch.Tensor) -> torch.Tensor:
     """[..., C, H, W] fp32 CUDA -> contiguous [..., H, W, C].  Zero-copy when the tensor already has
     channels-last strides (e.g. produced by a cuDNN conv in torch.channels_last memory format)."""
     _require_cuda(x, 'feature')
-    if x.dtype != torch.float32:
-        raise TypeError(f'features must be float32, got {x.dtype}')
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f'features must be float32 or bfloat16, got {x.dtype}')
     lead = x.shape[:-3]
     Cc, H, W = x.shape[-3:]
     perm = x.movedim(-3, -1)
     if perm.is_contiguous():
         return perm
+    if x.dtype == torch.bfloat16:
+        raise ValueError('bfloat16 features must already be channels-last ([...,C,H,W] with C innermost in memory), '
+                         'e.g. the output of a conv run in torch.channels_last under autocast')
     x4 = x.reshape(-1, Cc, H, W).contiguous()
     return _ChannelsLast.apply(x4).reshape(*lead, H, W, Cc)
 
@@ -135,8 +138,8 @@ def make_shape(feats_cl, n_layers: int) -> _lib.Shape:
     for s, f in enumerate(feats_cl):
         if f.dim() != 5 or f.shape[0] != B or f.shape[1] != V or f.shape[4] != Cc:
             raise ValueError('feature tensors disagree on batch / views / channels')
-        if f.dtype != torch.float32 or not f.is_contiguous():
-            raise ValueError('features must be contiguous float32 [B,V,fH,fW,C]')
+        if f.dtype not in (torch.float32, torch.bfloat16) or f.dtype != feats_cl[0].dtype or not f.is_contiguous():
+            raise ValueError('features must be contiguous float32 (or all bfloat16) [B,V,fH,fW,C]')
         shape.feat_h[s], shape.feat_w[s] = f.shape[2], f.shape[3]
     return shape
 
@@ -170,6 +173,8 @@ def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, w
         out = torch.empty(shape.batch, shape.channels, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
     ws = workspace if workspace is not None else workspace_for(geom, shape, flags, dev)
     f = int(flags) | (_lib.FLAG_WEIGHTS_PREPARED if prepared else 0)
+    if feats_cl[0].dtype == torch.bfloat16:
+        f |= _lib.FLAG_BF16_FEATURES
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().vfa_aggregate_fwd(C.byref(geom), C.byref(shape), table.boxes.data_ptr(),
                                                 _lib.ptr_array([t.data_ptr() for t in feats_cl]),
@@ -259,6 +264,12 @@ def aggregate(feats, table: ProjectionTable, weights, biases, flags: int = 0, ch
         cl.append(f if channels_last else to_channels_last(f))
     for t in list(weights) + list(biases):
         _require_cuda(t, 'collapse parameter')
+    if cl[0].dtype == torch.bfloat16:
+        # bf16 feature storage: inference only (the backward kernels read fp32 maps)
+        if any(t.requires_grad for t in list(cl) + list(weights) + list(biases)) and torch.is_grad_enabled():
+            raise RuntimeError('bfloat16 feature maps are forward-only; run under torch.no_grad() or pass float32')
+        return aggregate_forward_raw([t.contiguous() for t in cl], table, [w.detach() for w in weights],
+                                     [b.detach() for b in biases], flags)
     return _AggregateFn.apply(table.geom, table.boxes, int(flags), S, *cl, *weights, *biases)
 
 
