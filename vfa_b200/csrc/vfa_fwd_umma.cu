@@ -50,7 +50,7 @@ constexpr int B_BYTES = CH * KCH * 4;              // 32 KB per hi / lo slab (wh
 constexpr int B_LOCAL_BYTES = PAIR ? B_BYTES / 2 : B_BYTES;   // rows of the slab this CTA stages
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_LOCAL_BYTES;  // 64 KB (pair) / 96 KB
 #ifndef VFA_PRODUCER_WARPS
-#define VFA_PRODUCER_WARPS 8
+#define VFA_PRODUCER_WARPS 16
 #endif
 constexpr int NUM_PRODUCER_WARPS = VFA_PRODUCER_WARPS;   // 8 (deep per-warp prefetch) or 16 (more warps, shallower)
 constexpr int ROUNDS = TILE_M / (4 * NUM_PRODUCER_WARPS);  // items (4 cells each) per producer warp and K chunk
@@ -825,9 +825,9 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           }
           __syncwarp();
           if (extent <= 2)
-            produce_layer_small<2, DEPTH_2X2, BF16>(c, pipe);
+            produce_layer_small<2, (BF16 ? ROUNDS : DEPTH_2X2), BF16>(c, pipe);
           else if (extent <= 3)
-            produce_layer_small<3, (BF16 ? 4 : DEPTH_3X3), BF16>(c, pipe);
+            produce_layer_small<3, (BF16 ? ROUNDS : DEPTH_3X3), BF16>(c, pipe);
           else
             produce_layer_win<BF16>(c, nwx, nwy, &pipe);
         }
