@@ -300,7 +300,7 @@ struct UmmaArgs {
   int tiles_padded;    // cell tiles, rounded up to a multiple of the cluster size
   int tiles_x;         // tiles are TILE_H x TILE_W blocks of BEV cells: tile -> (tile / tiles_x, tile % tiles_x)
   int views_per_group;
-  int variant;         // debug bits: 1 = hi*hi only, 2 = no gather loads, 4 = no MMA, 8 = no weight loads
+  int variant;         // debug bits: 1 = hi*hi only, 2 = no gather loads, 4 = no MMA, 8 = no weight loads, 16 = no output pass, 32 = no drain
 };
 
 // ---- pooling producers ----------------------------------------------------------------------------------------
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
         const bool first_layer = (n == 0), last_layer = (n == p.nl - 1);
         // pass 1: fold this layer's partial into the fp32 running sum kept in TMEM columns [256, 512)
 #pragma unroll 1
-        for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
+        for (int c0 = col_begin; c0 < col_begin + CH / 2 && !(a.variant & 32); c0 += 32) {
           float acc[32], pre[32];
           tc_ld32(lane_addr + c0, acc);
           if (!first_layer) tc_ld32(lane_addr + CH + c0, pre);
@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
           if (PAIR && cta_rank != 0) mbar_arrive_remote(&tail->acc_empty, 0);
           else mbar_arrive(&tail->acc_empty);
         }
-        if (last_layer) {
+        if (last_layer && !(a.variant & 16)) {
           // pass 2 (overlaps the next layer's MMAs): + bias, ReLU (vfa_op.py:123-124), then the sum over scales and
           // views (vfanet.py:79, :82) straight into the [B, C, L*W] output
 #pragma unroll 1
@@ -886,13 +886,24 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
                 const int v_cur = v_begin + vs / p.S;
                 p.mask[((((size_t)b * p.V + v_cur) * p.S + s) * (CH / 32) + c0 / 32) * p.LW + cell] = bits;
               }
-              if (a.n_groups == 1 && vs == 0) {
+              float* o = outp + (size_t)c0 * p.LW;
+              if (a.n_groups == 1) {
+                // this CTA is the only writer of its output tile: first (view, scale) stores, later ones add with a
+                // plain read-modify-write (L2-resident).  Atomics are kept for the view-split case only: 131 M
+                // RED.ADD per frame ran into the L2 atomic-unit throughput (~95 G/s) and cost 1.4 ms of a 2.5 ms frame.
+                if (vs == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) outp[(size_t)(c0 + i) * p.LW] = fmaxf(y[i] + tail->bias[s][c0 + i], 0.f);
+                  for (int i = 0; i < 32; ++i) o[(size_t)i * p.LW] = fmaxf(y[i] + tail->bias[s][c0 + i], 0.f);
+                } else {
+                  float prev[32];
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) prev[i] = o[(size_t)i * p.LW];
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) o[(size_t)i * p.LW] = prev[i] + fmaxf(y[i] + tail->bias[s][c0 + i], 0.f);
+                }
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  atomicAdd(outp + (size_t)(c0 + i) * p.LW, fmaxf(y[i] + tail->bias[s][c0 + i], 0.f));
+                for (int i = 0; i < 32; ++i) atomicAdd(o + (size_t)i * p.LW, fmaxf(y[i] + tail->bias[s][c0 + i], 0.f));
               }
             }
           }
