@@ -1,24 +1,32 @@
 // Fused aggregation forward on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32 with the
 // accumulator in TMEM, 3xTF32 operand splitting for fp32-level accuracy.   C = 256 channels.
 //
-// One CTA (448 threads, 1 per SM) owns a tile of 128 consecutive BEV cells of one frame (= the 128 TMEM lanes)
-// and a group of views.  For every (view, scale) it runs a K loop over (height layer n, 32-channel chunk):
+// CTAs run as pairs (cluster of 2, tcgen05 cta_group::2, M = 256 cells across the pair).  One CTA (896 threads,
+// 1 per SM) owns an 8 x 16 block of BEV cells of one frame (= its 128 TMEM lanes) and a group of views.  For every
+// (view, scale) it runs a K loop over (height layer n, 32-channel chunk), 3 shared-memory stages of 64 KB:
 //
-//   warp 0      weight loader   one cp.async.bulk (UBLKCP) per stage: the pre-split, pre-swizzled [256 x 32]
-//                               hi and lo slabs of collapse.weight (64 KB, contiguous in the prepared layout)
-//   warp 1      MMA issuer      one thread: per stage 4 k-steps x {A_hi*B_hi, A_lo*B_hi, A_hi*B_lo}
-//                               tcgen05.mma.cta_group::1.kind::tf32, M=128 N=256 K=8, D in TMEM cols [0,256)
-//   warps 2-9   pool producers  derive the box taps (shared device function with the parity-checked table
-//                               kernel), gather 4 channels per thread with 128-bit loads from the channels-last
-//                               map (8 lanes = one 128 B row of a texel; 4 cells per warp instruction), split
-//                               into tf32 hi/lo and write the K-major SWIZZLE_128B operand tile in shared memory
-//   warps 10-13 epilogue        tcgen05.ld the accumulator, + bias, ReLU, add to the running BEV sum kept in
-//                               TMEM cols [256,512); after the last (view, scale) write [B,C,L,W] once
+//   warp 0       weight loader   per stage two cp.async.bulk (UBLKCP) of this CTA's half (128 rows) of the pre-split,
+//                                pre-swizzled hi and lo slabs of collapse.weight; the MMA reads the other half from
+//                                the peer CTA's shared memory
+//   warp 1       leader: MMA issuer, one thread, per stage 4 k-steps x {A_lo*B_hi, A_hi*B_lo, A_hi*B_hi}
+//                                tcgen05.mma.cta_group::2.kind::tf32, M=256 N=256 K=8, D in TMEM cols [0,256);
+//                                tcgen05.commit (multicast) frees the stage / publishes the layer in both CTAs
+//                follower: relays "my stage is full" to the leader with a remote mbarrier arrive
+//   warps 4-19   pool producers  build per-(cell, layer) gather recipes in shared memory (shared device function with
+//                                the parity-checked table kernel), gather 4 channels per thread with predicated
+//                                128-bit loads from the channels-last map (8 lanes = one 128 B row of a texel;
+//                                4 adjacent cells per warp instruction), split into tf32 hi/lo and write the
+//                                K-major SWIZZLE_128B operand tile
+//   warps 20-27  epilogue        after every height layer: tcgen05.ld the accumulator and fold it into an fp32
+//                                running sum in TMEM cols [256,512) (the tensor-core accumulator truncates, so
+//                                only 32 k-steps are chained in it); after the last layer + bias, ReLU, add into
+//                                [B,C,L,W] (read-modify-write; atomics when views are split over CTAs)
 //
-// mbarriers: full[stage] (8 producer warps + loader tx), empty[stage] (tcgen05.commit), acc_full (commit),
-// acc_empty (epilogue).  The [L*W, C*nl] matrix of the reference (vfa_op.py:118-120) only ever exists as
-// 16 KB operand tiles; the collapse (vfa_op.py:123) is the tensor-core contraction; ReLU and the sums over
-// scales and views (vfa_op.py:124, vfanet.py:79-82) are the epilogue.
+// mbarriers: full[stage] (16 producer warps + loader tx), empty[stage] (tcgen05.commit), peer_full[stage] (relay),
+// acc_full (commit), acc_empty (epilogue warps of both CTAs).  The [L*W, C*nl] matrix of the reference
+// (vfa_op.py:118-120) only ever exists as 16 KB operand tiles; the collapse (vfa_op.py:123) is the tensor-core
+// contraction; ReLU and the sums over scales and views (vfa_op.py:124, vfanet.py:79-82) are the epilogue.
+// Debug switches (environment, read at launch): VFA_UMMA_VARIANT knock-out bits, see UmmaArgs::variant.
 #include <stdlib.h>
 
 #include "vfa_common.cuh"
