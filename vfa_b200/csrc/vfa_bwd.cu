@@ -355,6 +355,127 @@ __global__ void __launch_bounds__(256) scatter_g_kernel(const ScatterParams q) {
   }
 }
 
+// Tile-local version of the scatter: a CTA takes a compact 8 x 16 block of BEV cells of one (scale, layer) and 64
+// output channels.  Neighbouring cells pool from overlapping texel windows (4x / 7x / 15x overlap at strides 8 / 16 /
+// 32 on the MultiviewC rig), so the contributions are first accumulated in shared memory over the block's bounding
+// texel region and only the region is flushed with global atomics -- the L2 atomic units (~95 G fp32 adds/s) were the
+// whole cost of the untiled kernel.  Blocks whose region does not fit (voxels next to a camera) scatter directly.
+constexpr int SC_TW = 16, SC_TH = 8, SC_CELLS = SC_TW * SC_TH;     // cells per CTA
+constexpr int SC_CH = 64;                                          // channels per CTA (2 per lane)
+constexpr int SC_RMAX = 448;                                       // texels of the shared-memory region (112 KB)
+
+__global__ void __launch_bounds__(256) scatter_g_tiled_kernel(const ScatterParams q, int tiles_x) {
+  const AggParams& p = q.p;
+  extern __shared__ __align__(16) float sacc[];                    // [SC_RMAX][SC_CH]
+  __shared__ BoxTaps taps[SC_CELLS];
+  __shared__ int cells[SC_CELLS];
+  __shared__ int rb[4];                                            // region x0, y0, x1, y1 (inclusive-exclusive)
+  __shared__ float bsum[8][SC_CH];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.y / p.nl, n = blockIdx.y % p.nl;
+  const int c0 = blockIdx.z * SC_CH + lane * 2;
+  const ScaleConst sc = p.sc[s];
+  const int ty0 = (blockIdx.x / tiles_x) * SC_TH, tx0 = (blockIdx.x % tiles_x) * SC_TW;
+  if (tid == 0) {
+    rb[0] = rb[1] = 1 << 30;
+    rb[2] = rb[3] = -1;
+  }
+  __syncthreads();
+  if (tid < SC_CELLS) {
+    const int y = ty0 + tid / SC_TW, x = tx0 + tid % SC_TW;
+    BoxTaps t;
+    t.x0 = t.y0 = t.nx = t.ny = 0;
+    t.wx_first = t.wx_last = t.wy_first = t.wy_last = t.wy_mid = 0.f;
+    int cell = -1;
+    if (y < p.L && x < p.W) {
+      cell = y * p.W + x;
+      t = derive_taps(reinterpret_cast<const float4*>(p.boxes)[((size_t)q.v * p.nl + n) * p.LW + cell], sc);
+    }
+    taps[tid] = t;
+    cells[tid] = cell;
+    if (t.nx > 0) {
+      atomicMin(&rb[0], t.x0);
+      atomicMin(&rb[1], t.y0);
+      atomicMax(&rb[2], t.x0 + t.nx);
+      atomicMax(&rb[3], t.y0 + t.ny);
+    }
+  }
+  __syncthreads();
+  const int rx0 = rb[0], ry0 = rb[1], rw = rb[2] - rb[0], rh = rb[3] - rb[1];
+  const bool any = rb[2] > 0;
+  const bool local = any && rw * rh <= SC_RMAX;
+  if (local) {
+    for (int i = tid; i < rw * rh * SC_CH / 4; i += 256) reinterpret_cast<float4*>(sacc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+
+  const bool chan_ok = c0 < p.C;
+  float2 bias_acc = make_float2(0.f, 0.f);
+  for (int i = 0; i < SC_CELLS / 8; ++i) {
+    const int r = warp * (SC_CELLS / 8) + i;
+    const int cell = cells[r];
+    if (cell < 0 || !chan_ok) continue;
+    const uint32_t word = p.mask[((((size_t)q.b * p.V + q.v) * p.S + s) * ((p.C + 31) / 32) + (c0 >> 5)) * p.LW + cell];
+    const uint32_t bits = (word >> (c0 & 31)) & 3u;
+    const float2 gv = __ldg(reinterpret_cast<const float2*>(q.gt + (size_t)cell * p.C + c0));
+    const float g0 = (bits & 1) ? gv.x : 0.f, g1 = (bits & 2) ? gv.y : 0.f;
+    bias_acc.x += g0;
+    bias_acc.y += g1;
+    const BoxTaps t = taps[r];
+    if (t.nx == 0 || (g0 == 0.f && g1 == 0.f)) continue;
+    if (local) {
+      float* base = sacc + ((size_t)(t.y0 - ry0) * rw + (t.x0 - rx0)) * SC_CH + lane * 2;
+      for (int ty = 0; ty < t.ny; ++ty) {
+        const float wy = tap_wy(t, ty);
+        for (int tx = 0; tx < t.nx; ++tx) {
+          const float w = wy * tap_wx(t, tx);
+          float* d = base + ((size_t)ty * rw + tx) * SC_CH;
+          atomicAdd(d, w * g0);
+          atomicAdd(d + 1, w * g1);
+        }
+      }
+    } else {
+      float* base = q.gs + q.gs_off[s] + (((size_t)t.y0 * sc.fw + t.x0) * p.nl + n) * p.C + c0;
+      const size_t tx_stride = (size_t)p.nl * p.C, ty_stride = (size_t)sc.fw * p.nl * p.C;
+      for (int ty = 0; ty < t.ny; ++ty) {
+        const float wy = tap_wy(t, ty);
+        for (int tx = 0; tx < t.nx; ++tx) {
+          const float w = wy * tap_wx(t, tx);
+          atomicAdd(reinterpret_cast<float2*>(base + ty * ty_stride + tx * tx_stride), make_float2(w * g0, w * g1));
+        }
+      }
+    }
+  }
+  // dBias_s[o] = sum over (frame, view, cell) of g: layer 0 only so every cell counts once; one atomic per CTA channel
+  if (n == 0 && q.gbias[s] != nullptr) {
+    bsum[warp][lane * 2] = bias_acc.x;
+    bsum[warp][lane * 2 + 1] = bias_acc.y;
+  }
+  __syncthreads();
+  if (n == 0 && q.gbias[s] != nullptr && tid < SC_CH) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += bsum[w][tid];
+    const int o = blockIdx.z * SC_CH + tid;
+    if (o < p.C && t != 0.f) atomicAdd(q.gbias[s] + o, t);
+  }
+  if (local) {
+    // flush the region: 16 float4 per texel, coalesced vector atomics
+    const int quads = SC_CH / 4;
+    for (int i = tid; i < rw * rh * quads; i += 256) {
+      const int tex = i / quads, qd = i % quads;
+      const float4 v4 = reinterpret_cast<const float4*>(sacc)[i];
+      if (v4.x == 0.f && v4.y == 0.f && v4.z == 0.f && v4.w == 0.f) continue;
+      const int o = blockIdx.z * SC_CH + qd * 4;
+      if (o >= p.C) continue;
+      const int ty = ry0 + tex / rw, tx = rx0 + tex % rw;
+      float* d = q.gs + q.gs_off[s] + (((size_t)ty * sc.fw + tx) * p.nl + n) * p.C + o;
+      atomicAdd(reinterpret_cast<float4*>(d), v4);
+    }
+  }
+}
+
 // dWr[n][o][c] -> dW[o, c*nl + n]
 __global__ void __launch_bounds__(256) unprep_dweight_kernel(const float* __restrict__ dwr, float* __restrict__ dw, int C,
                                                              int nl) {
@@ -426,8 +547,21 @@ static int launch_bwd_feature_side(AggParams p, const float* const* d_weight, co
       VFA_CUDA(cudaMemsetAsync(gs, 0, gs_elems * sizeof(float), st));
       q.b = b;
       q.v = v;
-      fs::scatter_g_kernel<<<sblocks, 256, 0, st>>>(q);
-      VFA_LAUNCH_CHECK("scatter_g_kernel");
+      if (getenv("VFA_BWD_UNTILED") != nullptr) {
+        fs::scatter_g_kernel<<<sblocks, 256, 0, st>>>(q);
+        VFA_LAUNCH_CHECK("scatter_g_kernel");
+      } else {
+        const int tiles_x = (p.W + fs::SC_TW - 1) / fs::SC_TW, tiles_y = (p.L + fs::SC_TH - 1) / fs::SC_TH;
+        const size_t smem = (size_t)fs::SC_RMAX * fs::SC_CH * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+          VFA_CUDA(cudaFuncSetAttribute(fs::scatter_g_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr_set = true;
+        }
+        dim3 grid(tiles_x * tiles_y, p.S * p.nl, (p.C + fs::SC_CH - 1) / fs::SC_CH);
+        fs::scatter_g_tiled_kernel<<<grid, 256, smem, st>>>(q, tiles_x);
+        VFA_LAUNCH_CHECK("scatter_g_tiled_kernel");
+      }
       for (int s = 0; s < p.S; ++s) {
         const int T = p.sc[s].fh * p.sc[s].fw;
         const float* gs_s = gs + q.gs_off[s];
