@@ -1,0 +1,48 @@
+"""Drop-in check at the network level (build container only: needs the reference tree, absent on the GPU box):
+the reference `VFANet` constructed on top of `vfa_b200.compat.install()` has exactly the reference's state dict."""
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'vfa')), reason='reference tree not present')
+
+
+def _import_vfanet(with_compat):
+    for n in [k for k in sys.modules if k == 'vfa' or k.startswith('vfa.')]:
+        del sys.modules[n]
+    for n in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.patches', 'matplotlib.gridspec'):
+        sys.modules.setdefault(n, types.ModuleType(n))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    if with_compat:
+        import vfa_b200.compat as compat
+        compat.install()
+    import vfa.model.vfanet as vfanet
+    return vfanet
+
+
+def test_reference_vfanet_builds_on_the_drop_in_module():
+    import vfa_b200
+    args = SimpleNamespace(data='MultiviewC', image_size=(720, 1280))
+    ref = _import_vfanet(False).VFANet(args, 'resnet18', 160, (25, 25, 32), 360, '3D', False)
+    ref_sd = {k: (tuple(v.shape), v.dtype) for k, v in ref.state_dict().items()}
+    net_mod = _import_vfanet(True)
+    ours = net_mod.VFANet(args, 'resnet18', 160, (25, 25, 32), 360, '3D', False)
+    assert isinstance(ours.vfa8, vfa_b200.VFA) and isinstance(ours.vfa32, vfa_b200.VFA)
+    our_sd = {k: (tuple(v.shape), v.dtype) for k, v in ours.state_dict().items()}
+    assert our_sd == ref_sd
+    # a reference checkpoint loads into the drop-in network and back, key for key
+    missing, unexpected = ours.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing and not unexpected
+    for k in ('vfa8.collapse.weight', 'vfa16.z_corners', 'vfa32.corners_offset'):
+        assert torch.equal(ours.state_dict()[k], ref.state_dict()[k])
+    # and the optimiser sees the collapse parameters (reference train.py:256)
+    names = {n for n, _ in ours.named_parameters()}
+    assert {'vfa8.collapse.weight', 'vfa8.collapse.bias', 'vfa16.collapse.weight', 'vfa32.collapse.bias'} <= names
+    for n in [k for k in sys.modules if k == 'vfa' or k.startswith('vfa.')]:
+        del sys.modules[n]
