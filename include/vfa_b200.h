@@ -7,7 +7,8 @@
  *
  * Conventions
  *   - every pointer named d_* is a DEVICE pointer owned by the caller; the library never allocates, frees,
- *     synchronises the device or keeps global state other than the thread-local last-error string;
+ *     synchronises the device or keeps global state other than the thread-local last-error string (and, for
+ *     vfa_aggregate_bwd only, one lazily created cuBLAS handle used for its two plain SGEMMs);
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued on it;
  *   - every function returns VFA_OK (0) or a negative vfa_status_t; vfa_last_error() describes the failure;
  *   - tensors are dense, row-major in the index order written in the comment.
