@@ -5,7 +5,7 @@
     python bench.py --impl reference ...                     # the reference algorithm on the box's host cores
 
 One "step" = one pass of the hot path over one batch of synthetic frames:
-    projection table (1 launch) + weight re-layout (3 launches) + fused gather/collapse/ReLU/sum kernel (1 launch).
+    projection table (1 launch) + weight re-layout (3) + tap-recipe table (1) + fused gather/collapse/ReLU/sum kernel (1).
 Default workload: MultiviewC-shaped (7 views, 1280x720 source, stride-8/16/32 maps 90x160 / 45x80 / 23x40, C = 256,
 156x156x5 voxel grid = the shipped config-of-record of "37.5 m x 37.5 m"), B frames per GPU.
 Multi-GPU = batch data parallel (frames are independent: no data-path collective, weak scaling).
@@ -271,7 +271,7 @@ def main():
     for _ in range(max(3, args.warmup)):
         step()
     path = vfa_b200.last_kernel_path()
-    launches_per_step = 5        # table_build + 3 x prep_weight + fused aggregate kernel (memsets not counted)
+    launches_per_step = 6        # table_build + 3 x prep_weight + tap-recipe table + fused aggregate kernel (memsets not counted)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()

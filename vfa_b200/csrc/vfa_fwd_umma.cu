@@ -301,12 +301,44 @@ __global__ void __launch_bounds__(256) prep_weight_umma_kernel(const float* __re
   }
 }
 
+// Per-(view, scale, layer, cell) gather recipe in its compact global form (32 bytes), built by a small pre-pass so the
+// hot kernel carries no float64 arithmetic (the fp64 pipe throttled the producers: 15 % of their stall samples).
+struct __align__(16) TapRec {
+  int xy;          // x0 | y0 << 16
+  int nxy;         // nx | ny << 16   (0 = not visible)
+  float wx_first, wx_last, wy_first, wy_last, wy_mid;
+  int pad;
+};
+
+__global__ void __launch_bounds__(256) taps_table_kernel(AggParams p, TapRec* __restrict__ recs) {
+  const long long total = (long long)p.V * p.S * p.nl * p.LW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(idx % p.LW);
+    const int n = (int)((idx / p.LW) % p.nl);
+    const int s = (int)((idx / ((long long)p.LW * p.nl)) % p.S);
+    const int v = (int)(idx / ((long long)p.LW * p.nl * p.S));
+    const BoxTaps t = derive_taps(reinterpret_cast<const float4*>(p.boxes)[((size_t)v * p.nl + n) * p.LW + cell], p.sc[s]);
+    TapRec r;
+    r.xy = t.x0 | (t.y0 << 16);
+    r.nxy = t.nx | (t.ny << 16);
+    r.wx_first = t.wx_first;
+    r.wx_last = t.wx_last;
+    r.wy_first = t.wy_first;
+    r.wy_last = t.wy_last;
+    r.wy_mid = t.wy_mid;
+    r.pad = 0;
+    recs[idx] = r;
+  }
+}
+
 struct UmmaArgs {
   AggParams p;
   const uint8_t* wprep[VFA_MAX_SCALES];
   int n_groups;        // view groups (grid.x = tiles_padded * n_groups); > 1 -> atomic accumulation into a zeroed output
   int tiles_padded;    // cell tiles, rounded up to a multiple of the cluster size
   int tiles_x;         // tiles are TILE_H x TILE_W blocks of BEV cells: tile -> (tile / tiles_x, tile % tiles_x)
+  const TapRec* recs;  // [V][S][nl][LW] gather recipes (taps_table_kernel)
   int views_per_group;
   int variant;         // debug bits: 1 = hi*hi only, 2 = no gather loads, 4 = no MMA, 8 = no weight loads, 16 = no output pass, 32 = no drain
 };
@@ -792,16 +824,16 @@ __global__ void __launch_bounds__(THREADS, 1) aggregate_fwd_umma_kernel(const Um
             d.nx = d.ny = 0;
             d.wx_first = d.wx_last = d.wy_first = d.wy_last = d.wy_mid = 0.f;
             if (cell >= 0) {
-              const BoxTaps t =
-                  derive_taps(reinterpret_cast<const float4*>(p.boxes)[((size_t)v * p.nl + n) * p.LW + cell], sc);
-              d.base = (t.y0 * sc.fw + t.x0) * CH;
-              d.nx = t.nx;
-              d.ny = t.ny;
-              d.wx_first = t.wx_first;
-              d.wx_last = t.wx_last;
-              d.wy_first = t.wy_first;
-              d.wy_last = t.wy_last;
-              d.wy_mid = t.wy_mid;
+              const uint4* rp = reinterpret_cast<const uint4*>(a.recs + (((size_t)v * p.S + s) * p.nl + n) * p.LW + cell);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              d.base = (((int)r0.x >> 16) * sc.fw + ((int)r0.x & 0xffff)) * CH;
+              d.nx = (int)r0.y & 0xffff;
+              d.ny = (int)r0.y >> 16;
+              d.wx_first = __uint_as_float(r0.z);
+              d.wx_last = __uint_as_float(r0.w);
+              d.wy_first = __uint_as_float(r1.x);
+              d.wy_last = __uint_as_float(r1.y);
+              d.wy_mid = __uint_as_float(r1.z);
             }
 #pragma unroll
             for (int ty = 0; ty < 3; ++ty)
@@ -940,7 +972,8 @@ bool umma_supported(const vfa_geometry_t* g, const vfa_shape_t* sh, uint32_t fla
 
 size_t umma_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh, uint32_t flags) {
   if (!umma_supported(g, sh, flags)) return 0;
-  return (size_t)sh->n_scales * g->n_layers * (CH / KCH) * (2 * B_BYTES);
+  return (size_t)sh->n_scales * g->n_layers * (CH / KCH) * (2 * B_BYTES) +
+         (size_t)sh->n_views * sh->n_scales * g->n_layers * g->grid_l * g->grid_w * sizeof(TapRec);
 }
 
 int prep_weights_umma(const AggParams& p, const float* const* d_weight, void* ws, cudaStream_t st) {
@@ -971,6 +1004,13 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, uint32_
   a.variant = var ? atoi(var) : 0;
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   for (int s = 0; s < VFA_MAX_SCALES; ++s) a.wprep[s] = reinterpret_cast<const uint8_t*>(ws) + (s < p.S ? s : 0) * per_scale;
+  // gather recipes of every (view, scale, layer, cell): behind the prepared weights in the workspace
+  {
+    TapRec* recs = reinterpret_cast<TapRec*>(reinterpret_cast<uint8_t*>(ws) + (size_t)p.S * per_scale);
+    taps_table_kernel<<<148 * 8, 256, 0, st>>>(p, recs);
+    VFA_LAUNCH_CHECK("taps_table_kernel");
+    a.recs = recs;
+  }
   a.tiles_x = (p.W + TILE_W - 1) / TILE_W;
   const int tiles = a.tiles_x * ((p.L + TILE_H - 1) / TILE_H);
   a.tiles_padded = PAIR ? (tiles + 1) / 2 * 2 : tiles;
