@@ -9,7 +9,7 @@ OBJS      := $(patsubst $(SRC_DIR)/%.cu,build/%.o,$(SRCS))
 
 all: $(OUT)
 
-build/%.o: $(SRC_DIR)/%.cu $(SRC_DIR)/vfa_common.cuh include/vfa_b200.h
+build/%.o: $(SRC_DIR)/%.cu $(wildcard $(SRC_DIR)/*.cuh) include/vfa_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) $(if $(filter vfa_table,$*),-fmad=false,) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 

@@ -74,6 +74,9 @@ typedef struct {
 #define VFA_FLAG_WEIGHTS_PREPARED 8u /* workspace already holds vfa_prepare_weights output for these flags */
 #define VFA_FLAG_BF16_FEATURES 16u  /* d_feats point to bf16 [B,V,fH,fW,C] maps (forward, C = 256 only): half the
                                         gather bytes; pooling / collapse arithmetic is unchanged (fp32, 3xTF32)    */
+#define VFA_FLAG_GRID_SIDE    32u    /* C = 256: use the fully fused grid-side kernel (pool, then contract; no
+                                        intermediate at all) instead of the default feature-side pair of kernels
+                                        (contract on the image plane, then pool; Y of a frame chunk in the workspace) */
 
 int vfa_version(void);
 const char* vfa_last_error(void);

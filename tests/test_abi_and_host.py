@@ -38,7 +38,8 @@ def test_struct_layouts_match_header():
     assert int(re.search(r'#define VFA_MAX_LAYERS (\d+)', h).group(1)) == _lib.VFA_MAX_LAYERS
     assert int(re.search(r'#define VFA_MAX_SCALES (\d+)', h).group(1)) == _lib.VFA_MAX_SCALES
     for name, val in (('FORCE_SIMT', _lib.FLAG_FORCE_SIMT), ('FORCE_UMMA', _lib.FLAG_FORCE_UMMA),
-                      ('BF16_MMA', _lib.FLAG_BF16_MMA), ('WEIGHTS_PREPARED', _lib.FLAG_WEIGHTS_PREPARED)):
+                      ('BF16_MMA', _lib.FLAG_BF16_MMA), ('WEIGHTS_PREPARED', _lib.FLAG_WEIGHTS_PREPARED),
+                      ('BF16_FEATURES', _lib.FLAG_BF16_FEATURES), ('GRID_SIDE', _lib.FLAG_GRID_SIDE)):
         assert int(re.search(rf'#define VFA_FLAG_{name}\s+(\d+)u', h).group(1)) == val
 
 

@@ -16,6 +16,7 @@ FLAG_FORCE_UMMA = 2
 FLAG_BF16_MMA = 4
 FLAG_WEIGHTS_PREPARED = 8
 FLAG_BF16_FEATURES = 16
+FLAG_GRID_SIDE = 32
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libvfa_b200.so')
 

@@ -47,7 +47,7 @@ int launch_fwd_simt(AggParams, const float* const*, void*, uint32_t, cudaStream_
 int prep_weights_umma(const AggParams&, const float* const*, void*, cudaStream_t);
 size_t umma_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
 bool umma_supported(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
-int launch_fwd_umma(AggParams, const float* const*, void*, uint32_t, cudaStream_t);
+int launch_fwd_umma(AggParams, const float* const*, void*, size_t, uint32_t, cudaStream_t);
 size_t bwd_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*);
 int launch_bwd(AggParams, const float* const*, const float*, float* const*, float* const*, float* const*, void*,
                cudaStream_t);
@@ -204,7 +204,7 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
   if (use_umma) {
     VFA_REQUIRE(workspace_bytes >= umma_workspace_bytes(geom, shape, flags), VFA_ERR_WORKSPACE,
                 "workspace %zu < required %zu", workspace_bytes, umma_workspace_bytes(geom, shape, flags));
-    return launch_fwd_umma(p, d_weight, d_workspace, flags, (cudaStream_t)stream);
+    return launch_fwd_umma(p, d_weight, d_workspace, workspace_bytes, flags, (cudaStream_t)stream);
   }
   VFA_REQUIRE(workspace_bytes >= simt_workspace_bytes(geom, shape), VFA_ERR_WORKSPACE, "workspace %zu < required %zu",
               workspace_bytes, simt_workspace_bytes(geom, shape));

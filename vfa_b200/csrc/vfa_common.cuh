@@ -167,4 +167,13 @@ struct AggParams {
   uint32_t* mask;                        // nullptr or [B, V, S, ceil(C/32), LW]: ReLU pass bits (word o/32, bit o%32)
 };
 
+// Per-(view, scale, layer, cell) gather recipe in its compact global form (32 bytes), built by a small pre-pass so the
+// hot kernel carries no float64 arithmetic (the fp64 pipe throttled the producers: 15 % of their stall samples).
+struct __align__(16) TapRec {
+  int xy;          // x0 | y0 << 16
+  int nxy;         // nx | ny << 16   (0 = not visible)
+  float wx_first, wx_last, wy_first, wy_last, wy_mid;
+  int pad;
+};
+
 }  // namespace vfa

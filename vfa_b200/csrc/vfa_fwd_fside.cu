@@ -1,0 +1,486 @@
+// Feature-side forward (C = 256): the collapse is applied BEFORE the pooling.
+//
+// Box pooling is linear in the feature map, so  collapse(pool(f))  ==  sum_n pool_n(f * W_n^T):  instead of pooling
+// every (cell, layer) and contracting [L*W, C*nl] x [C*nl, C] on the grid side (2*L*W*C*nl*C flops per view and
+// scale, 335 GFLOP per MultiviewC frame), the per-layer products  Y_n[texel, o] = sum_c f[texel, c] * W[o, c*nl + n]
+// are formed once on the image plane (2*fH*fW*C*nl*C: 87 GFLOP per frame) and the pooling runs on Y_n, summing the
+// height layers in registers; bias, ReLU and the sums over scales and views (vfa_op.py:123-124, vfanet.py:79-82) close
+// the pooling kernel.  Same arithmetic class as the reference (fp32 features, fp32-accurate products), 3.9x fewer
+// flops (the backward in vfa_bwd.cu uses the transposed identity).  Two kernels per chunk of frames:
+//
+//   ygemm_kernel   tcgen05 3xTF32 GEMM  [B*V*fH*fW, 256] x [256, nl*256] for the three scales in one launch.  CTA
+//                  pairs (cta_group::2, M = 256 texel rows per cluster), 3 stages of 64 KB: 8 producer warps load the
+//                  feature rows (coalesced 128-bit), split them into tf32 hi/lo and write the SWIZZLE_128B A tiles;
+//                  one thread bulk-copies this CTA's half of the pre-split weight slab; one thread issues
+//                  {A_lo*B_hi, A_hi*B_lo, A_hi*B_hi}; the accumulator of a layer (256 TMEM columns) is double-buffered,
+//                  so the 8 epilogue warps store layer n to Y while layer n+1 is multiplied.  K = 256 per output, i.e.
+//                  32 k-steps chained in the (truncating) tensor-core accumulator -- the same bound as the per-layer
+//                  drain of the grid-side kernel.
+//   pool_y_kernel  one warp per BEV cell, 8 channels per lane (a warp-wide load = the 1 KB row of one texel): walks
+//                  (view, scale, layer) with the tap records of taps_table_kernel, accumulates the box taps of Y_n
+//                  with fp32 FMAs, adds bias, ReLU, sums; optional ReLU mask for the backward.  No shared-memory
+//                  staging: the whole L1 serves the overlapping boxes of neighbouring cells.
+//
+// Y (fp32, [plane, layer, texel, o]) lives in the caller's workspace for a chunk of frames (678 MB per MultiviewC frame);
+// it is 5x the feature maps but a quarter of the [V, C, nl, L, W] tensor the reference materialises per scale.
+#include <stdlib.h>
+
+#include "vfa_common.cuh"
+#include "vfa_umma_ptx.cuh"
+
+namespace vfa {
+
+namespace fside {
+
+using namespace umma;
+
+constexpr int CH = 256;
+constexpr int TILE_M = 128;              // texel rows per CTA == TMEM lanes
+constexpr int KCH = 32;                  // K elements per stage
+constexpr int STAGES = 3;
+constexpr int A_BYTES = TILE_M * KCH * 4;            // 16 KB per hi / lo tile
+constexpr int B_BYTES = CH * KCH * 4;                // 32 KB per hi / lo slab (N = 256)
+constexpr int B_LOCAL_BYTES = B_BYTES / 2;           // the rows this CTA of the pair stages
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_LOCAL_BYTES;   // 64 KB
+constexpr int NUM_PRODUCER_WARPS = 8;
+constexpr int FIRST_PRODUCER_WARP = 4;
+constexpr int FIRST_EPILOGUE_WARP = FIRST_PRODUCER_WARP + NUM_PRODUCER_WARPS;   // 12: (warp & 3) == TMEM lane quarter
+constexpr int NUM_EPILOGUE_WARPS = 8;
+constexpr int THREADS = (FIRST_EPILOGUE_WARP + NUM_EPILOGUE_WARPS) * 32;       // 640
+constexpr int ITEMS = TILE_M * (KCH / 4) / (NUM_PRODUCER_WARPS * 32);          // float4 items per producer thread and stage
+constexpr int TMEM_COLS = 512;           // two accumulator slots of 256 columns
+constexpr int CHUNKS = CH / KCH;         // stages per layer
+constexpr uint32_t IDESC = make_idesc_tf32(CH, 2 * TILE_M);
+
+struct __align__(16) SmemTail {
+  unsigned long long full[STAGES];        // producer warps + weight loader (tx) of THIS CTA
+  unsigned long long empty[STAGES];       // tcgen05.commit, multicast to both CTAs
+  unsigned long long peer_full[STAGES];   // leader only: the follower's relay
+  unsigned long long acc_full[2];         // tcgen05.commit per accumulator slot
+  unsigned long long acc_empty[2];        // epilogue warps of both CTAs, on the leader's barrier
+  uint32_t tmem_base;
+};
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
+
+struct YGemmArgs {
+  const uint8_t* feats[VFA_MAX_SCALES];   // [rows, 256] channels-last rows of this chunk (fp32 or bf16)
+  float* y[VFA_MAX_SCALES];               // [plane][layer][texel][256]
+  const uint8_t* wprep[VFA_MAX_SCALES];   // prepared weights (prep_weight_umma_kernel layout)
+  int rows[VFA_MAX_SCALES];               // planes * fh * fw
+  int hw[VFA_MAX_SCALES];                 // fh * fw
+  int tile_begin[VFA_MAX_SCALES + 1];     // cluster tiles (256 rows) of scale s: [tile_begin[s], tile_begin[s+1])
+  int nl, S;
+};
+
+__device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const float4& v) {
+  uint4 hi, lo;
+  hi.x = to_tf32(v.x);
+  hi.y = to_tf32(v.y);
+  hi.z = to_tf32(v.z);
+  hi.w = to_tf32(v.w);
+  // lo = v - hi is exact in fp32; the tensor core reads its top 19 bits
+  const float2 l01 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-__uint_as_float(hi.x), -__uint_as_float(hi.y)));
+  const float2 l23 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-__uint_as_float(hi.z), -__uint_as_float(hi.w)));
+  lo.x = __float_as_uint(l01.x);
+  lo.y = __float_as_uint(l01.y);
+  lo.z = __float_as_uint(l23.x);
+  lo.w = __float_as_uint(l23.y);
+  *reinterpret_cast<uint4*>(a_hi + off) = hi;
+  *reinterpret_cast<uint4*>(a_hi + A_BYTES + off) = lo;
+}
+
+// kernel-parameter arrays indexed by a run-time scale: a select chain instead of a local-memory copy of the struct
+template <typename T>
+__device__ __forceinline__ T pick(const T (&arr)[VFA_MAX_SCALES], int s) {
+  static_assert(VFA_MAX_SCALES == 3, "");
+  return s == 0 ? arr[0] : (s == 1 ? arr[1] : arr[2]);
+}
+
+template <bool BF16>
+__device__ __forceinline__ float4 load_feat4(const uint8_t* p) {
+  if (BF16) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));      // 4 x bf16; bf16 -> fp32 is a 16-bit shift (exact)
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+  }
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int ctile = blockIdx.x >> 1;
+  const int s = (a.S > 2 && ctile >= a.tile_begin[2]) ? 2 : ((a.S > 1 && ctile >= a.tile_begin[1]) ? 1 : 0);
+  const int tile0 = s == 0 ? 0 : (s == 1 ? a.tile_begin[1] : a.tile_begin[2]);
+  const int row0 = (ctile - tile0) * (2 * TILE_M) + (int)cta_rank * TILE_M;      // first texel row of this CTA
+  const int rows = pick(a.rows, s);
+  const uint8_t* const feats_s = pick(a.feats, s);
+  const uint8_t* const wprep_s = pick(a.wprep, s);
+  float* const y_s = pick(a.y, s);
+  const int total = a.nl * CHUNKS;                                                      // stages of this tile
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&tail->full[i], NUM_PRODUCER_WARPS + 1);
+      mbar_init(&tail->empty[i], 1);
+      mbar_init(&tail->peer_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tail->acc_full[i], 1);
+      mbar_init(&tail->acc_empty[i], 2 * NUM_EPILOGUE_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp == 0) {
+    // ================= weight loader =================
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int st = it % STAGES;
+        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+        uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
+        mbar_arrive_expect_tx(&tail->full[st], 2 * B_LOCAL_BYTES);
+        const uint8_t* src = wprep_s + (size_t)it * (2 * B_BYTES);      // kc = n * CHUNKS + cc == it
+        bulk_g2s(dst, src + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+        bulk_g2s(dst + B_LOCAL_BYTES, src + B_BYTES + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta_rank != 0) {
+      // pair follower: relays "my stage is full" to the leader
+      for (int it = 0; it < total; ++it) {
+        const int st = it % STAGES;
+        mbar_wait(&tail->full[st], (it / STAGES) & 1);
+        mbar_arrive_remote(&tail->peer_full[st], 0);
+      }
+    } else if (lane == 0) {
+      // ================= MMA issuer (pair leader) =================
+      int it = 0;
+      for (int n = 0; n < a.nl; ++n) {
+        const int slot = n & 1;
+        mbar_wait_cluster(&tail->acc_empty[slot], ((n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)slot * CH;
+        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->full[st], (it / STAGES) & 1);
+          mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+          const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_LOCAL_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KCH / 8; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+            tc_mma_tf32_t<true>(d_tmem, a_lo + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
+            tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+            tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+          }
+          tc_commit_t<true>(&tail->empty[st]);
+        }
+        tc_commit_t<true>(&tail->acc_full[slot]);
+      }
+    }
+  } else if (warp >= FIRST_PRODUCER_WARP && warp < FIRST_EPILOGUE_WARP) {
+    // ================= A producers: feature rows -> tf32 hi / lo operand tiles =================
+    constexpr int ES = BF16 ? 2 : 4;
+    const int pw = warp - FIRST_PRODUCER_WARP;
+    const int j = lane & 7;                          // 16-byte chunk of the 128-byte K row
+    const uint8_t* src[ITEMS];
+    uint32_t off[ITEMS];
+    bool ok[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int r = 32 * i + 4 * pw + (lane >> 3);   // 4 rows x 128 B per warp instruction
+      ok[i] = row0 + r < rows;
+      src[i] = feats_s + ((size_t)(row0 + r) * CH + j * 4) * ES;
+      off[i] = swz((uint32_t)r, (uint32_t)j);
+    }
+    float4 cur[ITEMS], nxt[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      cur[i] = ok[i] ? load_feat4<BF16>(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int it = 0; it < total; ++it) {
+      const int st = it % STAGES;
+      if (it + 1 < total) {
+        const int cc = (it + 1) % CHUNKS;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+          if (ok[i]) nxt[i] = load_feat4<BF16>(src[i] + (size_t)cc * KCH * ES);
+      }
+      mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+      uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) store_split(a_hi, off[i], cur[i]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->full[st]);
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
+    }
+  } else if (warp >= FIRST_EPILOGUE_WARP) {
+    // ================= epilogue: accumulator of layer n -> Y[plane][n][texel][:] =================
+    const int e = warp - FIRST_EPILOGUE_WARP;
+    const int quarter = warp & 3;
+    const int col_begin = (e >> 2) * (CH / 2);
+    const int r = row0 + quarter * 32 + lane;
+    const bool ok = r < rows;
+    const int hw = pick(a.hw, s);
+    const int plane = ok ? r / hw : 0, texel = ok ? r % hw : 0;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int n = 0; n < a.nl; ++n) {
+      const int slot = n & 1;
+      mbar_wait_sleep(&tail->acc_full[slot], (n >> 1) & 1);
+      tc_fence_after();
+      float* dst = y_s + (((size_t)plane * a.nl + n) * hw + texel) * CH + col_begin;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CH / 2; c0 += 32) {
+        float v[32];
+        tc_ld32(lane_addr + (uint32_t)(slot * CH + col_begin + c0), v);
+        tc_wait_ld();
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank != 0) mbar_arrive_remote(&tail->acc_empty[slot], 0);
+        else mbar_arrive(&tail->acc_empty[slot]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+// ---- pooling of Y ------------------------------------------------------------------------------------------------
+constexpr int POOL_TW = 4, POOL_TH = 4;                 // cells per CTA: 4 x 4, one warp each
+constexpr int POOL_WARPS = POOL_TW * POOL_TH;
+constexpr int TAP_BATCH = 3;                            // taps of a box row in flight per warp
+
+struct PoolArgs {
+  AggParams p;
+  const float* y[VFA_MAX_SCALES];
+  const TapRec* recs;        // [V][S][nl][LW]
+  int b0;                    // first frame of this chunk (output / mask index); Y planes are chunk-relative
+  int tiles_x;
+};
+
+__device__ __forceinline__ void fma8(float (&acc)[8], float w, const float4& a, const float4& b) {
+  const float2 w2 = make_float2(w, w);
+  const float2 r0 = __ffma2_rn(w2, make_float2(a.x, a.y), make_float2(acc[0], acc[1]));
+  const float2 r1 = __ffma2_rn(w2, make_float2(a.z, a.w), make_float2(acc[2], acc[3]));
+  const float2 r2 = __ffma2_rn(w2, make_float2(b.x, b.y), make_float2(acc[4], acc[5]));
+  const float2 r3 = __ffma2_rn(w2, make_float2(b.z, b.w), make_float2(acc[6], acc[7]));
+  acc[0] = r0.x; acc[1] = r0.y; acc[2] = r1.x; acc[3] = r1.y;
+  acc[4] = r2.x; acc[5] = r2.y; acc[6] = r3.x; acc[7] = r3.y;
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolArgs a) {
+  const AggParams& p = a.p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cy = (blockIdx.x / a.tiles_x) * POOL_TH + warp / POOL_TW;
+  const int cx = (blockIdx.x % a.tiles_x) * POOL_TW + warp % POOL_TW;
+  if (cy >= p.L || cx >= p.W) return;                 // no block-level synchronisation below
+  const int cell = cy * p.W + cx;
+  const int bl = blockIdx.y;                          // frame inside the chunk
+  const int b = a.b0 + bl;
+
+  float out[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = 0.f;
+
+  const uint4* rp = reinterpret_cast<const uint4*>(a.recs + cell);
+  const size_t rec_stride = (size_t)p.LW * (sizeof(TapRec) / sizeof(uint4));
+  uint4 n0 = __ldg(rp), n1 = __ldg(rp + 1);           // record of (v, s, n) = (0, 0, 0), prefetched one step ahead
+  const int total = p.V * p.S * p.nl;
+  int j = 0;
+  for (int v = 0; v < p.V; ++v) {
+    for (int s = 0; s < p.S; ++s) {
+      const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
+      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 8;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int n = 0; n < p.nl; ++n, ++j, yplane += (size_t)hw * CH) {
+        const uint4 r0 = n0, r1 = n1;
+        if (j + 1 < total) {
+          rp += rec_stride;
+          n0 = __ldg(rp);
+          n1 = __ldg(rp + 1);
+        }
+        const int nx = (int)r0.y & 0xffff, ny = (int)r0.y >> 16;
+        if (nx == 0) continue;                        // not visible (warp-uniform)
+        const float wx_first = __uint_as_float(r0.z), wx_last = __uint_as_float(r0.w);
+        const float wy_first = __uint_as_float(r1.x), wy_last = __uint_as_float(r1.y), wy_mid = __uint_as_float(r1.z);
+        const float* row = yplane + (size_t)(((int)r0.x >> 16) * fw + ((int)r0.x & 0xffff)) * CH;
+        for (int ty = 0; ty < ny; ++ty, row += (size_t)fw * CH) {
+          const float wy = ty == 0 ? wy_first : (ty == ny - 1 ? wy_last : wy_mid);
+          if (wy == 0.f) continue;
+          for (int tx = 0; tx < nx; tx += TAP_BATCH) {
+            float w[TAP_BATCH];
+            float4 va[TAP_BATCH], vb[TAP_BATCH];
+#pragma unroll
+            for (int k = 0; k < TAP_BATCH; ++k) {
+              const int t = tx + k;
+              w[k] = t < nx ? wy * (t == 0 ? wx_first : (t == nx - 1 ? wx_last : 1.0f)) : 0.f;
+              va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (w[k] != 0.f) {                      // taps of weight 0 are never fetched
+                va[k] = __ldg(reinterpret_cast<const float4*>(row + (size_t)t * CH));
+                vb[k] = __ldg(reinterpret_cast<const float4*>(row + (size_t)t * CH + 4));
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < TAP_BATCH; ++k)
+              if (w[k] != 0.f) fma8(acc, w[k], va[k], vb[k]);
+          }
+        }
+      }
+      // + bias, ReLU (vfa_op.py:123-124), sum over scales and views (vfanet.py:79, :82)
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8 + 4));
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = acc[i] + bb[i];
+        bits |= (t > 0.f ? 1u : 0u) << i;
+        out[i] += fmaxf(t, 0.f);
+      }
+      if (MASK) {       // word o/32, bit o%32: lanes 4k .. 4k+3 hold the four bytes of word k
+        bits <<= 8 * (lane & 3);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        if ((lane & 3) == 0)
+          p.mask[((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (lane >> 2)) * p.LW + cell] = bits;
+      }
+    }
+  }
+  float* o = p.out + ((size_t)b * CH + lane * 8) * p.LW + cell;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[(size_t)i * p.LW] = out[i];
+}
+
+}  // namespace fside
+
+using namespace fside;
+
+// bytes of Y for one frame
+size_t fside_y_bytes_per_frame(const AggParams& p) {
+  size_t texels = 0;
+  for (int s = 0; s < p.S; ++s) texels += (size_t)p.sc[s].fh * p.sc[s].fw;
+  return texels * p.V * p.nl * CH * sizeof(float);
+}
+
+// frames per chunk for a Y budget (the workspace holds Y of one chunk)
+int fside_chunk_frames(const AggParams& p) {
+  const size_t budget = (size_t)6 << 30;
+  const size_t per = fside_y_bytes_per_frame(p);
+  size_t cb = budget / per;
+  if (cb < 1) cb = 1;
+  if (cb > (size_t)p.B) cb = (size_t)p.B;
+  return (int)cb;
+}
+
+int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, float* y_ws, size_t y_bytes,
+                     bool bf16, int variant, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxL1));
+    VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxL1));
+    attr_set = true;
+  }
+  const size_t per_frame = fside_y_bytes_per_frame(p);
+  int cb = fside_chunk_frames(p);
+  if ((size_t)cb * per_frame > y_bytes) cb = (int)(y_bytes / per_frame);
+  if (cb < 1) {
+    set_error("feature-side forward: workspace holds %zu bytes for Y, one frame needs %zu", y_bytes, per_frame);
+    return VFA_ERR_WORKSPACE;
+  }
+  const size_t es = bf16 ? 2 : 4;
+  for (int b0 = 0; b0 < p.B; b0 += cb) {
+    const int nb = p.B - b0 < cb ? p.B - b0 : cb;
+    YGemmArgs g;
+    PoolArgs q;
+    q.p = p;
+    q.recs = recs;
+    q.b0 = b0;
+    q.tiles_x = (p.W + POOL_TW - 1) / POOL_TW;
+    g.nl = p.nl;
+    g.S = p.S;
+    size_t y_off = 0;      // floats
+    g.tile_begin[0] = 0;
+    for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+      const int ss = s < p.S ? s : 0;
+      const int hw = p.sc[ss].fh * p.sc[ss].fw;
+      g.hw[s] = hw;
+      g.rows[s] = nb * p.V * hw;
+      g.feats[s] = reinterpret_cast<const uint8_t*>(p.feats[ss]) + (size_t)b0 * p.V * hw * CH * es;
+      g.wprep[s] = wprep[ss];
+      g.y[s] = y_ws + (s < p.S ? y_off : 0);
+      q.y[s] = g.y[s];
+      if (s < p.S) {
+        y_off += (size_t)cb * p.V * p.nl * hw * CH;
+        g.tile_begin[s + 1] = g.tile_begin[s] + (g.rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+      }
+    }
+    if (!(variant & 128)) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * g.tile_begin[p.S]);
+      cfg.blockDim = dim3(THREADS);
+      cfg.dynamicSmemBytes = SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (bf16)
+        VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<true>, g));
+      else
+        VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<false>, g));
+      VFA_LAUNCH_CHECK("ygemm_kernel");
+    }
+    if (!(variant & 64)) {
+      const dim3 grid(q.tiles_x * ((p.L + POOL_TH - 1) / POOL_TH), nb);
+      if (p.mask != nullptr)
+        pool_y_kernel<true><<<grid, POOL_WARPS * 32, 0, st>>>(q);
+      else
+        pool_y_kernel<false><<<grid, POOL_WARPS * 32, 0, st>>>(q);
+      VFA_LAUNCH_CHECK("pool_y_kernel");
+    }
+  }
+  return VFA_OK;
+}
+
+}  // namespace vfa
