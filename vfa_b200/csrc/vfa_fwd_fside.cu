@@ -60,7 +60,11 @@ struct __align__(16) SmemTail {
   unsigned long long acc_empty[2];        // epilogue warps of both CTAs, on the leader's barrier
   uint32_t tmem_base;
 };
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
+constexpr int TAIL_BYTES = 256;           // SmemTail, padded
+constexpr int PATCH_BYTES = 32 * 128;     // per epilogue warp: 32 rows x 32 fp32, swizzled
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + TAIL_BYTES + (size_t)NUM_EPILOGUE_WARPS * PATCH_BYTES;
+static_assert(sizeof(SmemTail) <= TAIL_BYTES, "");
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 
 struct YGemmArgs {
   const uint8_t* feats[VFA_MAX_SCALES];   // [rows, 256] channels-last rows of this chunk (fp32 or bf16)
@@ -70,6 +74,7 @@ struct YGemmArgs {
   int hw[VFA_MAX_SCALES];                 // fh * fw
   int tile_begin[VFA_MAX_SCALES + 1];     // cluster tiles (256 rows) of scale s: [tile_begin[s], tile_begin[s+1])
   int nl, S;
+  int n_tiles;                            // tile_begin[S]
 };
 
 __device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const float4& v) {
@@ -106,6 +111,28 @@ __device__ __forceinline__ float4 load_feat4(const uint8_t* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
 
+// Geometry of one cluster tile (256 texel rows of one scale), decoded from the flat tile index.
+struct TileInfo {
+  int s, row0, rows, hw;
+  const uint8_t* feats;
+  const uint8_t* wprep;
+  float* y;
+};
+__device__ __forceinline__ TileInfo tile_info(const YGemmArgs& a, int ctile, uint32_t cta_rank) {
+  TileInfo t;
+  t.s = (a.S > 2 && ctile >= a.tile_begin[2]) ? 2 : ((a.S > 1 && ctile >= a.tile_begin[1]) ? 1 : 0);
+  const int tile0 = t.s == 0 ? 0 : (t.s == 1 ? a.tile_begin[1] : a.tile_begin[2]);
+  t.row0 = (ctile - tile0) * (2 * TILE_M) + (int)cta_rank * TILE_M;      // first texel row of this CTA
+  t.rows = pick(a.rows, t.s);
+  t.hw = pick(a.hw, t.s);
+  t.feats = pick(a.feats, t.s);
+  t.wprep = pick(a.wprep, t.s);
+  t.y = pick(a.y, t.s);
+  return t;
+}
+
+// Persistent: cluster c works on tiles c, c + n_clusters, ... ; every role keeps its stage / layer counters running
+// across tiles, so the last layer's epilogue and the next tile's first loads overlap the tensor-core work.
 template <bool BF16>
 __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -114,15 +141,9 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cta_rank = cluster_ctarank();
-  const int ctile = blockIdx.x >> 1;
-  const int s = (a.S > 2 && ctile >= a.tile_begin[2]) ? 2 : ((a.S > 1 && ctile >= a.tile_begin[1]) ? 1 : 0);
-  const int tile0 = s == 0 ? 0 : (s == 1 ? a.tile_begin[1] : a.tile_begin[2]);
-  const int row0 = (ctile - tile0) * (2 * TILE_M) + (int)cta_rank * TILE_M;      // first texel row of this CTA
-  const int rows = pick(a.rows, s);
-  const uint8_t* const feats_s = pick(a.feats, s);
-  const uint8_t* const wprep_s = pick(a.wprep, s);
-  float* const y_s = pick(a.y, s);
-  const int total = a.nl * CHUNKS;                                                      // stages of this tile
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int n_tiles = a.n_tiles;
+  const int total = a.nl * CHUNKS;                                       // stages per tile
 
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -150,50 +171,58 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
   if (warp == 0) {
     // ================= weight loader =================
     if (lane == 0) {
-      for (int it = 0; it < total; ++it) {
-        const int st = it % STAGES;
-        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
-        uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
-        mbar_arrive_expect_tx(&tail->full[st], 2 * B_LOCAL_BYTES);
-        const uint8_t* src = wprep_s + (size_t)it * (2 * B_BYTES);      // kc = n * CHUNKS + cc == it
-        bulk_g2s(dst, src + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
-        bulk_g2s(dst + B_LOCAL_BYTES, src + B_BYTES + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+      int it = 0;
+      for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
+        const TileInfo t = tile_info(a, ctile, cta_rank);
+        for (int k = 0; k < total; ++k, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+          uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
+          mbar_arrive_expect_tx(&tail->full[st], 2 * B_LOCAL_BYTES);
+          const uint8_t* src = t.wprep + (size_t)k * (2 * B_BYTES);      // kc = n * CHUNKS + cc == k
+          bulk_g2s(dst, src + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+          bulk_g2s(dst + B_LOCAL_BYTES, src + B_BYTES + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && cta_rank != 0) {
       // pair follower: relays "my stage is full" to the leader
-      for (int it = 0; it < total; ++it) {
-        const int st = it % STAGES;
-        mbar_wait(&tail->full[st], (it / STAGES) & 1);
-        mbar_arrive_remote(&tail->peer_full[st], 0);
-      }
-    } else if (lane == 0) {
-      // ================= MMA issuer (pair leader) =================
       int it = 0;
-      for (int n = 0; n < a.nl; ++n) {
-        const int slot = n & 1;
-        mbar_wait_cluster(&tail->acc_empty[slot], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem + (uint32_t)slot * CH;
-        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+      for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters)
+        for (int k = 0; k < total; ++k, ++it) {
           const int st = it % STAGES;
           mbar_wait(&tail->full[st], (it / STAGES) & 1);
-          mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
-          const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_LOCAL_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < KCH / 8; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-            tc_mma_tf32_t<true>(d_tmem, a_lo + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
-            tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-            tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
-          }
-          tc_commit_t<true>(&tail->empty[st]);
+          mbar_arrive_remote(&tail->peer_full[st], 0);
         }
-        tc_commit_t<true>(&tail->acc_full[slot]);
+    } else if (lane == 0) {
+      // ================= MMA issuer (pair leader) =================
+      int it = 0, ln = 0;                               // running stage / layer counters
+      for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
+        for (int n = 0; n < a.nl; ++n, ++ln) {
+          const int slot = ln & 1;
+          mbar_wait_cluster(&tail->acc_empty[slot], ((ln >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + (uint32_t)slot * CH;
+          for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+            const int st = it % STAGES;
+            mbar_wait(&tail->full[st], (it / STAGES) & 1);
+            mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+            const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+            const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_LOCAL_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < KCH / 8; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+              tc_mma_tf32_t<true>(d_tmem, a_lo + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
+              tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+              tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+            }
+            tc_commit_t<true>(&tail->empty[st]);
+          }
+          tc_commit_t<true>(&tail->acc_full[slot]);
+        }
       }
     }
   } else if (warp >= FIRST_PRODUCER_WARP && warp < FIRST_EPILOGUE_WARP) {
@@ -204,68 +233,101 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
     const uint8_t* src[ITEMS];
     uint32_t off[ITEMS];
     bool ok[ITEMS];
+    auto bind_tile = [&](int ctile) {                // source rows of this thread's items in tile `ctile`
+      const TileInfo t = tile_info(a, ctile, cta_rank);
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int r = 32 * i + 4 * pw + (lane >> 3);   // 4 rows x 128 B per warp instruction
-      ok[i] = row0 + r < rows;
-      src[i] = feats_s + ((size_t)(row0 + r) * CH + j * 4) * ES;
-      off[i] = swz((uint32_t)r, (uint32_t)j);
-    }
+      for (int i = 0; i < ITEMS; ++i) {
+        const int r = 32 * i + 4 * pw + (lane >> 3); // 4 rows x 128 B per warp instruction
+        ok[i] = t.row0 + r < t.rows;
+        src[i] = t.feats + ((size_t)(t.row0 + r) * CH + j * 4) * ES;
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) off[i] = swz((uint32_t)(32 * i + 4 * pw + (lane >> 3)), (uint32_t)j);
     float4 cur[ITEMS], nxt[ITEMS];
+    if (cluster < n_tiles) bind_tile(cluster);
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-      cur[i] = ok[i] ? load_feat4<BF16>(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      cur[i] = (cluster < n_tiles && ok[i]) ? load_feat4<BF16>(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
       nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int it = 0; it < total; ++it) {
-      const int st = it % STAGES;
-      if (it + 1 < total) {
-        const int cc = (it + 1) % CHUNKS;
+    int it = 0;
+    for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
+      for (int k = 0; k < total; ++k, ++it) {
+        const int st = it % STAGES;
+        // loads of the next stage (possibly the first stage of the next tile) fly while this one is stored
+        int cc = (k + 1) % CHUNKS;
+        bool more = true;
+        if (k + 1 == total) {
+          more = ctile + n_clusters < n_tiles;
+          if (more) bind_tile(ctile + n_clusters);
+          cc = 0;
+        }
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i)
-          if (ok[i]) nxt[i] = load_feat4<BF16>(src[i] + (size_t)cc * KCH * ES);
+        for (int i = 0; i < ITEMS; ++i) {
+          nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (more && ok[i]) nxt[i] = load_feat4<BF16>(src[i] + (size_t)cc * KCH * ES);
+        }
+        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+        uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) store_split(a_hi, off[i], cur[i]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->full[st]);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
       }
-      mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
-      uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) store_split(a_hi, off[i], cur[i]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->full[st]);
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
     }
   } else if (warp >= FIRST_EPILOGUE_WARP) {
     // ================= epilogue: accumulator of layer n -> Y[plane][n][texel][:] =================
+    // A thread owns one accumulator row (TMEM lane); written directly, a warp store would touch 32 different 1 KB
+    // rows of Y.  Each 32 x 32 chunk is therefore transposed through a swizzled 4 KB shared-memory patch of the warp,
+    // so that a store instruction writes 4 rows x 128 contiguous bytes.
     const int e = warp - FIRST_EPILOGUE_WARP;
     const int quarter = warp & 3;
     const int col_begin = (e >> 2) * (CH / 2);
-    const int r = row0 + quarter * 32 + lane;
-    const bool ok = r < rows;
-    const int hw = pick(a.hw, s);
-    const int plane = ok ? r / hw : 0, texel = ok ? r % hw : 0;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int n = 0; n < a.nl; ++n) {
-      const int slot = n & 1;
-      mbar_wait_sleep(&tail->acc_full[slot], (n >> 1) & 1);
-      tc_fence_after();
-      float* dst = y_s + (((size_t)plane * a.nl + n) * hw + texel) * CH + col_begin;
-#pragma unroll 1
-      for (int c0 = 0; c0 < CH / 2; c0 += 32) {
-        float v[32];
-        tc_ld32(lane_addr + (uint32_t)(slot * CH + col_begin + c0), v);
-        tc_wait_ld();
-        if (ok) {
+    uint8_t* patch = smem + (size_t)STAGES * STAGE_BYTES + TAIL_BYTES + (size_t)e * PATCH_BYTES;
+    const int sub = lane >> 3, chunk = lane & 7;      // store phase: row 4*rr + sub of the patch, 16-byte chunk
+    int ln = 0;
+    for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
+      const TileInfo t = tile_info(a, ctile, cta_rank);
+      uint32_t yrow[8];                               // 1 KB row of Y (layer 0) of patch row 4*rr + sub; ~0u = outside
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
+      for (int rr = 0; rr < 8; ++rr) {
+        const int r = t.row0 + quarter * 32 + 4 * rr + sub;
+        yrow[rr] = r < t.rows ? (uint32_t)((r / t.hw) * a.nl * t.hw + r % t.hw) : 0xffffffffu;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (cta_rank != 0) mbar_arrive_remote(&tail->acc_empty[slot], 0);
-        else mbar_arrive(&tail->acc_empty[slot]);
+      for (int n = 0; n < a.nl; ++n, ++ln) {
+        const int slot = ln & 1;
+        mbar_wait_sleep(&tail->acc_full[slot], (ln >> 1) & 1);
+        tc_fence_after();
+        float* dst = t.y + (size_t)n * t.hw * CH + col_begin + chunk * 4;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CH / 2; c0 += 32) {
+          float v[32];
+          tc_ld32(lane_addr + (uint32_t)(slot * CH + col_begin + c0), v);
+          tc_wait_ld();
+          __syncwarp();                               // the previous chunk has left the patch
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(patch + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int prow = 4 * rr + sub;
+            const float4 q = *reinterpret_cast<const float4*>(patch + prow * 128 + ((chunk ^ (prow & 7)) << 4));
+            if (yrow[rr] != 0xffffffffu) *reinterpret_cast<float4*>(dst + (size_t)yrow[rr] * CH + c0) = q;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta_rank != 0) mbar_arrive_remote(&tail->acc_empty[slot], 0);
+          else mbar_arrive(&tail->acc_empty[slot]);
+        }
       }
     }
   }
@@ -454,7 +516,6 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     }
     if (!(variant & 128)) {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * g.tile_begin[p.S]);
       cfg.blockDim = dim3(THREADS);
       cfg.dynamicSmemBytes = SMEM_BYTES;
       cfg.stream = st;
@@ -465,6 +526,19 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
+      static int resident_clusters = 0;      // CTA pairs the device can hold at once (1 CTA per SM)
+      if (resident_clusters == 0) {
+        cfg.gridDim = dim3(2 * 148);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, ygemm_kernel<false>, &cfg) != cudaSuccess || n < 1) {
+          (void)cudaGetLastError();
+          n = 64;
+        }
+        resident_clusters = n;
+      }
+      const int n_tiles = g.tile_begin[p.S];
+      g.n_tiles = n_tiles;
+      cfg.gridDim = dim3(2 * (n_tiles < resident_clusters ? n_tiles : resident_clusters));
       if (bf16)
         VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<true>, g));
       else
