@@ -447,6 +447,158 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
   for (int i = 0; i < 8; ++i) o[(size_t)i * p.LW] = out[i];
 }
 
+
+// ---- pooling of Y, four cells per warp ------------------------------------------------------------------------------
+// The boxes of neighbouring BEV cells overlap heavily (the union bounding box of a 2 x 2 block of cells holds 31-36 % of
+// the texels its four boxes hold one by one), and the one-cell-per-warp kernel above runs into the L1 data pipe
+// (128 B / clk / SM, 80 % busy).  Here a warp owns a 2 x 2 quad of cells: per (view, scale, layer) it walks the UNION of
+// the four boxes once, loads every texel once (2 x LDG.128 per lane = the 1 KB row) and applies it to each cell whose
+// box contains it.  Lane 4*j + c computes the weight of cell c for column j of the current 8-column block; the weight
+// of (cell, texel) then reaches all lanes by one shuffle.  Output partial sums live in shared memory (48 KB per CTA).
+constexpr int QX = 4, QY = 3;                           // quads per CTA: 6 x 8 cells
+constexpr int QWARPS = QX * QY;
+
+template <bool MASK>
+__global__ void __launch_bounds__(QWARPS * 32, 2) pool_quad_kernel(const PoolArgs a) {
+  __shared__ float out_s[QWARPS][4][CH];
+  const AggParams& p = a.p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cy0 = (blockIdx.x / a.tiles_x) * (2 * QY) + 2 * (warp / QX);
+  const int cx0 = (blockIdx.x % a.tiles_x) * (2 * QX) + 2 * (warp % QX);
+  if (cy0 >= p.L || cx0 >= p.W) return;                 // no block-level synchronisation below
+  const int bl = blockIdx.y;
+  const int b = a.b0 + bl;
+  const int cl = lane & 3, jl = lane >> 2;              // this lane's cell (records, weights) and block column
+  const bool my_valid = cy0 + (cl >> 1) < p.L && cx0 + (cl & 1) < p.W;
+  const int my_cell = my_valid ? (cy0 + (cl >> 1)) * p.W + cx0 + (cl & 1) : cy0 * p.W + cx0;
+
+  float* const outw = &out_s[warp][0][lane * 8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    *reinterpret_cast<float4*>(outw + c * CH) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(outw + c * CH + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  const uint4* rp = reinterpret_cast<const uint4*>(a.recs + my_cell);
+  const size_t rec_stride = (size_t)p.LW * (sizeof(TapRec) / sizeof(uint4));
+  uint4 n0 = __ldg(rp), n1 = __ldg(rp + 1);             // record of (v, s, n) = (0, 0, 0), prefetched one step ahead
+  const int total = p.V * p.S * p.nl;
+  int j_rec = 0;
+  for (int v = 0; v < p.V; ++v) {
+    for (int s = 0; s < p.S; ++s) {
+      const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
+      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 8;
+      float acc[4][8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+      for (int n = 0; n < p.nl; ++n, ++j_rec, yplane += (size_t)hw * CH) {
+        const uint4 r0 = n0, r1 = n1;
+        if (j_rec + 1 < total) {
+          rp += rec_stride;
+          n0 = __ldg(rp);
+          n1 = __ldg(rp + 1);
+        }
+        const int nx = my_valid ? ((int)r0.y & 0xffff) : 0, ny = (int)r0.y >> 16;
+        const int x0 = (int)r0.x & 0xffff, y0 = (int)r0.x >> 16;
+        const bool vis = nx != 0;
+        // union of the visible boxes of the quad (warp-uniform)
+        const int ux1 = __reduce_max_sync(0xffffffffu, vis ? x0 + nx - 1 : -1);
+        if (ux1 < 0) continue;
+        const int ux0 = __reduce_min_sync(0xffffffffu, vis ? x0 : 0x7fff);
+        const int uy0 = __reduce_min_sync(0xffffffffu, vis ? y0 : 0x7fff);
+        const int uy1 = __reduce_max_sync(0xffffffffu, vis ? y0 + ny - 1 : -1);
+        const float wx_first = __uint_as_float(r0.z), wx_last = __uint_as_float(r0.w);
+        const float wy_first = __uint_as_float(r1.x), wy_last = __uint_as_float(r1.y), wy_mid = __uint_as_float(r1.z);
+        const float* rowp = yplane + ((size_t)uy0 * fw + ux0) * CH;
+        for (int ty = uy0; ty <= uy1; ++ty, rowp += (size_t)fw * CH) {
+          const int ry = ty - y0;
+          const float wy = (vis && ry >= 0 && ry < ny) ? (ry == 0 ? wy_first : (ry == ny - 1 ? wy_last : wy_mid)) : 0.f;
+          for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
+            const int rx = ux0 + cb + jl - x0;
+            const float wx = (rx >= 0 && rx < nx) ? (rx == 0 ? wx_first : (rx == nx - 1 ? wx_last : 1.0f)) : 0.f;
+            const float wl = wy * wx;                   // weight of (cell cl, column cb + jl) in this row
+            const uint32_t bm = __ballot_sync(0xffffffffu, wl != 0.f);     // bit 4*j + c
+#pragma unroll 1
+            for (int j = 0; j < 8 && (bm >> (4 * j)) != 0u; j += 2) {
+              const uint32_t m0 = (bm >> (4 * j)) & 0xfu, m1 = (bm >> (4 * j + 4)) & 0xfu;
+              const float* tp = rowp + (size_t)(cb + j) * CH;
+              float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
+              if (m0) {                                 // texels no box of the quad covers are never fetched
+                a0 = __ldg(reinterpret_cast<const float4*>(tp));
+                b0 = __ldg(reinterpret_cast<const float4*>(tp + 4));
+              }
+              if (m1) {
+                a1 = __ldg(reinterpret_cast<const float4*>(tp + CH));
+                b1 = __ldg(reinterpret_cast<const float4*>(tp + CH + 4));
+              }
+              if (m0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float w = __shfl_sync(0xffffffffu, wl, 4 * j + c);
+                  if (w != 0.f) fma8(acc[c], w, a0, b0);
+                }
+              }
+              if (m1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float w = __shfl_sync(0xffffffffu, wl, 4 * j + 4 + c);
+                  if (w != 0.f) fma8(acc[c], w, a1, b1);
+                }
+              }
+            }
+          }
+        }
+      }
+      // + bias, ReLU (vfa_op.py:123-124), sum over scales and views (vfanet.py:79, :82)
+      const float4 bi0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8));
+      const float4 bi1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8 + 4));
+      const float bb[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
+        float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
+        float t[8];
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          t[i] = acc[c][i] + bb[i];
+          bits |= (t[i] > 0.f ? 1u : 0u) << i;
+        }
+        o0.x += fmaxf(t[0], 0.f); o0.y += fmaxf(t[1], 0.f); o0.z += fmaxf(t[2], 0.f); o0.w += fmaxf(t[3], 0.f);
+        o1.x += fmaxf(t[4], 0.f); o1.y += fmaxf(t[5], 0.f); o1.z += fmaxf(t[6], 0.f); o1.w += fmaxf(t[7], 0.f);
+        *reinterpret_cast<float4*>(outw + c * CH) = o0;
+        *reinterpret_cast<float4*>(outw + c * CH + 4) = o1;
+        if (MASK) {     // word o/32, bit o%32: lanes 4k .. 4k+3 hold the four bytes of word k
+          bits <<= 8 * (lane & 3);
+          bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+          bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+          const int cy = cy0 + (c >> 1), cx = cx0 + (c & 1);
+          if ((lane & 3) == 0 && cy < p.L && cx < p.W)
+            p.mask[((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (lane >> 2)) * p.LW + cy * p.W + cx] = bits;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int cy = cy0 + (c >> 1), cx = cx0 + (c & 1);
+    if (cy >= p.L || cx >= p.W) continue;
+    const float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
+    const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
+    float* o = p.out + ((size_t)b * CH + lane * 8) * p.LW + cy * p.W + cx;
+    o[0] = o0.x;
+    o[(size_t)1 * p.LW] = o0.y;
+    o[(size_t)2 * p.LW] = o0.z;
+    o[(size_t)3 * p.LW] = o0.w;
+    o[(size_t)4 * p.LW] = o1.x;
+    o[(size_t)5 * p.LW] = o1.y;
+    o[(size_t)6 * p.LW] = o1.z;
+    o[(size_t)7 * p.LW] = o1.w;
+  }
+}
+
 }  // namespace fside
 
 using namespace fside;
@@ -478,6 +630,9 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
                                   (int)cudaSharedmemCarveoutMaxL1));
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxL1));
+    // two CTAs x 48 KB of partial sums per SM, the rest of the unified array as L1
+    VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     attr_set = true;
   }
   const size_t per_frame = fside_y_bytes_per_frame(p);
@@ -546,12 +701,27 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       VFA_LAUNCH_CHECK("ygemm_kernel");
     }
     if (!(variant & 64)) {
-      const dim3 grid(q.tiles_x * ((p.L + POOL_TH - 1) / POOL_TH), nb);
-      if (p.mask != nullptr)
-        pool_y_kernel<true><<<grid, POOL_WARPS * 32, 0, st>>>(q);
-      else
-        pool_y_kernel<false><<<grid, POOL_WARPS * 32, 0, st>>>(q);
-      VFA_LAUNCH_CHECK("pool_y_kernel");
+      static int quad = -1;            // VFA_POOL_QUAD=0 selects the one-cell-per-warp kernel (debug / comparison)
+      if (quad < 0) {
+        const char* e = getenv("VFA_POOL_QUAD");
+        quad = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+      }
+      if (quad) {
+        q.tiles_x = (p.W + 2 * QX - 1) / (2 * QX);
+        const dim3 grid(q.tiles_x * ((p.L + 2 * QY - 1) / (2 * QY)), nb);
+        if (p.mask != nullptr)
+          pool_quad_kernel<true><<<grid, QWARPS * 32, 0, st>>>(q);
+        else
+          pool_quad_kernel<false><<<grid, QWARPS * 32, 0, st>>>(q);
+        VFA_LAUNCH_CHECK("pool_quad_kernel");
+      } else {
+        const dim3 grid(q.tiles_x * ((p.L + POOL_TH - 1) / POOL_TH), nb);
+        if (p.mask != nullptr)
+          pool_y_kernel<true><<<grid, POOL_WARPS * 32, 0, st>>>(q);
+        else
+          pool_y_kernel<false><<<grid, POOL_WARPS * 32, 0, st>>>(q);
+        VFA_LAUNCH_CHECK("pool_y_kernel");
+      }
     }
   }
   return VFA_OK;
