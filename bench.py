@@ -75,7 +75,14 @@ def workload_numbers(geom, batch, esize=4):
     out_bytes = batch * C * L * W * 4
     const_bytes = 3 * (C * C * nl + C) * 4 + V * nl * L * W * 16 + L * W * 12 + V * 48
     flops = 2.0 * L * W * (C * nl) * C * 3 * V * batch          # collapse contraction, grid-side (as the reference)
-    return dict(bytes=feat_bytes + out_bytes + const_bytes, flops=flops, feat_bytes=feat_bytes, out_bytes=out_bytes)
+    # feature-side formulation (vfa_fwd_fside.cu): contraction on the image plane, Y = per-layer products in HBM
+    fside_flops = 2.0 * batch * V * px * C * (C * nl)
+    y_bytes = batch * V * nl * px * C * 4
+    rec_bytes = V * len(geom.feature_sizes()) * nl * L * W * 32
+    y_frame = V * nl * px * C * 4
+    chunk = min(batch, max(1, (6 << 30) // y_frame))            # fside_chunk_frames()
+    return dict(bytes=feat_bytes + out_bytes + const_bytes, flops=flops, feat_bytes=feat_bytes, out_bytes=out_bytes,
+                fside_flops=fside_flops, y_bytes=y_bytes, rec_bytes=rec_bytes, fside_chunks=-(-batch // chunk))
 
 
 class ClockSampler(threading.Thread):
@@ -271,7 +278,8 @@ def main():
     for _ in range(max(3, args.warmup)):
         step()
     path = vfa_b200.last_kernel_path()
-    launches_per_step = 6        # table_build + 3 x prep_weight + tap-recipe table + fused aggregate kernel (memsets not counted)
+    # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | per frame chunk: ygemm + pool_quad}
+    launches_per_step = 5 + (2 * nums['fside_chunks'] if path.startswith('fside') else 1)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -293,6 +301,28 @@ def main():
     frames_per_step = B if args.mode == 'slab' else world * B
     value = frames_per_step * args.steps / (total_ms * 1e-3)
     kern = sum(kernel_ms) / len(kernel_ms)
+
+    # ---- per-kernel durations of the feature-side pair (CUDA events; debug bits switch one kernel off at a time:
+    #      64 = GEMM only, 128 = pooling only, 256 = reuse the tap records -> exactly one launch between the events) ----
+    per_kernel = None
+    if path.startswith('fside') and args.mode == 'dp' and not args.backward:
+        table = vfa_b200.build_table(cgeom, calibs, grid)
+        per_kernel = {}
+        for kname, bits in (('ygemm_kernel', 64 | 256), ('pool_quad_kernel', 128 | 256)):
+            os.environ['VFA_UMMA_VARIANT'] = str(bits)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for i in range(-2, args.steps):
+                if i >= 0:
+                    evs[i][0].record()
+                vfa_b200.aggregate_forward_raw(feats_cl, table, weights, biases, args.flags, out=out, workspace=ws,
+                                               prepared=True)
+                if i >= 0:
+                    evs[i][1].record()
+            torch.cuda.synchronize()
+            per_kernel[kname] = sum(a.elapsed_time(b) for a, b in evs) / len(evs) / nums['fside_chunks']
+        os.environ.pop('VFA_UMMA_VARIANT', None)
+        vfa_b200.aggregate_forward_raw(feats_cl, table, weights, biases, args.flags, out=out, workspace=ws, prepared=True)
+        torch.cuda.synchronize()
 
     # ---- end to end through the public API: pinned host NCHW features -> device -> aggregate -> host ----
     e2e = None
@@ -349,6 +379,66 @@ def main():
             per_frame = tj.get(args.workload, {}).get(path)
             if per_frame is not None:
                 traffic = per_frame * B
+        def traffic_of(kernel):
+            per_frame = None
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    per_frame = json.load(f).get(args.workload, {}).get(kernel)
+            return None if per_frame is None else per_frame * B / nums['fside_chunks']
+
+        if per_kernel is not None:
+            # dominant kernel: the pooling of Y.  Its compulsory HBM traffic per launch: Y once, the tap records once,
+            # the output once.  (What actually binds it is the SM-side gather: L1 data pipe and issue slots.)
+            frames = B / nums['fside_chunks']
+            pool_bytes = (nums['y_bytes'] + nums['out_bytes']) / nums['fside_chunks'] + nums['rec_bytes']
+            t_pool, t_gemm = per_kernel['pool_quad_kernel'], per_kernel['ygemm_kernel']
+            pool_gbs = pool_bytes / (t_pool * 1e-3) / 1e9
+            gemm_tflops = nums['fside_flops'] / nums['fside_chunks'] / (t_gemm * 1e-3) / 1e12
+            step_bytes = nums['bytes'] + 2 * nums['y_bytes'] + nums['rec_bytes']
+            roofline = {
+                'bound': 'hbm', 'achieved': pool_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': pool_gbs / peaks['hbm_gbs'], 'traffic': traffic_of('pool_quad_kernel'),
+                'kernel': 'pool_quad_kernel', 'kernel_ms': t_pool, 'frames_per_launch': frames,
+                'kernel_share_of_step': t_pool * nums['fside_chunks'] * args.steps / total_ms,
+                'algorithmic_bytes_per_launch': pool_bytes,
+                'peak_source': peaks['source'],
+                'note': 'pooling of the per-layer products Y (fp32 [plane, layer, texel, C]): algorithmic bytes = Y once + tap '
+                        'records once + output once; the kernel is bound by the SM-side gather (L1 data pipe 63 %, issue '
+                        'slots 54 % in profiles/r1_fside_ncu_full.json), not by HBM',
+                'second_kernel': {
+                    'kernel': 'ygemm_kernel', 'bound': 'tensor', 'achieved': gemm_tflops, 'peak': peaks['tflops'],
+                    'unit': 'TFLOP/s', 'frac': gemm_tflops / peaks['tflops'], 'kernel_ms': t_gemm,
+                    'kernel_share_of_step': t_gemm * nums['fside_chunks'] * args.steps / total_ms,
+                    'traffic': traffic_of('ygemm_kernel'),
+                    'algorithmic_flops_per_launch': nums['fside_flops'] / nums['fside_chunks'],
+                    'tf32x3_ceiling_tflops': peaks['tflops'] / 6.0,
+                    'frac_of_tf32x3_ceiling': gemm_tflops / (peaks['tflops'] / 6.0),
+                    'note': 'image-plane contraction 2*B*V*fH*fW*C*(C*nl); fp32 parity needs 3 TF32 passes at half the bf16 '
+                            'rate: the ceiling of a 3xTF32 GEMM is peak/6'},
+                'step': {
+                    'fused_ms': kern, 'algorithmic_bytes': step_bytes,
+                    'hbm_frac': step_bytes / (kern * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                    'reference_formulation_tflops': tflops,
+                    'note': 'bytes = features + output + constants (SURVEY 8(d)) + Y written and read once + tap records; '
+                            'reference_formulation_tflops = grid-side flop count of the reference (2*L*W*K*C per view and '
+                            'scale) / time, for comparison with the fused grid-side kernel (--flags 32)'},
+            }
+        else:
+            roofline = {
+                'bound': 'tensor', 'achieved': tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                'frac': tflops / peaks['tflops'], 'traffic': traffic,
+                'kernel': 'aggregate_fwd_umma_kernel' if path.startswith('umma') else 'aggregate_fwd_simt_kernel',
+                'kernel_ms': kern, 'kernel_share_of_step': kern * args.steps / total_ms,
+                'algorithmic_flops_per_launch': nums['flops'], 'algorithmic_bytes_per_launch': nums['bytes'],
+                'hbm_achieved_gbs': gbs, 'hbm_peak_gbs': peaks['hbm_gbs'], 'hbm_frac': gbs / peaks['hbm_gbs'],
+                'peak_source': peaks['source'],
+                'tf32x3_ceiling_tflops': peaks['tflops'] / 6.0,
+                'frac_of_tf32x3_ceiling': tflops / (peaks['tflops'] / 6.0),
+                'note': 'collapse contraction counted grid-side (2*L*W*K*C per view and scale, as the reference computes '
+                        'it); fp32 parity needs 3 TF32 tensor-core passes, so executed tensor flops are 3x the algorithmic '
+                        'count and the TF32 rate is half the bf16 figure used as `peak`: the ceiling of this formulation '
+                        'is peak/6 (tf32x3_ceiling_tflops)',
+            }
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
@@ -364,21 +454,7 @@ def main():
             'clocks': clocks,
             'e2e': e2e,
             'gpu_launches': launches_per_step * args.steps,
-            'roofline': {
-                'bound': 'tensor', 'achieved': tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                'frac': tflops / peaks['tflops'], 'traffic': traffic,
-                'kernel': 'aggregate_fwd_umma_kernel' if path.startswith('umma') else 'aggregate_fwd_simt_kernel',
-                'kernel_ms': kern, 'kernel_share_of_step': kern * args.steps / total_ms,
-                'algorithmic_flops_per_launch': nums['flops'], 'algorithmic_bytes_per_launch': nums['bytes'],
-                'hbm_achieved_gbs': gbs, 'hbm_peak_gbs': peaks['hbm_gbs'], 'hbm_frac': gbs / peaks['hbm_gbs'],
-                'peak_source': peaks['source'],
-                'tf32x3_ceiling_tflops': peaks['tflops'] / 6.0,
-                'frac_of_tf32x3_ceiling': tflops / (peaks['tflops'] / 6.0),
-                'note': 'collapse contraction counted grid-side (2*L*W*K*C per view and scale, as the reference computes '
-                        'it); fp32 parity needs 3 TF32 tensor-core passes, so executed tensor flops are 3x the algorithmic '
-                        'count and the TF32 rate is half the bf16 figure used as `peak`: the ceiling of this formulation '
-                        'is peak/6 (tf32x3_ceiling_tflops)',
-            },
+            'roofline': roofline,
             'cpu_baseline': cpu_baseline,
         }
         print(json.dumps(line), flush=True)

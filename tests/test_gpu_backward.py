@@ -86,8 +86,10 @@ def test_fused_backward_matches_port(name, channels):
         _close(bs[s].grad.cpu().numpy(), gb[s].numpy(), f'{name} scale {s} dBias')
 
 
-def test_full_width_backward_matches_port():
-    """C = 256: tcgen05 forward (writes the ReLU mask) + CUDA backward on a strided sub-grid vs the float64 port.
+@pytest.mark.parametrize('path', ['fside_tf32x3', 'umma_tf32x3'])
+def test_full_width_backward_matches_port(path):
+    """C = 256: tcgen05 forward (either formulation; writes the ReLU mask) + CUDA backward on a strided sub-grid vs
+    the float64 port.
 
     ReLU makes the gradient discontinuous where a pre-activation is ~0, and 3xTF32 vs float64 may disagree on the
     sign of a few of the 2.7 M pre-activations; so the oracle gradient is taken through the SAME pass mask the
@@ -108,13 +110,15 @@ def test_full_width_backward_matches_port():
     fc = [t.cuda().requires_grad_(True) for t in feats]
     ws = [w.cuda().requires_grad_(True) for w, _ in params]
     bs = [b.cuda().requires_grad_(True) for _, b in params]
-    out = vfa_b200.aggregate(fc, table, ws, bs)
-    assert vfa_b200.last_kernel_path() == 'umma_tf32x3'
+    flags = vfa_b200.FLAG_GRID_SIDE if path == 'umma_tf32x3' else 0
+    out = vfa_b200.aggregate(fc, table, ws, bs, flags=flags)
+    assert vfa_b200.last_kernel_path() == path
     out.backward(gout.cuda())
     # the pass mask of the same forward
     mask = torch.empty(1, 2, 2, 8, LW, dtype=torch.int32, device='cuda')
     cl = [vfa_b200.to_channels_last(t.detach()) for t in fc]
-    vfa_b200.aggregate_forward_raw(cl, table, [w.detach() for w in ws], [b.detach() for b in bs], relu_mask=mask)
+    vfa_b200.aggregate_forward_raw(cl, table, [w.detach() for w in ws], [b.detach() for b in bs], flags=flags,
+                                   relu_mask=mask)
     bits = ((mask.cpu().long().unsqueeze(4) >> torch.arange(32).view(1, 1, 1, 1, 32, 1)) & 1).bool()
     bits = bits.reshape(1, 2, 2, 256, *grid.shape[:2])
 

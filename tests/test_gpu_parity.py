@@ -143,10 +143,18 @@ def test_fused_aggregate_matches_port(name):
     assert torch.equal(out, out2)
 
 
-@pytest.mark.parametrize('name,path', [('MultiviewC', 'umma_tf32x3'), ('MultiviewC', 'simt_fp32'),
-                                       ('MultiviewX', 'umma_tf32x3'), ('Wildtrack', 'umma_tf32x3')])
+PATH_FLAGS = {'simt_fp32': vfa_b200.FLAG_FORCE_SIMT,
+              'fside_tf32x3': vfa_b200.FLAG_FORCE_UMMA,                              # default for C = 256
+              'umma_tf32x3': vfa_b200.FLAG_FORCE_UMMA | vfa_b200.FLAG_GRID_SIDE}
+
+
+@pytest.mark.parametrize('name,path', [('MultiviewC', 'fside_tf32x3'), ('MultiviewC', 'umma_tf32x3'),
+                                       ('MultiviewC', 'simt_fp32'), ('MultiviewX', 'fside_tf32x3'),
+                                       ('MultiviewX', 'umma_tf32x3'), ('Wildtrack', 'fside_tf32x3'),
+                                       ('Wildtrack', 'umma_tf32x3')])
 def test_full_width_single_call_matches_port(name, path):
-    """C = 256 (the real channel count), full grid, one (view, scale) -- both kernel families vs the float64 port."""
+    """C = 256 (the real channel count), full grid, one (view, scale) -- the three kernel families (feature-side
+    tcgen05, grid-side fused tcgen05, generic fp32) vs the float64 port."""
     g = geometry.GEOMETRIES[name]
     grid = geometry.grid_for(g)
     calibs = synthetic.ring_calibs(g, n_views=1)
@@ -156,7 +164,7 @@ def test_full_width_single_call_matches_port(name, path):
                                 g.grid_height, g.cube_size, name, g.image_size).numpy()
     args = SimpleNamespace(data=name, image_size=g.image_size)
     m = vfa_b200.VFA(256, g.grid_height, g.cube_size, 1 / 16., args).cuda()
-    m.flags = vfa_b200.FLAG_FORCE_SIMT if path == 'simt_fp32' else vfa_b200.FLAG_FORCE_UMMA
+    m.flags = PATH_FLAGS[path]
     with torch.no_grad():
         m.collapse.weight.copy_(params[0][0])
         m.collapse.bias.copy_(params[0][1])
@@ -170,8 +178,8 @@ def test_full_width_single_call_matches_port(name, path):
 
 @pytest.mark.parametrize('name', NAMES)
 def test_tensor_core_path_matches_simt_path_full_size(name):
-    """Whole frame (all views, 3 scales, C=256, batch 2 -> no view split; batch 1 -> view-split + atomics): the
-    tcgen05 3xTF32 kernel against the fp32 FFMA kernel, both inside the north_star tolerance of each other."""
+    """Whole frame (all views, 3 scales, C=256, batch 2 -> no view split; batch 1 -> view-split + atomics): both
+    tcgen05 3xTF32 formulations against the fp32 FFMA kernel, inside the north_star tolerance of each other."""
     g = geometry.GEOMETRIES[name]
     grid = geometry.grid_for(g)
     calibs = synthetic.ring_calibs(g, n_views=g.n_views - 1, in_field=True)      # includes the ghost-producing camera
@@ -181,14 +189,15 @@ def test_tensor_core_path_matches_simt_path_full_size(name):
     table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
     simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
     assert vfa_b200.last_kernel_path() == 'simt_fp32'
-    umma = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_UMMA)
-    assert vfa_b200.last_kernel_path() == 'umma_tf32x3'
-    ok, err = _within(umma.cpu().numpy().astype(np.float64), simt.cpu().numpy().astype(np.float64))
-    print(f'{name}: umma vs simt outside tol {1 - ok.mean():.2e}, worst abs {err.max():.2e}')
-    assert ok.all()
-    one = vfa_b200.aggregate([f[:1] for f in feats], table, ws, bs, flags=vfa_b200.FLAG_FORCE_UMMA)
-    ok, err = _within(one.cpu().numpy().astype(np.float64), simt[:1].cpu().numpy().astype(np.float64))
-    assert ok.all()
+    for path in ('fside_tf32x3', 'umma_tf32x3'):
+        got = vfa_b200.aggregate(feats, table, ws, bs, flags=PATH_FLAGS[path])
+        assert vfa_b200.last_kernel_path() == path
+        ok, err = _within(got.cpu().numpy().astype(np.float64), simt.cpu().numpy().astype(np.float64))
+        print(f'{name}: {path} vs simt outside tol {1 - ok.mean():.2e}, worst abs {err.max():.2e}')
+        assert ok.all()
+        one = vfa_b200.aggregate([f[:1] for f in feats], table, ws, bs, flags=PATH_FLAGS[path])
+        ok, err = _within(one.cpu().numpy().astype(np.float64), simt[:1].cpu().numpy().astype(np.float64))
+        assert ok.all()
 
 
 def test_full_size_properties():
@@ -283,7 +292,7 @@ def test_bf16_feature_storage():
     table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
     f16 = [f.cuda().permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16) for f in feats]       # [B,V,H,W,C] bf16
     out = vfa_b200.aggregate(f16, table, ws, bs, channels_last=True)
-    assert vfa_b200.last_kernel_path() == 'umma_tf32x3_bf16feat' and out.dtype == torch.float32
+    assert vfa_b200.last_kernel_path() == 'fside_tf32x3_bf16feat' and out.dtype == torch.float32
     # (a) same quantised inputs, fp32 path: identical arithmetic after the widening -> fp32 tolerance
     fq = [t.float() for t in f16]
     ref = vfa_b200.aggregate(fq, table, ws, bs, channels_last=True)

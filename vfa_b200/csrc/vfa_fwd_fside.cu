@@ -455,8 +455,19 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
 // the four boxes once, loads every texel once (2 x LDG.128 per lane = the 1 KB row) and applies it to each cell whose
 // box contains it.  Lane 4*j + c computes the weight of cell c for column j of the current 8-column block; the weight
 // of (cell, texel) then reaches all lanes by one shuffle.  Output partial sums live in shared memory (48 KB per CTA).
-constexpr int QX = 4, QY = 3;                           // quads per CTA: 6 x 8 cells
+#ifndef VFA_QUAD_X
+#define VFA_QUAD_X 4
+#endif
+#ifndef VFA_QUAD_Y
+#define VFA_QUAD_Y 3
+#endif
+#ifndef VFA_QUAD_BATCH
+#define VFA_QUAD_BATCH 2
+#endif
+constexpr int QX = VFA_QUAD_X, QY = VFA_QUAD_Y;         // quads per CTA: 6 x 8 cells
 constexpr int QWARPS = QX * QY;
+constexpr int QTB = VFA_QUAD_BATCH;                     // texels of a union row in flight per warp (2 x LDG.128 each)
+static_assert(8 % QTB == 0, "");
 
 template <bool MASK>
 __global__ void __launch_bounds__(QWARPS * 32, 2) pool_quad_kernel(const PoolArgs a) {
@@ -518,33 +529,28 @@ __global__ void __launch_bounds__(QWARPS * 32, 2) pool_quad_kernel(const PoolArg
           for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
             const int rx = ux0 + cb + jl - x0;
             const float wx = (rx >= 0 && rx < nx) ? (rx == 0 ? wx_first : (rx == nx - 1 ? wx_last : 1.0f)) : 0.f;
-            const float wl = wy * wx;                   // weight of (cell cl, column cb + jl) in this row
+            float wl = wy * wx;                         // weight of (cell cl, column cb + jl) in this row
+            asm volatile("" : "+f"(wl));                // keep it in a register (no rematerialisation per shuffle)
             const uint32_t bm = __ballot_sync(0xffffffffu, wl != 0.f);     // bit 4*j + c
 #pragma unroll 1
-            for (int j = 0; j < 8 && (bm >> (4 * j)) != 0u; j += 2) {
-              const uint32_t m0 = (bm >> (4 * j)) & 0xfu, m1 = (bm >> (4 * j + 4)) & 0xfu;
+            for (int j = 0; j < 8 && (bm >> (4 * j)) != 0u; j += QTB) {
               const float* tp = rowp + (size_t)(cb + j) * CH;
-              float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0, a1 = a0, b1 = a0;
-              if (m0) {                                 // texels no box of the quad covers are never fetched
-                a0 = __ldg(reinterpret_cast<const float4*>(tp));
-                b0 = __ldg(reinterpret_cast<const float4*>(tp + 4));
-              }
-              if (m1) {
-                a1 = __ldg(reinterpret_cast<const float4*>(tp + CH));
-                b1 = __ldg(reinterpret_cast<const float4*>(tp + CH + 4));
-              }
-              if (m0) {
+              float4 va[QTB], vb[QTB];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float w = __shfl_sync(0xffffffffu, wl, 4 * j + c);
-                  if (w != 0.f) fma8(acc[c], w, a0, b0);
+              for (int k = 0; k < QTB; ++k) {
+                if ((bm >> (4 * (j + k))) & 0xfu) {     // texels no box of the quad covers are never fetched
+                  va[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH));
+                  vb[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH + 4));
                 }
               }
-              if (m1) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float w = __shfl_sync(0xffffffffu, wl, 4 * j + 4 + c);
-                  if (w != 0.f) fma8(acc[c], w, a1, b1);
+              for (int k = 0; k < QTB; ++k) {
+                if ((bm >> (4 * (j + k))) & 0xfu) {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    const float w = __shfl_sync(0xffffffffu, wl, 4 * (j + k) + c);
+                    if (w != 0.f) fma8(acc[c], w, va[k], vb[k]);
+                  }
                 }
               }
             }

@@ -170,7 +170,8 @@ struct UmmaArgs {
   int tiles_x;         // tiles are TILE_H x TILE_W blocks of BEV cells: tile -> (tile / tiles_x, tile % tiles_x)
   const TapRec* recs;  // [V][S][nl][LW] gather recipes (taps_table_kernel)
   int views_per_group;
-  int variant;         // debug bits: 1 = hi*hi only, 2 = no gather loads, 4 = no MMA, 8 = no weight loads, 16 = no output pass, 32 = no drain
+  int variant;         // debug bits: 1 = hi*hi only, 2 = no gather loads, 4 = no MMA, 8 = no weight loads, 16 = no output pass, 32 = no drain,
+                       // 64 = feature-side: GEMM only, 128 = feature-side: pooling only, 256 = reuse the tap records
 };
 
 // ---- pooling producers ----------------------------------------------------------------------------------------
@@ -866,8 +867,10 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, size_t 
   // gather recipes of every (view, scale, layer, cell): behind the prepared weights in the workspace
   {
     TapRec* recs = reinterpret_cast<TapRec*>(reinterpret_cast<uint8_t*>(ws) + (size_t)p.S * per_scale);
-    taps_table_kernel<<<148 * 8, 256, 0, st>>>(p, recs);
-    VFA_LAUNCH_CHECK("taps_table_kernel");
+    if (!(a.variant & 256)) {     // (debug bit 256: reuse the records already in the workspace)
+      taps_table_kernel<<<148 * 8, 256, 0, st>>>(p, recs);
+      VFA_LAUNCH_CHECK("taps_table_kernel");
+    }
     a.recs = recs;
   }
   if (!grid_side_requested(flags)) {
