@@ -464,13 +464,19 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
 #ifndef VFA_QUAD_BATCH
 #define VFA_QUAD_BATCH 2
 #endif
+#ifndef VFA_QUAD_MINBLOCKS
+#define VFA_QUAD_MINBLOCKS 2
+#endif
+#ifndef VFA_QUAD_PREFETCH
+#define VFA_QUAD_PREFETCH 0
+#endif
 constexpr int QX = VFA_QUAD_X, QY = VFA_QUAD_Y;         // quads per CTA: 6 x 8 cells
 constexpr int QWARPS = QX * QY;
 constexpr int QTB = VFA_QUAD_BATCH;                     // texels of a union row in flight per warp (2 x LDG.128 each)
 static_assert(8 % QTB == 0, "");
 
 template <bool MASK>
-__global__ void __launch_bounds__(QWARPS * 32, 2) pool_quad_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_kernel(const PoolArgs a) {
   __shared__ float out_s[QWARPS][4][CH];
   const AggParams& p = a.p;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -532,8 +538,9 @@ __global__ void __launch_bounds__(QWARPS * 32, 2) pool_quad_kernel(const PoolArg
             float wl = wy * wx;                         // weight of (cell cl, column cb + jl) in this row
             asm volatile("" : "+f"(wl));                // keep it in a register (no rematerialisation per shuffle)
             const uint32_t bm = __ballot_sync(0xffffffffu, wl != 0.f);     // bit 4*j + c
-#pragma unroll 1
-            for (int j = 0; j < 8 && (bm >> (4 * j)) != 0u; j += QTB) {
+#pragma unroll          // j static: the shuffles get immediate lane indices
+            for (int j = 0; j < 8; j += QTB) {
+              if ((bm >> (4 * j)) == 0u) break;
               const float* tp = rowp + (size_t)(cb + j) * CH;
               float4 va[QTB], vb[QTB];
 #pragma unroll
@@ -541,6 +548,10 @@ __global__ void __launch_bounds__(QWARPS * 32, 2) pool_quad_kernel(const PoolArg
                 if ((bm >> (4 * (j + k))) & 0xfu) {     // texels no box of the quad covers are never fetched
                   va[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH));
                   vb[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH + 4));
+#if VFA_QUAD_PREFETCH
+                  // the same column of the next union row: one warp-wide prefetch covers the texel's 8 lines
+                  if (ty < uy1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k * CH + (size_t)fw * CH));
+#endif
                 }
               }
 #pragma unroll
@@ -548,8 +559,9 @@ __global__ void __launch_bounds__(QWARPS * 32, 2) pool_quad_kernel(const PoolArg
                 if ((bm >> (4 * (j + k))) & 0xfu) {
 #pragma unroll
                   for (int c = 0; c < 4; ++c) {
-                    const float w = __shfl_sync(0xffffffffu, wl, 4 * (j + k) + c);
-                    if (w != 0.f) fma8(acc[c], w, va[k], vb[k]);
+                    // weight 0 for a cell whose box does not hold this texel: the FMA is issued anyway (a predicate
+                    // would cost an extra instruction per cell and texel)
+                    fma8(acc[c], __shfl_sync(0xffffffffu, wl, 4 * (j + k) + c), va[k], vb[k]);
                   }
                 }
               }
