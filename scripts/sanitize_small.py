@@ -11,7 +11,7 @@ calibs = synthetic.ring_calibs(g, n_views=2, in_field=True).cuda()
 zs = list(range(0, g.grid_height, g.cube_size[2]))
 geom = vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid.shape[:2], g.name, g.image_size)
 table = vfa_b200.build_table(geom, calibs, grid)
-for C, flags in ((256, 0), (256, vfa_b200.FLAG_FORCE_SIMT), (16, 0)):
+for C, flags in ((256, 0), (256, vfa_b200.FLAG_GRID_SIDE), (256, vfa_b200.FLAG_FORCE_SIMT), (16, 0)):
     feats = [f.cuda().requires_grad_(True) for f in synthetic.features(g, batch=2, n_views=3, channels=C, seed=1)]
     params = synthetic.collapse_params(g, channels=C, seed=1)
     ws = [w.cuda().requires_grad_(True) for w, _ in params]

@@ -306,3 +306,54 @@ def test_bf16_feature_storage():
     assert rel < 4e-3
     with pytest.raises(RuntimeError, match='forward-only'):
         vfa_b200.aggregate(f16, table, [w.requires_grad_(True) for w in ws], bs, channels_last=True)
+
+
+def test_feature_side_chunking_and_ragged_grids(monkeypatch):
+    """Feature-side forward (default, C = 256): frame chunks (Y budget forced down to one frame per chunk), grids whose
+    sides are not multiples of the 2 x 2 quads / 6 x 8 CTA tiles, a texel-row count that is not a multiple of the
+    256-row GEMM tile -- all bit-identical to the unchunked run and inside the tolerance of the fp32 FFMA kernel."""
+    g = geometry.MULTIVIEWC
+    full = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g, n_views=2, in_field=True)
+    params = synthetic.collapse_params(g, seed=4)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    feats = [f.cuda() for f in synthetic.features(g, batch=3, n_views=3, seed=4)]
+    for sl in ((slice(0, 45, 2), slice(1, 60, 3)),            # 23 x 20 cells
+               (slice(0, 7), slice(0, 9)),                    # 7 x 9: one partial CTA tile, odd quads on both sides
+               (slice(100, 101), slice(0, 156))):             # a single row
+        grid = full[sl].contiguous()
+        table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+        monkeypatch.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
+        ref = vfa_b200.aggregate(feats, table, ws, bs)
+        assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
+        simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
+        ok, err = _within(ref.cpu().numpy().astype(np.float64), simt.cpu().numpy().astype(np.float64))
+        assert ok.all(), f'grid {tuple(grid.shape[:2])}: worst {err.max():.2e}'
+        # Y of one MultiviewC frame with 3 views is 291 MB: 300 MB -> one frame per chunk, 3 chunks
+        monkeypatch.setenv('VFA_FSIDE_Y_BUDGET_MB', '300')
+        chunked = vfa_b200.aggregate(feats, table, ws, bs)
+        assert torch.equal(chunked, ref)
+    monkeypatch.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
+
+
+def test_relu_mask_agrees_between_formulations():
+    """The ReLU pass bits the backward consumes: feature-side and grid-side forwards may only disagree where the
+    pre-activation is within rounding of zero."""
+    g = geometry.MULTIVIEWC
+    grid = geometry.grid_for(g)[::2, ::2].contiguous()
+    LW = grid.shape[0] * grid.shape[1]
+    calibs = synthetic.ring_calibs(g, n_views=2)
+    feats = [vfa_b200.to_channels_last(f.cuda()) for f in synthetic.features(g, batch=2, n_views=2, seed=12)]
+    params = synthetic.collapse_params(g, seed=12)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    masks = []
+    for flags in (0, vfa_b200.FLAG_GRID_SIDE):
+        m = torch.zeros(2, 2, 3, 8, LW, dtype=torch.int32, device='cuda')
+        vfa_b200.aggregate_forward_raw(feats, table, ws, bs, flags=flags, relu_mask=m)
+        masks.append(m)
+    diff = (masks[0] ^ masks[1]).cpu().numpy().view(np.uint32)
+    flipped = int(np.unpackbits(diff.view(np.uint8)).sum())
+    total = diff.size * 32
+    print(f'mask bits that differ: {flipped} of {total}')
+    assert flipped <= total * 1e-4

@@ -630,7 +630,11 @@ size_t fside_y_bytes_per_frame(const AggParams& p) {
 
 // frames per chunk for a Y budget (the workspace holds Y of one chunk)
 int fside_chunk_frames(const AggParams& p) {
-  const size_t budget = (size_t)6 << 30;
+  size_t budget = (size_t)6 << 30;
+  if (const char* e = getenv("VFA_FSIDE_Y_BUDGET_MB")) {      // tests: force several chunks on small inputs
+    const long long mb = atoll(e);
+    if (mb > 0) budget = (size_t)mb << 20;
+  }
   const size_t per = fside_y_bytes_per_frame(p);
   size_t cb = budget / per;
   if (cb < 1) cb = 1;
