@@ -86,8 +86,9 @@ def test_fused_backward_matches_port(name, channels):
         _close(bs[s].grad.cpu().numpy(), gb[s].numpy(), f'{name} scale {s} dBias')
 
 
-@pytest.mark.parametrize('path', ['fside_tf32x3', 'umma_tf32x3'])
-def test_full_width_backward_matches_port(path):
+@pytest.mark.parametrize('path,bwd', [('fside_tf32x3', 'gather'), ('umma_tf32x3', 'gather'), ('fside_tf32x3', 'overflow'),
+                                      ('fside_tf32x3', 'scatter')])
+def test_full_width_backward_matches_port(path, bwd, monkeypatch):
     """C = 256: tcgen05 forward (either formulation; writes the ReLU mask) + CUDA backward on a strided sub-grid vs
     the float64 port.
 
@@ -110,6 +111,12 @@ def test_full_width_backward_matches_port(path):
     fc = [t.cuda().requires_grad_(True) for t in feats]
     ws = [w.cuda().requires_grad_(True) for w, _ in params]
     bs = [b.cuda().requires_grad_(True) for _, b in params]
+    # backward variants: CSR gather + tcgen05 dFeature product (default); the same with a CSR too small for most rows
+    # (they are completed by the atomic overflow kernel); the older scatter + cuBLAS path
+    if bwd == 'overflow':
+        monkeypatch.setenv('VFA_BWD_CSR_PER_BOX', '1')
+    if bwd == 'scatter':
+        monkeypatch.setenv('VFA_BWD_SCATTER', '1')
     flags = vfa_b200.FLAG_GRID_SIDE if path == 'umma_tf32x3' else 0
     out = vfa_b200.aggregate(fc, table, ws, bs, flags=flags)
     assert vfa_b200.last_kernel_path() == path

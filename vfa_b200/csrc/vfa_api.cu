@@ -49,7 +49,7 @@ size_t umma_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*, uint32_t)
 bool umma_supported(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
 int launch_fwd_umma(AggParams, const float* const*, void*, size_t, uint32_t, cudaStream_t);
 size_t bwd_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*);
-int launch_bwd(AggParams, const float* const*, const float*, float* const*, float* const*, float* const*, void*,
+int launch_bwd(AggParams, const float* const*, const float*, float* const*, float* const*, float* const*, void*, size_t,
                cudaStream_t);
 
 static int validate_geometry(const vfa_geometry_t* g) {
@@ -254,7 +254,8 @@ int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
               "workspace must be a 256-byte aligned device pointer");
   VFA_REQUIRE(workspace_bytes >= bwd_workspace_bytes(geom, shape), VFA_ERR_WORKSPACE, "workspace %zu < required %zu",
               workspace_bytes, bwd_workspace_bytes(geom, shape));
-  return launch_bwd(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, d_workspace, (cudaStream_t)stream);
+  return launch_bwd(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, d_workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -493,6 +493,32 @@ __global__ void __launch_bounds__(256) unprep_dweight_kernel(const float* __rest
 
 int launch_transpose(const float*, float*, long long, int, long long, cudaStream_t);
 
+// row-major C[n x m] += B^T[n x k] * A[k x m]   (A: [k, lda >= m], B: [k, ldb >= n]) through the lazily loaded cuBLAS:
+// the dWeight product of the feature-side backwards (fp32 SGEMM, no TF32)
+int fs_sgemm_nt_acc(cudaStream_t st, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc) {
+  fs::Cublas* cb = nullptr;
+  if (int rc = fs::get_cublas(&cb)) return rc;
+  VFA_REQUIRE(cb->set_stream(cb->handle, st) == 0, VFA_ERR_CUDA, "cublasSetStream failed");
+  const float one = 1.f;
+  VFA_REQUIRE(cb->sgemm(cb->handle, 0, 1, m, n, k, &one, a, lda, b, ldb, &one, c, ldc) == 0, VFA_ERR_CUDA,
+              "cublasSgemm (dWeight) failed");
+  return VFA_OK;
+}
+
+int launch_unprep_dweight(const float* dwr, float* dw, int C, int nl, cudaStream_t st) {
+  const size_t per_scale = (size_t)C * C * nl;
+  const int blocks = (int)((per_scale + 255) / 256 < 148 * 8 ? (per_scale + 255) / 256 : 148 * 8);
+  fs::unprep_dweight_kernel<<<blocks, 256, 0, st>>>(dwr, dw, C, nl);
+  VFA_LAUNCH_CHECK("unprep_dweight_kernel");
+  return VFA_OK;
+}
+
+// C = 256: gather-form backward with the tcgen05 dFeature product (vfa_bwd_fside.cu)
+size_t bwd_fside_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh);
+int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_grad_out, float* const* d_grad_feats,
+                     float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, cudaStream_t st);
+static bool gather_backward(int channels) { return channels == 256 && getenv("VFA_BWD_SCATTER") == nullptr; }
+
 static size_t fs_gs_elems(const AggParams& p) {
   size_t px = 0;
   for (int s = 0; s < p.S; ++s) px += (size_t)p.sc[s].fh * p.sc[s].fw;
@@ -602,12 +628,19 @@ size_t bwd_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh) {
     elems = 2 * (size_t)sh->n_scales * per_scale + (size_t)g->grid_l * g->grid_w * sh->channels +
             px * g->n_layers * sh->channels;
   }
-  return elems * sizeof(float);
+  size_t bytes = elems * sizeof(float);
+  if (sh->channels == 256) {                                       // sized for either C = 256 path
+    const size_t g2 = bwd_fside_workspace_bytes(g, sh);
+    if (g2 > bytes) bytes = g2;
+  }
+  return bytes;
 }
 
 int launch_bwd(AggParams p, const float* const* d_weight, const float* d_grad_out, float* const* d_grad_feats,
-               float* const* d_grad_weight, float* const* d_grad_bias, void* ws, cudaStream_t st) {
+               float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, cudaStream_t st) {
   VFA_REQUIRE(p.C <= MAXC, VFA_ERR_UNSUPPORTED, "backward supports up to %d channels (got %d)", MAXC, p.C);
+  if (gather_backward(p.C))
+    return launch_bwd_fside(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, ws, ws_bytes, st);
   if (feature_side_ok(p) && getenv("VFA_BWD_GENERIC") == nullptr)
     return launch_bwd_feature_side(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, ws, st);
   BwdParams q;

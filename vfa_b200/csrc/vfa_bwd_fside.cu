@@ -1,0 +1,560 @@
+// Backward of the aggregation for C = 256, on the image plane and without scatter atomics.
+//
+// Transposing the feature-side forward (vfa_fwd_fside.cu):  out = sum_{v,s} relu(b_s + sum_n pool_n(f W_n^T))  gives
+//
+//   gm[b,v,s][cell, o]       = dOut[b, o, cell] * relu_mask[b, v, s, o, cell]                            (mask_grad_kernel)
+//   dBias_s[o]               = sum_{b, v, cell} gm
+//   Gs[b,v,s][texel, n, o]   = sum_{cells whose layer-n box holds texel} wy * wx * gm[cell, o]           (dy_gather_kernel)
+//   dFeat[b,v,s][texel, c]   = sum_{n,o} Gs[texel, n, o] * W_s[o, c*nl + n]          tcgen05 3xTF32 (ygemm_kernel, MODE 1)
+//   dWeight_s[o, c*nl + n]  += sum_{b,v,texel} Gs[texel, n, o] * f[texel, c]          library SGEMM (cuBLAS, fp32)
+//
+// The reference's autograd scatters through 4 grid_sampler backwards and two reverse cumsums (vfa_op.py:110-124); the
+// first version of this path scattered Gs with atomics (vfa_bwd.cu, still used for C < 256) and spent its time in the L2
+// atomic units.  Here the box -> texel relation is inverted once per call into a CSR list (texel row -> (cell, weight)
+// entries: count, exclusive scan, fill; the projection is static, so the list is the same for every frame), and Gs is
+// GATHERED: one warp per texel row of a layer plane, 8 channels per lane, every row written exactly once, no memset, no
+// atomics.  The list has a fixed capacity (12 entries per box on average, 1.6x - 2.3x the rigs' need); rows beyond it
+// (none on the three rigs) are completed by overflow_scatter_kernel with atomics, so the result is exact for any rig.
+#include <stdlib.h>
+
+#include "vfa_common.cuh"
+#include "vfa_umma_ptx.cuh"
+
+namespace vfa {
+
+// vfa_fwd_umma.cu / vfa_fwd_fside.cu / vfa_bwd.cu / vfa_table.cu
+int launch_taps_table(const AggParams& p, TapRec* recs, cudaStream_t st);
+int launch_ygemm_accum(const float* const* a_rows, float* const* out, const uint8_t* const* wprep_t, const int* rows,
+                       int nl, int S, cudaStream_t st);
+int fs_sgemm_nt_acc(cudaStream_t st, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc);
+int launch_unprep_dweight(const float* dwr, float* dw, int C, int nl, cudaStream_t st);
+int launch_transpose(const float*, float*, long long, int, long long, cudaStream_t);
+
+namespace bfs {
+
+using umma::swz;
+using umma::to_tf32;
+
+constexpr int CH = 256;
+constexpr int KCH = 32;
+constexpr int B_BYTES = CH * KCH * 4;
+constexpr int CSR_PER_BOX = 12;            // capacity of the entry list, per (view, scale, layer, cell) box
+
+struct __align__(8) CsrEntry {
+  int cell;
+  float w;
+};
+
+// Rows of the CSR = texels of every (scale, view, layer) plane: row = base[s] + (v * nl + n) * hw[s] + texel.
+struct RowMap {
+  int base[VFA_MAX_SCALES];
+  int hw[VFA_MAX_SCALES];
+  int fw[VFA_MAX_SCALES];
+  int total;
+};
+
+// collapse.weight [C, C*nl] (column c*nl+n) -> per scale, per K chunk kc = n*(C/32) + o/32 a 64 KB block
+// [hi: 256 rows (c) x 128 B (32 o), swizzled][lo: same]: the B operand of dFeat = Gs * W.
+__global__ void __launch_bounds__(256) prep_weight_umma_t_kernel(const float* __restrict__ w, uint8_t* __restrict__ wp, int nl) {
+  const int K = CH * nl;
+  const long long total = (long long)CH * K;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % KCH);
+    const int c = (int)((idx / KCH) % CH);
+    const int kc = (int)(idx / ((long long)KCH * CH));
+    const int n = kc / (CH / KCH), oc = kc % (CH / KCH);
+    const int o = oc * KCH + kk;
+    const float v = w[(long long)o * K + (long long)c * nl + n];
+    const uint32_t hi = to_tf32(v);
+    const uint32_t lo = to_tf32(v - __uint_as_float(hi));
+    uint8_t* blk = wp + (long long)kc * (2 * B_BYTES);
+    const uint32_t off = swz(c, kk >> 2) + (kk & 3) * 4;
+    *reinterpret_cast<uint32_t*>(blk + off) = hi;
+    *reinterpret_cast<uint32_t*>(blk + B_BYTES + off) = lo;
+  }
+}
+
+// ---- CSR of the box -> texel relation ----------------------------------------------------------------------------
+__device__ __forceinline__ float rec_wx(const TapRec& r, int nx, int i) {
+  return i == 0 ? r.wx_first : (i == nx - 1 ? r.wx_last : 1.0f);
+}
+__device__ __forceinline__ float rec_wy(const TapRec& r, int ny, int i) {
+  return i == 0 ? r.wy_first : (i == ny - 1 ? r.wy_last : r.wy_mid);
+}
+
+// FILL = false: counts[row] += 1 per tap;  FILL = true: entries[offsets[row] + cursor[row]++] = (cell, weight)
+template <bool FILL>
+__global__ void __launch_bounds__(256) csr_walk_kernel(AggParams p, const TapRec* __restrict__ recs, RowMap rm,
+                                                       int* __restrict__ counts, const int* __restrict__ offsets,
+                                                       CsrEntry* __restrict__ entries, int capacity) {
+  const long long total = (long long)p.V * p.S * p.nl * p.LW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const TapRec r = recs[idx];
+    const int nx = r.nxy & 0xffff, ny = r.nxy >> 16;
+    if (nx == 0) continue;
+    const int cell = (int)(idx % p.LW);
+    const int n = (int)((idx / p.LW) % p.nl);
+    const int s = (int)((idx / ((long long)p.LW * p.nl)) % p.S);
+    const int v = (int)(idx / ((long long)p.LW * p.nl * p.S));
+    const int fw = s == 0 ? rm.fw[0] : (s == 1 ? rm.fw[1] : rm.fw[2]);
+    const int hw = s == 0 ? rm.hw[0] : (s == 1 ? rm.hw[1] : rm.hw[2]);
+    const int base = s == 0 ? rm.base[0] : (s == 1 ? rm.base[1] : rm.base[2]);
+    const int row0 = base + (v * p.nl + n) * hw + (r.xy >> 16) * fw + (r.xy & 0xffff);
+    for (int ty = 0; ty < ny; ++ty) {
+      const float wy = rec_wy(r, ny, ty);
+      for (int tx = 0; tx < nx; ++tx) {
+        const float w = wy * rec_wx(r, nx, tx);
+        if (w == 0.f) continue;                          // the forward never fetches these taps either
+        const int row = row0 + ty * fw + tx;
+        if (!FILL) {
+          atomicAdd(counts + row, 1);
+        } else if (offsets[row + 1] <= capacity) {
+          const int pos = atomicAdd(counts + row, 1);
+          CsrEntry e;
+          e.cell = cell;
+          e.w = w;
+          entries[offsets[row] + pos] = e;
+        }
+      }
+    }
+  }
+}
+
+// exclusive scan of n ints in three passes (1024 elements per block)
+__global__ void __launch_bounds__(1024) scan_block_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                          int* __restrict__ block_sums, int n) {
+  __shared__ int warp_sums[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = i < n ? in[i] : 0;
+  int v = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  if (lane == 31) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  const int incl = v + (warp > 0 ? warp_sums[warp - 1] : 0);
+  if (i < n) out[i] = incl - x;
+  if (threadIdx.x == 1023) block_sums[blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ block_sums, int nblocks) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const int x = i < nblocks ? block_sums[i] : 0;
+    int v = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = v + (warp > 0 ? warp_sums[warp - 1] : 0);
+    if (i < nblocks) block_sums[i] = carry + incl - x;      // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + incl;
+    __syncthreads();
+  }
+}
+// out[i] += block offset; out[n] = grand total
+__global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, const int* __restrict__ block_sums,
+                                                        const int* __restrict__ in, int n) {
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) {
+    const int o = out[i] + block_sums[blockIdx.x];
+    out[i] = o;
+    if (i == n - 1) out[n] = o + in[i];
+  }
+}
+
+// ---- gm = dOut^T * mask, dBias ---------------------------------------------------------------------------------------
+struct GradParams {
+  AggParams p;
+  const float* gt;           // [nb][LW][C]  dOut of the chunk, transposed
+  float* gm;                 // [nb][V][S][LW][C]
+  float* gbias[VFA_MAX_SCALES];
+  int b0;
+};
+
+constexpr int MG_WARPS = 8, MG_CELLS = 16;       // cells per warp
+
+__global__ void __launch_bounds__(MG_WARPS * 32) mask_grad_kernel(const GradParams q) {
+  __shared__ float bsum[MG_WARPS][CH];
+  const AggParams& p = q.p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bvs = blockIdx.y;                                  // (bl * V + v) * S + s
+  const int s = bvs % p.S, v = (bvs / p.S) % p.V, bl = bvs / (p.S * p.V);
+  const int b = q.b0 + bl;
+  const uint32_t* mrow = p.mask + ((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (lane >> 2)) * p.LW;
+  const float* grow = q.gt + (size_t)bl * p.LW * CH + lane * 8;
+  float* out = q.gm + (size_t)bvs * p.LW * CH + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int cell0 = (blockIdx.x * MG_WARPS + warp) * MG_CELLS;
+  for (int k = 0; k < MG_CELLS; ++k) {
+    const int cell = cell0 + k;
+    if (cell >= p.LW) break;
+    const uint32_t bits = (__ldg(mrow + cell) >> (8 * (lane & 3))) & 0xffu;
+    float4 a = __ldg(reinterpret_cast<const float4*>(grow + (size_t)cell * CH));
+    float4 c = __ldg(reinterpret_cast<const float4*>(grow + (size_t)cell * CH + 4));
+    a.x = (bits & 1u) ? a.x : 0.f;
+    a.y = (bits & 2u) ? a.y : 0.f;
+    a.z = (bits & 4u) ? a.z : 0.f;
+    a.w = (bits & 8u) ? a.w : 0.f;
+    c.x = (bits & 16u) ? c.x : 0.f;
+    c.y = (bits & 32u) ? c.y : 0.f;
+    c.z = (bits & 64u) ? c.z : 0.f;
+    c.w = (bits & 128u) ? c.w : 0.f;
+    *reinterpret_cast<float4*>(out + (size_t)cell * CH) = a;
+    *reinterpret_cast<float4*>(out + (size_t)cell * CH + 4) = c;
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += c.x; acc[5] += c.y; acc[6] += c.z; acc[7] += c.w;
+  }
+  float* gb = s == 0 ? q.gbias[0] : (s == 1 ? q.gbias[1] : q.gbias[2]);
+  if (gb == nullptr) return;                                   // uniform per CTA
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bsum[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < MG_WARPS; ++w) t += bsum[w][threadIdx.x];
+  if (t != 0.f) atomicAdd(gb + threadIdx.x, t);
+}
+
+// ---- Gs = gather of gm through the CSR ------------------------------------------------------------------------------
+struct GatherParams {
+  AggParams p;
+  RowMap rm;
+  const int* offsets;
+  const CsrEntry* entries;
+  const float* gm;                  // [nb][V][S][LW][C]
+  float* gs[VFA_MAX_SCALES];        // per scale [nb*V planes][texel][nl][C]
+  int tile_begin[VFA_MAX_SCALES + 1];   // CTA tiles (4 x 4 texels of one (view, layer) plane) per scale, prefix
+  int tiles_x[VFA_MAX_SCALES], tiles[VFA_MAX_SCALES];
+  int capacity;
+};
+
+constexpr int GT = 4;                            // texel tile side: one warp per texel
+
+__global__ void __launch_bounds__(GT * GT * 32, 2) dy_gather_kernel(const GatherParams q) {
+  const AggParams& p = q.p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bx = blockIdx.x, bl = blockIdx.y;
+  const int s = (p.S > 2 && bx >= q.tile_begin[2]) ? 2 : ((p.S > 1 && bx >= q.tile_begin[1]) ? 1 : 0);
+  const int tb = s == 0 ? 0 : (s == 1 ? q.tile_begin[1] : q.tile_begin[2]);
+  const int tiles = s == 0 ? q.tiles[0] : (s == 1 ? q.tiles[1] : q.tiles[2]);
+  const int tiles_x = s == 0 ? q.tiles_x[0] : (s == 1 ? q.tiles_x[1] : q.tiles_x[2]);
+  const int fw = s == 0 ? q.rm.fw[0] : (s == 1 ? q.rm.fw[1] : q.rm.fw[2]);
+  const int hw = s == 0 ? q.rm.hw[0] : (s == 1 ? q.rm.hw[1] : q.rm.hw[2]);
+  const int base = s == 0 ? q.rm.base[0] : (s == 1 ? q.rm.base[1] : q.rm.base[2]);
+  float* gs = s == 0 ? q.gs[0] : (s == 1 ? q.gs[1] : q.gs[2]);
+  const int vn = (bx - tb) / tiles, tile = (bx - tb) % tiles;
+  const int v = vn / p.nl, n = vn % p.nl;
+  const int ty = (tile / tiles_x) * GT + warp / GT, tx = (tile % tiles_x) * GT + warp % GT;
+  if (tx >= fw || ty * fw + tx >= hw) return;
+  const int texel = ty * fw + tx;
+  const int row = base + vn * hw + texel;
+  const int e0 = __ldg(q.offsets + row), e1 = __ldg(q.offsets + row + 1);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (e1 <= q.capacity) {
+    const float* gm = q.gm + (((size_t)bl * p.V + v) * p.S + s) * p.LW * CH + lane * 8;
+    const int2* ent = reinterpret_cast<const int2*>(q.entries);
+    int e = e0;
+    for (; e + 1 < e1; e += 2) {                       // two entries (4 x LDG.128) in flight
+      const int2 a = __ldg(ent + e), c = __ldg(ent + e + 1);
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH + 4));
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)c.x * CH));
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)c.x * CH + 4));
+      const float wa = __int_as_float(a.y), wc = __int_as_float(c.y);
+      acc[0] += wa * a0.x; acc[1] += wa * a0.y; acc[2] += wa * a0.z; acc[3] += wa * a0.w;
+      acc[4] += wa * a1.x; acc[5] += wa * a1.y; acc[6] += wa * a1.z; acc[7] += wa * a1.w;
+      acc[0] += wc * c0.x; acc[1] += wc * c0.y; acc[2] += wc * c0.z; acc[3] += wc * c0.w;
+      acc[4] += wc * c1.x; acc[5] += wc * c1.y; acc[6] += wc * c1.z; acc[7] += wc * c1.w;
+    }
+    if (e < e1) {
+      const int2 a = __ldg(ent + e);
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH + 4));
+      const float wa = __int_as_float(a.y);
+      acc[0] += wa * a0.x; acc[1] += wa * a0.y; acc[2] += wa * a0.z; acc[3] += wa * a0.w;
+      acc[4] += wa * a1.x; acc[5] += wa * a1.y; acc[6] += wa * a1.z; acc[7] += wa * a1.w;
+    }
+  }
+  float* dst = gs + ((((size_t)bl * p.V + v) * hw + texel) * p.nl + n) * CH + lane * 8;
+  *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// Rows the CSR could not hold (offsets[row + 1] > capacity): completed with atomics.  Exits at once when there are none.
+__global__ void __launch_bounds__(256) overflow_scatter_kernel(const GatherParams q, const TapRec* __restrict__ recs, int nb) {
+  const AggParams& p = q.p;
+  if (__ldg(q.offsets + q.rm.total) <= q.capacity) return;
+  const int lane = threadIdx.x & 31;
+  const long long boxes = (long long)p.V * p.S * p.nl * p.LW;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < boxes; idx += warps) {
+    const TapRec r = recs[idx];
+    const int nx = r.nxy & 0xffff, ny = r.nxy >> 16;
+    if (nx == 0) continue;
+    const int cell = (int)(idx % p.LW);
+    const int n = (int)((idx / p.LW) % p.nl);
+    const int s = (int)((idx / ((long long)p.LW * p.nl)) % p.S);
+    const int v = (int)(idx / ((long long)p.LW * p.nl * p.S));
+    const int fw = q.rm.fw[s], hw = q.rm.hw[s];
+    const int tex0 = (r.xy >> 16) * fw + (r.xy & 0xffff);
+    const int row0 = q.rm.base[s] + (v * p.nl + n) * hw + tex0;
+    for (int ty = 0; ty < ny; ++ty) {
+      const float wy = rec_wy(r, ny, ty);
+      for (int tx = 0; tx < nx; ++tx) {
+        const float w = wy * rec_wx(r, nx, tx);
+        const int row = row0 + ty * fw + tx;
+        if (w == 0.f || __ldg(q.offsets + row + 1) <= q.capacity) continue;
+        for (int bl = 0; bl < nb; ++bl) {
+          const float* g = q.gm + ((((size_t)bl * p.V + v) * p.S + s) * p.LW + cell) * CH + lane * 8;
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(g)), g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+          float* dst = q.gs[s] + ((((size_t)bl * p.V + v) * hw + tex0 + ty * fw + tx) * p.nl + n) * CH + lane * 8;
+          atomicAdd(reinterpret_cast<float4*>(dst), make_float4(w * g0.x, w * g0.y, w * g0.z, w * g0.w));
+          atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(w * g1.x, w * g1.y, w * g1.z, w * g1.w));
+        }
+      }
+    }
+  }
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Plan {
+  size_t px;                 // texels of one view over all scales
+  int rows;                  // CSR rows
+  int capacity;
+  size_t off_wprep, off_dwr, off_recs, off_counts, off_offsets, off_bsums, off_entries, off_chunk;
+  size_t per_frame;          // bytes of (gT + gm + Gs) for one frame
+};
+
+static Plan make_plan(int V, int S, int nl, size_t LW, const int* fh, const int* fw) {
+  Plan pl;
+  pl.px = 0;
+  for (int s = 0; s < S; ++s) pl.px += (size_t)fh[s] * fw[s];
+  pl.rows = (int)(pl.px * V * nl);
+  int per_box = CSR_PER_BOX;
+  if (const char* e = getenv("VFA_BWD_CSR_PER_BOX")) {     // tests: a tiny list forces the overflow path
+    const int v = atoi(e);
+    if (v > 0) per_box = v;
+  }
+  pl.capacity = (int)((size_t)per_box * V * S * nl * LW);
+  size_t o = 0;
+  pl.off_wprep = o;   o += align256((size_t)S * nl * (CH / KCH) * (2 * B_BYTES));
+  pl.off_dwr = o;     o += align256((size_t)S * CH * CH * nl * sizeof(float));
+  pl.off_recs = o;    o += align256((size_t)V * S * nl * LW * sizeof(TapRec));
+  pl.off_counts = o;  o += align256(((size_t)pl.rows + 1) * sizeof(int));
+  pl.off_offsets = o; o += align256(((size_t)pl.rows + 1) * sizeof(int));
+  pl.off_bsums = o;   o += align256(((size_t)pl.rows / 1024 + 2) * sizeof(int));
+  pl.off_entries = o; o += align256((size_t)pl.capacity * sizeof(CsrEntry));
+  pl.off_chunk = o;
+  pl.per_frame = (LW * CH + (size_t)V * S * LW * CH + (size_t)V * pl.px * nl * CH) * sizeof(float);
+  return pl;
+}
+
+static int chunk_frames(const Plan& pl, int B) {
+  size_t budget = (size_t)6 << 30;
+  if (const char* e = getenv("VFA_FSIDE_Y_BUDGET_MB")) {
+    const long long mb = atoll(e);
+    if (mb > 0) budget = (size_t)mb << 20;
+  }
+  size_t cb = budget / pl.per_frame;
+  if (cb < 1) cb = 1;
+  if (cb > (size_t)B) cb = (size_t)B;
+  return (int)cb;
+}
+
+}  // namespace bfs
+
+size_t bwd_fside_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh) {
+  const bfs::Plan pl = bfs::make_plan(sh->n_views, sh->n_scales, g->n_layers, (size_t)g->grid_l * g->grid_w, sh->feat_h, sh->feat_w);
+  return pl.off_chunk + (size_t)bfs::chunk_frames(pl, sh->batch) * pl.per_frame + 256;
+}
+
+int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_grad_out, float* const* d_grad_feats,
+                     float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace bfs;
+  int fh[VFA_MAX_SCALES] = {0, 0, 0}, fwv[VFA_MAX_SCALES] = {0, 0, 0};
+  for (int s = 0; s < p.S; ++s) {
+    fh[s] = p.sc[s].fh;
+    fwv[s] = p.sc[s].fw;
+  }
+  const Plan pl = make_plan(p.V, p.S, p.nl, (size_t)p.LW, fh, fwv);
+  int cb = chunk_frames(pl, p.B);
+  if (ws_bytes < pl.off_chunk + pl.per_frame) {
+    set_error("backward workspace %zu < required %zu", ws_bytes, pl.off_chunk + pl.per_frame);
+    return VFA_ERR_WORKSPACE;
+  }
+  if (pl.off_chunk + (size_t)cb * pl.per_frame > ws_bytes) cb = (int)((ws_bytes - pl.off_chunk) / pl.per_frame);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  uint8_t* wprep = w8 + pl.off_wprep;
+  float* dwr = reinterpret_cast<float*>(w8 + pl.off_dwr);
+  TapRec* recs = reinterpret_cast<TapRec*>(w8 + pl.off_recs);
+  int* counts = reinterpret_cast<int*>(w8 + pl.off_counts);
+  int* offsets = reinterpret_cast<int*>(w8 + pl.off_offsets);
+  int* bsums = reinterpret_cast<int*>(w8 + pl.off_bsums);
+  CsrEntry* entries = reinterpret_cast<CsrEntry*>(w8 + pl.off_entries);
+  float* gt = reinterpret_cast<float*>(w8 + pl.off_chunk);
+  float* gm = gt + (size_t)cb * p.LW * CH;
+  float* gs = gm + (size_t)cb * p.V * p.S * p.LW * CH;
+
+  const size_t per_scale_w = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
+  const size_t per_scale = (size_t)CH * CH * p.nl;
+  bool any_w = false, any_f = false;
+  for (int s = 0; s < p.S; ++s) {
+    VFA_REQUIRE((d_grad_weight[s] == nullptr) == (d_grad_bias[s] == nullptr), VFA_ERR_INVALID_ARGUMENT,
+                "scale %d: pass both or neither of d_grad_weight / d_grad_bias", s);
+    any_w |= d_grad_weight[s] != nullptr;
+    any_f |= d_grad_feats[s] != nullptr;
+    if (d_grad_bias[s] != nullptr) VFA_CUDA(cudaMemsetAsync(d_grad_bias[s], 0, CH * sizeof(float), st));
+  }
+  if (any_f)
+    for (int s = 0; s < p.S; ++s) {
+      prep_weight_umma_t_kernel<<<148 * 4, 256, 0, st>>>(d_weight[s], wprep + s * per_scale_w, p.nl);
+      VFA_LAUNCH_CHECK("prep_weight_umma_t_kernel");
+    }
+  if (any_w) VFA_CUDA(cudaMemsetAsync(dwr, 0, p.S * per_scale * sizeof(float), st));
+
+  // ---- the box -> texel relation, inverted once per call ----
+  if (int rc = launch_taps_table(p, recs, st)) return rc;
+  RowMap rm;
+  int base = 0;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+    rm.base[s] = base;
+    rm.hw[s] = s < p.S ? fh[s] * fwv[s] : 1;
+    rm.fw[s] = s < p.S ? fwv[s] : 1;
+    if (s < p.S) base += p.V * p.nl * rm.hw[s];
+  }
+  rm.total = base;
+  const int nblk = (rm.total + 1023) / 1024;
+  VFA_CUDA(cudaMemsetAsync(counts, 0, ((size_t)rm.total + 1) * sizeof(int), st));
+  csr_walk_kernel<false><<<148 * 8, 256, 0, st>>>(p, recs, rm, counts, nullptr, nullptr, 0);
+  VFA_LAUNCH_CHECK("csr_walk_kernel<count>");
+  scan_block_kernel<<<nblk, 1024, 0, st>>>(counts, offsets, bsums, rm.total);
+  VFA_LAUNCH_CHECK("scan_block_kernel");
+  scan_sums_kernel<<<1, 1024, 0, st>>>(bsums, nblk);
+  VFA_LAUNCH_CHECK("scan_sums_kernel");
+  scan_add_kernel<<<nblk, 1024, 0, st>>>(offsets, bsums, counts, rm.total);
+  VFA_LAUNCH_CHECK("scan_add_kernel");
+  VFA_CUDA(cudaMemsetAsync(counts, 0, ((size_t)rm.total + 1) * sizeof(int), st));      // reused as the fill cursor
+  csr_walk_kernel<true><<<148 * 8, 256, 0, st>>>(p, recs, rm, counts, offsets, entries, pl.capacity);
+  VFA_LAUNCH_CHECK("csr_walk_kernel<fill>");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    VFA_CUDA(cudaFuncSetAttribute(dy_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxL1));
+    attr_set = true;
+  }
+
+  for (int b0 = 0; b0 < p.B; b0 += cb) {
+    const int nb = p.B - b0 < cb ? p.B - b0 : cb;
+    // dOut[b0 .. b0+nb) : [C, LW] -> [LW, C]
+    if (int rc = launch_transpose(d_grad_out + (size_t)b0 * CH * p.LW, gt, nb, CH, p.LW, st)) return rc;
+    GradParams gq;
+    gq.p = p;
+    gq.gt = gt;
+    gq.gm = gm;
+    gq.b0 = b0;
+    for (int s = 0; s < VFA_MAX_SCALES; ++s) gq.gbias[s] = s < p.S ? d_grad_bias[s] : nullptr;
+    {
+      const dim3 grid((p.LW + MG_WARPS * MG_CELLS - 1) / (MG_WARPS * MG_CELLS), nb * p.V * p.S);
+      mask_grad_kernel<<<grid, MG_WARPS * 32, 0, st>>>(gq);
+      VFA_LAUNCH_CHECK("mask_grad_kernel");
+    }
+    GatherParams q;
+    q.p = p;
+    q.rm = rm;
+    q.offsets = offsets;
+    q.entries = entries;
+    q.gm = gm;
+    q.capacity = pl.capacity;
+    q.tile_begin[0] = 0;
+    size_t gs_off = 0;
+    const float* a_rows[VFA_MAX_SCALES];
+    float* outs[VFA_MAX_SCALES];
+    const uint8_t* wts[VFA_MAX_SCALES];
+    int rows[VFA_MAX_SCALES];
+    for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+      const int ss = s < p.S ? s : 0;
+      q.gs[s] = gs + (s < p.S ? gs_off : 0);
+      q.tiles_x[s] = (fwv[ss] + GT - 1) / GT;
+      q.tiles[s] = q.tiles_x[s] * ((fh[ss] + GT - 1) / GT);
+      if (s < p.S) {
+        q.tile_begin[s + 1] = q.tile_begin[s] + q.tiles[s] * p.V * p.nl;
+        gs_off += (size_t)cb * p.V * rm.hw[s] * p.nl * CH;
+      }
+      a_rows[s] = q.gs[s];
+      outs[s] = d_grad_feats[ss] != nullptr ? d_grad_feats[ss] + (size_t)b0 * p.V * rm.hw[ss] * CH : nullptr;
+      wts[s] = wprep + ss * per_scale_w;
+      rows[s] = nb * p.V * rm.hw[ss];
+    }
+    {
+      const dim3 grid(q.tile_begin[p.S], nb);
+      dy_gather_kernel<<<grid, GT * GT * 32, 0, st>>>(q);
+      VFA_LAUNCH_CHECK("dy_gather_kernel");
+      overflow_scatter_kernel<<<148 * 8, 256, 0, st>>>(q, recs, nb);
+      VFA_LAUNCH_CHECK("overflow_scatter_kernel");
+    }
+    if (any_f) {
+      // scales whose dFeature is not wanted get zero rows
+      for (int s = 0; s < p.S; ++s)
+        if (outs[s] == nullptr) rows[s] = 0;
+      if (int rc = launch_ygemm_accum(a_rows, outs, wts, rows, p.nl, p.S, st)) return rc;
+    }
+    if (any_w) {
+      for (int s = 0; s < p.S; ++s) {
+        if (d_grad_weight[s] == nullptr) continue;
+        // row-major dWr[nl*C x C] += Gs^T[nl*C x T] * F[T x C]
+        const int T = nb * p.V * rm.hw[s];
+        if (int rc = fs_sgemm_nt_acc(st, CH, p.nl * CH, T, p.feats[s] + (size_t)b0 * p.V * rm.hw[s] * CH, CH, q.gs[s],
+                                     p.nl * CH, dwr + s * per_scale, CH))
+          return rc;
+      }
+    }
+  }
+  for (int s = 0; s < p.S; ++s) {
+    if (d_grad_weight[s] == nullptr) continue;
+    if (int rc = launch_unprep_dweight(dwr + s * per_scale, d_grad_weight[s], CH, p.nl, st)) return rc;
+  }
+  return VFA_OK;
+}
+
+}  // namespace vfa

@@ -66,9 +66,14 @@ constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + TAIL_BYTES +
 static_assert(sizeof(SmemTail) <= TAIL_BYTES, "");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 
+// MODE 0 (forward): A = feature rows [rows, 256], re-read for every layer; output = one [rows-of-plane, 256] slab per
+//                   layer, Y[plane][layer][texel][256].
+// MODE 1 (backward, dFeature): A = Gs rows [rows, nl*256], the K loop runs through the layers; the layer partials are
+//                   summed into ONE output row block out[rows, 256] (first layer stores, later layers add with fp32
+//                   read-modify-write: the tensor-core accumulator is only trusted for 32 k-steps).
 struct YGemmArgs {
-  const uint8_t* feats[VFA_MAX_SCALES];   // [rows, 256] channels-last rows of this chunk (fp32 or bf16)
-  float* y[VFA_MAX_SCALES];               // [plane][layer][texel][256]
+  const uint8_t* feats[VFA_MAX_SCALES];   // A rows of this chunk (fp32; bf16 in MODE 0 with VFA_FLAG_BF16_FEATURES)
+  float* y[VFA_MAX_SCALES];               // MODE 0: [plane][layer][texel][256]; MODE 1: [rows][256]
   const uint8_t* wprep[VFA_MAX_SCALES];   // prepared weights (prep_weight_umma_kernel layout)
   int rows[VFA_MAX_SCALES];               // planes * fh * fw
   int hw[VFA_MAX_SCALES];                 // fh * fw
@@ -133,7 +138,7 @@ __device__ __forceinline__ TileInfo tile_info(const YGemmArgs& a, int ctile, uin
 
 // Persistent: cluster c works on tiles c, c + n_clusters, ... ; every role keeps its stage / layer counters running
 // across tiles, so the last layer's epilogue and the next tile's first loads overlap the tensor-core work.
-template <bool BF16>
+template <bool BF16, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
       for (int i = 0; i < ITEMS; ++i) {
         const int r = 32 * i + 4 * pw + (lane >> 3); // 4 rows x 128 B per warp instruction
         ok[i] = t.row0 + r < t.rows;
-        src[i] = t.feats + ((size_t)(t.row0 + r) * CH + j * 4) * ES;
+        src[i] = t.feats + ((size_t)(t.row0 + r) * (MODE == 0 ? CH : a.nl * CH) + j * 4) * ES;
       }
     };
 #pragma unroll
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
       for (int k = 0; k < total; ++k, ++it) {
         const int st = it % STAGES;
         // loads of the next stage (possibly the first stage of the next tile) fly while this one is stored
-        int cc = (k + 1) % CHUNKS;
+        int cc = MODE == 0 ? (k + 1) % CHUNKS : k + 1;       // K chunk of the next stage inside an A row
         bool more = true;
         if (k + 1 == total) {
           more = ctile + n_clusters < n_tiles;
@@ -293,17 +298,20 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
     int ln = 0;
     for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
       const TileInfo t = tile_info(a, ctile, cta_rank);
-      uint32_t yrow[8];                               // 1 KB row of Y (layer 0) of patch row 4*rr + sub; ~0u = outside
+      uint32_t yrow[8];                               // 1 KB output row (layer 0) of patch row 4*rr + sub; ~0u = outside
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) {
         const int r = t.row0 + quarter * 32 + 4 * rr + sub;
-        yrow[rr] = r < t.rows ? (uint32_t)((r / t.hw) * a.nl * t.hw + r % t.hw) : 0xffffffffu;
+        if (MODE == 0)
+          yrow[rr] = r < t.rows ? (uint32_t)((r / t.hw) * a.nl * t.hw + r % t.hw) : 0xffffffffu;
+        else
+          yrow[rr] = r < t.rows ? (uint32_t)r : 0xffffffffu;
       }
       for (int n = 0; n < a.nl; ++n, ++ln) {
         const int slot = ln & 1;
         mbar_wait_sleep(&tail->acc_full[slot], (ln >> 1) & 1);
         tc_fence_after();
-        float* dst = t.y + (size_t)n * t.hw * CH + col_begin + chunk * 4;
+        float* dst = t.y + (MODE == 0 ? (size_t)n * t.hw * CH : (size_t)0) + col_begin + chunk * 4;
 #pragma unroll 1
         for (int c0 = 0; c0 < CH / 2; c0 += 32) {
           float v[32];
@@ -318,8 +326,15 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr) {
             const int prow = 4 * rr + sub;
-            const float4 q = *reinterpret_cast<const float4*>(patch + prow * 128 + ((chunk ^ (prow & 7)) << 4));
-            if (yrow[rr] != 0xffffffffu) *reinterpret_cast<float4*>(dst + (size_t)yrow[rr] * CH + c0) = q;
+            float4 q = *reinterpret_cast<const float4*>(patch + prow * 128 + ((chunk ^ (prow & 7)) << 4));
+            if (yrow[rr] != 0xffffffffu) {
+              float4* o4 = reinterpret_cast<float4*>(dst + (size_t)yrow[rr] * CH + c0);
+              if (MODE == 1 && n > 0) {               // layer partials summed in fp32 (this thread owns the element)
+                const float4 prev = *o4;
+                q.x += prev.x; q.y += prev.y; q.z += prev.z; q.w += prev.w;
+              }
+              *o4 = q;
+            }
           }
         }
         tc_fence_before();
@@ -621,6 +636,69 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
 
 using namespace fside;
 
+// One persistent launch over all cluster tiles of `g` (tile_begin must be filled for g.S scales).
+static int launch_ygemm(YGemmArgs& g, int mode, bool bf16, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int resident_clusters = 0;      // CTA pairs the device can hold at once (1 CTA per SM)
+  if (resident_clusters == 0) {
+    cfg.gridDim = dim3(2 * 148);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, ygemm_kernel<false, 0>, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = 64;
+    }
+    resident_clusters = n;
+  }
+  g.n_tiles = g.tile_begin[g.S];
+  if (g.n_tiles <= 0) return VFA_OK;
+  cfg.gridDim = dim3(2 * (g.n_tiles < resident_clusters ? g.n_tiles : resident_clusters));
+  if (mode == 1)
+    VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<false, 1>, g));
+  else if (bf16)
+    VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<true, 0>, g));
+  else
+    VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<false, 0>, g));
+  VFA_LAUNCH_CHECK("ygemm_kernel");
+  return VFA_OK;
+}
+
+// out_s[rows_s, 256] = sum over the nl*256 columns of a_s[rows_s, nl*256] against the TRANSPOSED prepared weights
+// (prep_weight_umma_T_kernel): the dFeature product of the backward.  3xTF32, layer partials added in fp32.
+int launch_ygemm_accum(const float* const* a_rows, float* const* out, const uint8_t* const* wprep_t, const int* rows,
+                       int nl, int S, cudaStream_t st) {
+  YGemmArgs g;
+  g.nl = nl;
+  g.S = S;
+  g.tile_begin[0] = 0;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+    const int ss = s < S ? s : 0;
+    g.feats[s] = reinterpret_cast<const uint8_t*>(a_rows[ss]);
+    g.y[s] = out[ss];
+    g.wprep[s] = wprep_t[ss];
+    g.rows[s] = rows[ss];
+    g.hw[s] = 1;
+    if (s < S) g.tile_begin[s + 1] = g.tile_begin[s] + (rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+  }
+  return launch_ygemm(g, 1, false, st);
+}
+
 // bytes of Y for one frame
 size_t fside_y_bytes_per_frame(const AggParams& p) {
   size_t texels = 0;
@@ -646,8 +724,6 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
                      bool bf16, int variant, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxL1));
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -692,35 +768,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       }
     }
     if (!(variant & 128)) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.blockDim = dim3(THREADS);
-      cfg.dynamicSmemBytes = SMEM_BYTES;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      static int resident_clusters = 0;      // CTA pairs the device can hold at once (1 CTA per SM)
-      if (resident_clusters == 0) {
-        cfg.gridDim = dim3(2 * 148);
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, ygemm_kernel<false>, &cfg) != cudaSuccess || n < 1) {
-          (void)cudaGetLastError();
-          n = 64;
-        }
-        resident_clusters = n;
-      }
-      const int n_tiles = g.tile_begin[p.S];
-      g.n_tiles = n_tiles;
-      cfg.gridDim = dim3(2 * (n_tiles < resident_clusters ? n_tiles : resident_clusters));
-      if (bf16)
-        VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<true>, g));
-      else
-        VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_kernel<false>, g));
-      VFA_LAUNCH_CHECK("ygemm_kernel");
+      if (int rc = launch_ygemm(g, 0, bf16, st)) return rc;
     }
     if (!(variant & 64)) {
       static int quad = -1;            // VFA_POOL_QUAD=0 selects the one-cell-per-warp kernel (debug / comparison)

@@ -162,6 +162,12 @@ __global__ void __launch_bounds__(256) taps_table_kernel(AggParams p, TapRec* __
   }
 }
 
+int launch_taps_table(const AggParams& p, TapRec* recs, cudaStream_t st) {
+  taps_table_kernel<<<148 * 8, 256, 0, st>>>(p, recs);
+  VFA_LAUNCH_CHECK("taps_table_kernel");
+  return VFA_OK;
+}
+
 struct UmmaArgs {
   AggParams p;
   const uint8_t* wprep[VFA_MAX_SCALES];
