@@ -6,7 +6,7 @@
 //   dBias_s[o]               = sum_{b, v, cell} gm
 //   Gs[b,v,s][texel, n, o]   = sum_{cells whose layer-n box holds texel} wy * wx * gm[cell, o]           (dy_gather_kernel)
 //   dFeat[b,v,s][texel, c]   = sum_{n,o} Gs[texel, n, o] * W_s[o, c*nl + n]          tcgen05 3xTF32 (ygemm_kernel, MODE 1)
-//   dWeight_s[o, c*nl + n]  += sum_{b,v,texel} Gs[texel, n, o] * f[texel, c]          library SGEMM (cuBLAS, fp32)
+//   dWeight_s[o, c*nl + n]  += sum_{b,v,texel} Gs[texel, n, o] * f[texel, c]          tcgen05 3xTF32, MN-major (dweight_kernel)
 //
 // The reference's autograd scatters through 4 grid_sampler backwards and two reverse cumsums (vfa_op.py:110-124); the
 // first version of this path scattered Gs with atomics (vfa_bwd.cu, still used for C < 256) and spent its time in the L2
@@ -355,6 +355,324 @@ __global__ void __launch_bounds__(256) overflow_scatter_kernel(const GatherParam
   }
 }
 
+}  // namespace bfs
+
+// ---- dWeight on the tensor cores ---------------------------------------------------------------------------------------
+// dWr_s[(n,o), c] += sum_t Gs_s[t, (n,o)] * F_s[t, c]:  M = nl*256, N = 256, K = texel rows of the chunk (10^5 .. 4*10^5).
+// Both operands are stored with the contraction index OUTERMOST ([t][m], [t][c]), i.e. they are MN-major for the MMA:
+// a 128-byte run of a texel row (32 consecutive m or c) becomes one row of a SWIZZLE_128B atom, so the producers load
+// coalesced 512-byte runs, split into tf32 hi / lo and store 128-bit -- no transposition anywhere (layout type
+// SWIZZLE_128B_BASE32B, the one MN-major layout the tensor core accepts for 32-bit data).  CTA pairs
+// (cta_group::2): a cluster owns a 256-row M tile and a range of 256-texel K blocks; 3 stages of 32 texels; after every
+// K block (32 k-steps: the truncating accumulator is not trusted for more) the 8 epilogue warps fold the accumulator into an
+// fp32 running sum in TMEM columns [256, 512); when the cluster's range leaves the (scale, M tile) segment the running sum is
+// added to dWr with vector atomics (split-K).  Work is dealt in equal contiguous ranges of K blocks over the resident pairs.
+namespace dwg {
+
+using namespace umma;
+using bfs::CH;
+
+constexpr int TILE_M = 128, KST = 32, STAGES = 3;
+constexpr int OP_BYTES = TILE_M * KST * 4;                    // 16 KB: one hi or lo operand tile (A or B)
+constexpr int STAGE_BYTES = 4 * OP_BYTES;                     // A hi, A lo, B hi, B lo
+constexpr int NUM_PRODUCER_WARPS = 16, FIRST_PRODUCER_WARP = 4;
+constexpr int FIRST_EPILOGUE_WARP = FIRST_PRODUCER_WARP + NUM_PRODUCER_WARPS;   // 20: (warp & 3) == TMEM lane quarter
+constexpr int NUM_EPILOGUE_WARPS = 8;
+constexpr int THREADS = (FIRST_EPILOGUE_WARP + NUM_EPILOGUE_WARPS) * 32;       // 896
+constexpr int STAGES_PER_BLOCK = 8;                           // 256 texels per K block
+constexpr uint32_t LBO = 512, SBO = 2048;                     // 512-byte atoms: 4 along M/N, then 8 along K (4 texels each)
+constexpr uint32_t IDESC = make_idesc_tf32(CH, 2 * TILE_M) | (1u << 15) | (1u << 16);     // A and B MN-major
+
+struct __align__(16) SmemTail {
+  unsigned long long full[STAGES];
+  unsigned long long empty[STAGES];
+  unsigned long long peer_full[STAGES];
+  unsigned long long acc_full;
+  unsigned long long acc_empty;
+  uint32_t tmem_base;
+};
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(SmemTail);
+
+struct Args {
+  const float* gs[VFA_MAX_SCALES];     // [T_s][nl*256]
+  const float* f[VFA_MAX_SCALES];      // [T_s][256]
+  float* dwr[VFA_MAX_SCALES];          // [nl*256][256], zeroed / accumulated by the caller
+  int T[VFA_MAX_SCALES];               // texel rows of the chunk
+  int kblocks[VFA_MAX_SCALES];         // ceil(T / 256)
+  int unit_begin[VFA_MAX_SCALES + 1];  // units (M tile, K block) of scale s: nl * kblocks[s], prefix
+  int nl, S, n_units;
+};
+
+struct Unit {
+  int s, mt, kb, kblocks;
+};
+__device__ __forceinline__ Unit decode_unit(const Args& a, int u) {
+  Unit r;
+  r.s = (a.S > 2 && u >= a.unit_begin[2]) ? 2 : ((a.S > 1 && u >= a.unit_begin[1]) ? 1 : 0);
+  const int u0 = r.s == 0 ? 0 : (r.s == 1 ? a.unit_begin[1] : a.unit_begin[2]);
+  r.kblocks = r.s == 0 ? a.kblocks[0] : (r.s == 1 ? a.kblocks[1] : a.kblocks[2]);
+  r.mt = (u - u0) / r.kblocks;
+  r.kb = (u - u0) % r.kblocks;
+  return r;
+}
+
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint32_t off, const float4& v) {
+  uint4 hi, lo;
+  hi.x = to_tf32(v.x);
+  hi.y = to_tf32(v.y);
+  hi.z = to_tf32(v.z);
+  hi.w = to_tf32(v.w);
+  const float2 l01 = __fadd2_rn(make_float2(v.x, v.y), make_float2(-__uint_as_float(hi.x), -__uint_as_float(hi.y)));
+  const float2 l23 = __fadd2_rn(make_float2(v.z, v.w), make_float2(-__uint_as_float(hi.z), -__uint_as_float(hi.w)));
+  lo.x = __float_as_uint(l01.x);
+  lo.y = __float_as_uint(l01.y);
+  lo.z = __float_as_uint(l23.x);
+  lo.w = __float_as_uint(l23.y);
+  *reinterpret_cast<uint4*>(hi_tile + off) = hi;
+  *reinterpret_cast<uint4*>(hi_tile + OP_BYTES + off) = lo;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // this cluster's contiguous range of units
+  const int u_begin = (int)((long long)a.n_units * cluster / n_clusters);
+  const int u_end = (int)((long long)a.n_units * (cluster + 1) / n_clusters);
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&tail->full[i], NUM_PRODUCER_WARPS);
+      mbar_init(&tail->empty[i], 1);
+      mbar_init(&tail->peer_full[i], 1);
+    }
+    mbar_init(&tail->acc_full, 1);
+    mbar_init(&tail->acc_empty, 2 * NUM_EPILOGUE_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp == 1) {
+    if (lane == 0 && cta_rank != 0) {
+      int it = 0;
+      for (int u = u_begin; u < u_end; ++u)
+        for (int k = 0; k < STAGES_PER_BLOCK; ++k, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->full[st], (it / STAGES) & 1);
+          mbar_arrive_remote(&tail->peer_full[st], 0);
+        }
+    } else if (lane == 0) {
+      // ================= MMA issuer (pair leader) =================
+      int it = 0, blk = 0;
+      for (int u = u_begin; u < u_end; ++u, ++blk) {
+        mbar_wait_cluster(&tail->acc_empty, (blk & 1) ^ 1);
+        tc_fence_after();
+        for (int k = 0; k < STAGES_PER_BLOCK; ++k, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->full[st], (it / STAGES) & 1);
+          mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+#pragma unroll
+          for (int kg = 0; kg < KST / 8; ++kg) {           // one MMA K step = 8 texels = two atoms along K
+            const uint64_t a_hi = make_desc_mn32(sa + kg * (2 * SBO), LBO, SBO);
+            const uint64_t a_lo = make_desc_mn32(sa + OP_BYTES + kg * (2 * SBO), LBO, SBO);
+            const uint64_t b_hi = make_desc_mn32(sa + 2 * OP_BYTES + kg * (2 * SBO), LBO, SBO);
+            const uint64_t b_lo = make_desc_mn32(sa + 3 * OP_BYTES + kg * (2 * SBO), LBO, SBO);
+            tc_mma_tf32_t<true>(tmem, a_lo, b_hi, IDESC, (k | kg) ? 1u : 0u);
+            tc_mma_tf32_t<true>(tmem, a_hi, b_lo, IDESC, 1u);
+            tc_mma_tf32_t<true>(tmem, a_hi, b_hi, IDESC, 1u);
+          }
+          tc_commit_t<true>(&tail->empty[st]);
+        }
+        tc_commit_t<true>(&tail->acc_full);
+      }
+    }
+  } else if (warp >= FIRST_PRODUCER_WARP && warp < FIRST_EPILOGUE_WARP) {
+    // ================= producers: 512-byte runs of Gs rows (A) and F rows (B) -> MN-major hi / lo tiles =================
+    const int pw = warp - FIRST_PRODUCER_WARP;
+    const int j = lane & 7, mc = lane >> 3;              // 16-byte chunk, 32-element chunk of the 128 M (N) rows
+    uint32_t off[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = pw * 2 + i;                          // texel of the stage
+      off[i] = (uint32_t)((mc + 4 * (k >> 2)) * 512) + swz_mn32((uint32_t)(k & 3), (uint32_t)j);
+    }
+    float4 ca[2], cbv[2], na[2], nb[2];
+    auto load_stage = [&](int u, int k, float4(&va)[2], float4(&vb)[2]) {
+      const Unit w = decode_unit(a, u);
+      const int T = w.s == 0 ? a.T[0] : (w.s == 1 ? a.T[1] : a.T[2]);
+      const float* gs = w.s == 0 ? a.gs[0] : (w.s == 1 ? a.gs[1] : a.gs[2]);
+      const float* f = w.s == 0 ? a.f[0] : (w.s == 1 ? a.f[1] : a.f[2]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int t = w.kb * (STAGES_PER_BLOCK * KST) + k * KST + pw * 2 + i;
+        va[i] = vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < T) {
+          va[i] = __ldg(reinterpret_cast<const float4*>(gs + (size_t)t * (a.nl * CH) + w.mt * (2 * TILE_M) +
+                                                        (int)cta_rank * TILE_M + mc * 32 + j * 4));
+          vb[i] = __ldg(reinterpret_cast<const float4*>(f + (size_t)t * CH + (int)cta_rank * TILE_M + mc * 32 + j * 4));
+        }
+      }
+    };
+    if (u_begin < u_end) load_stage(u_begin, 0, ca, cbv);
+    int it = 0;
+    for (int u = u_begin; u < u_end; ++u) {
+      for (int k = 0; k < STAGES_PER_BLOCK; ++k, ++it) {
+        const int st = it % STAGES;
+        int nu = u, nk = k + 1;
+        if (nk == STAGES_PER_BLOCK) {
+          nk = 0;
+          ++nu;
+        }
+        if (nu < u_end) load_stage(nu, nk, na, nb);
+        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+        uint8_t* base = smem + (size_t)st * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          store_split(base, off[i], ca[i]);
+          store_split(base + 2 * OP_BYTES, off[i], cbv[i]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->full[st]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          ca[i] = na[i];
+          cbv[i] = nb[i];
+        }
+      }
+    }
+  } else if (warp >= FIRST_EPILOGUE_WARP) {
+    // ================= epilogue: per-K-block drain into the fp32 running sum, split-K flush =================
+    const int e = warp - FIRST_EPILOGUE_WARP;
+    const int quarter = warp & 3;
+    const int col_begin = (e >> 2) * (CH / 2);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    int blk = 0;
+    bool first = true;                                    // first K block of the current (scale, M tile) segment
+    for (int u = u_begin; u < u_end; ++u, ++blk) {
+      const Unit w = decode_unit(a, u);
+      mbar_wait_sleep(&tail->acc_full, blk & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
+        float acc[32], pre[32];
+        tc_ld32(lane_addr + c0, acc);
+        if (!first) tc_ld32(lane_addr + CH + c0, pre);
+        tc_wait_ld();
+        if (!first) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] += pre[i];
+        }
+        tc_st32(lane_addr + CH + c0, acc);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank != 0) mbar_arrive_remote(&tail->acc_empty, 0);
+        else mbar_arrive(&tail->acc_empty);
+      }
+      first = false;
+      // leave the segment?  (next unit belongs to another (scale, M tile), or this was the cluster's last unit)
+      bool flush = u + 1 == u_end;
+      if (!flush) {
+        const Unit nxt = decode_unit(a, u + 1);
+        flush = nxt.s != w.s || nxt.mt != w.mt;
+      }
+      if (flush) {
+        float* dwr = w.s == 0 ? a.dwr[0] : (w.s == 1 ? a.dwr[1] : a.dwr[2]);
+        float* dst = dwr + (size_t)(w.mt * (2 * TILE_M) + (int)cta_rank * TILE_M + quarter * 32 + lane) * CH;
+#pragma unroll 1
+        for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
+          float v[32];
+          tc_ld32(lane_addr + CH + c0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + c0 + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+        first = true;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+}  // namespace dwg
+
+// dwr_s[nl*256][256] += Gs_s^T F_s for the S scales of one frame chunk (one persistent launch)
+static int launch_dweight(const float* const* gs, const float* const* f, float* const* dwr, const int* T, int nl, int S,
+                          cudaStream_t st) {
+  using namespace dwg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VFA_CUDA(cudaFuncSetAttribute(dweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  Args a;
+  a.nl = nl;
+  a.S = S;
+  a.unit_begin[0] = 0;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+    const int ss = s < S ? s : 0;
+    a.gs[s] = gs[ss];
+    a.f[s] = f[ss];
+    a.dwr[s] = dwr[ss];
+    a.T[s] = T[ss];
+    a.kblocks[s] = (T[ss] + STAGES_PER_BLOCK * KST - 1) / (STAGES_PER_BLOCK * KST);
+    if (a.kblocks[s] < 1) a.kblocks[s] = 1;
+    if (s < S) a.unit_begin[s + 1] = a.unit_begin[s] + (dwr[s] != nullptr && T[s] > 0 ? nl * a.kblocks[s] : 0);
+  }
+  a.n_units = a.unit_begin[S];
+  if (a.n_units == 0) return VFA_OK;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int resident_clusters = 0;
+  if (resident_clusters == 0) {
+    cfg.gridDim = dim3(2 * 148);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, dweight_kernel, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = 64;
+    }
+    resident_clusters = n;
+  }
+  const int clusters = a.n_units < resident_clusters ? a.n_units : resident_clusters;
+  cfg.gridDim = dim3(2 * clusters);
+  VFA_CUDA(cudaLaunchKernelEx(&cfg, dweight_kernel, a));
+  VFA_LAUNCH_CHECK("dweight_kernel");
+  return VFA_OK;
+}
+
+namespace bfs {
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Plan {
@@ -539,7 +857,20 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
         if (outs[s] == nullptr) rows[s] = 0;
       if (int rc = launch_ygemm_accum(a_rows, outs, wts, rows, p.nl, p.S, st)) return rc;
     }
-    if (any_w) {
+    if (any_w && getenv("VFA_BWD_CUBLAS_DW") == nullptr) {
+      const float* gsp[VFA_MAX_SCALES];
+      const float* fp[VFA_MAX_SCALES];
+      float* dwp[VFA_MAX_SCALES];
+      int Ts[VFA_MAX_SCALES];
+      for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+        const int ss = s < p.S ? s : 0;
+        gsp[s] = q.gs[ss];
+        fp[s] = p.feats[ss] + (size_t)b0 * p.V * rm.hw[ss] * CH;
+        dwp[s] = d_grad_weight[ss] != nullptr ? dwr + ss * per_scale : nullptr;
+        Ts[s] = nb * p.V * rm.hw[ss];
+      }
+      if (int rc = launch_dweight(gsp, fp, dwp, Ts, p.nl, p.S, st)) return rc;
+    } else if (any_w) {
       for (int s = 0; s < p.S; ++s) {
         if (d_grad_weight[s] == nullptr) continue;
         // row-major dWr[nl*C x C] += Gs^T[nl*C x T] * F[T x C]

@@ -172,6 +172,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// MN-major descriptor for 32-bit operands.  tf32 / fp32 data can only be transposed by the tensor core from the
+// SWIZZLE_128B_BASE32B layout (cute::UMMA::Layout_MN_SW128_32B_Atom, layout type 1): 512-byte atoms of 4 K-rows x 128
+// bytes (32 consecutive M / N elements of one K index per row); inside a row the four 32-byte chunks are XOR-swizzled
+// with the row index (Swizzle<2,5,2> on the byte address).  lbo = byte distance between atoms along M / N, sbo =
+// between atoms along K (make_umma_desc<Major::MN>: ((8,n),(4,k)):((1,LBO),(8,SBO)) in units of 16 bytes).
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset of the 16-byte chunk j (0..7) of K-row kr (0..3) inside such an atom
+__device__ __host__ __forceinline__ uint32_t swz_mn32(uint32_t kr, uint32_t j) {
+  return kr * 128u + ((((j >> 1) ^ kr) & 3u) << 5) + ((j & 1u) << 4);
+}
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N, M
 constexpr uint32_t make_idesc_tf32(int n, int m) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
