@@ -163,3 +163,30 @@ def test_grad_flags_are_respected():
     vfa_b200.aggregate(fc, table, ws, bs).sum().backward()
     assert fc[0].grad is not None and fc[1].grad is None and fc[2].grad is None
     assert ws[1].grad is not None and ws[0].grad is None and ws[2].grad is None
+
+
+def test_full_size_backward_variants_agree(monkeypatch):
+    """BASELINE-size problem (MultiviewC, 7 views, 3 scales, C = 256, 2 frames): the gather-form backward (CSR + tcgen05
+    dFeature / dWeight) against the scatter + SGEMM backward, gradients of a random cotangent."""
+    g = geometry.MULTIVIEWC
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g)
+    feats = synthetic.features(g, batch=2, seed=21)
+    params = synthetic.collapse_params(g, seed=21)
+    zs = list(range(0, g.grid_height, g.cube_size[2]))
+    geom = vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid.shape[:2], g.name, g.image_size)
+    table = vfa_b200.build_table(geom, calibs.cuda(), grid.cuda())
+    gout = torch.randn(2, 256, *grid.shape[:2], generator=torch.Generator().manual_seed(3)).cuda()
+    grads = {}
+    for tag in ('gather', 'scatter'):
+        if tag == 'scatter':
+            monkeypatch.setenv('VFA_BWD_SCATTER', '1')
+        fc = [t.cuda().requires_grad_(True) for t in feats]
+        ws = [w.cuda().requires_grad_(True) for w, _ in params]
+        bs = [b.cuda().requires_grad_(True) for _, b in params]
+        vfa_b200.aggregate(fc, table, ws, bs).backward(gout)
+        grads[tag] = [t.grad for t in fc + ws + bs]
+    monkeypatch.delenv('VFA_BWD_SCATTER', raising=False)
+    names = [f'dFeature{s}' for s in range(3)] + [f'dWeight{s}' for s in range(3)] + [f'dBias{s}' for s in range(3)]
+    for name, a, b in zip(names, grads['gather'], grads['scatter']):
+        _close(a.cpu().numpy(), b.cpu().numpy().astype(np.float64), f'full size {name}')

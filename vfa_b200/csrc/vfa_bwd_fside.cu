@@ -266,6 +266,20 @@ struct GatherParams {
 };
 
 constexpr int GT = 4;                            // texel tile side: one warp per texel
+#ifndef VFA_GATHER_BATCH
+#define VFA_GATHER_BATCH 4
+#endif
+constexpr int GB = VFA_GATHER_BATCH;             // CSR entries in flight per warp
+
+__device__ __forceinline__ void fma8w(float (&acc)[8], float w, const float4& a, const float4& b) {
+  const float2 w2 = make_float2(w, w);
+  const float2 r0 = __ffma2_rn(w2, make_float2(a.x, a.y), make_float2(acc[0], acc[1]));
+  const float2 r1 = __ffma2_rn(w2, make_float2(a.z, a.w), make_float2(acc[2], acc[3]));
+  const float2 r2 = __ffma2_rn(w2, make_float2(b.x, b.y), make_float2(acc[4], acc[5]));
+  const float2 r3 = __ffma2_rn(w2, make_float2(b.z, b.w), make_float2(acc[6], acc[7]));
+  acc[0] = r0.x; acc[1] = r0.y; acc[2] = r1.x; acc[3] = r1.y;
+  acc[4] = r2.x; acc[5] = r2.y; acc[6] = r3.x; acc[7] = r3.y;
+}
 
 __global__ void __launch_bounds__(GT * GT * 32, 2) dy_gather_kernel(const GatherParams q) {
   const AggParams& p = q.p;
@@ -293,25 +307,24 @@ __global__ void __launch_bounds__(GT * GT * 32, 2) dy_gather_kernel(const Gather
     const float* gm = q.gm + (((size_t)bl * p.V + v) * p.S + s) * p.LW * CH + lane * 8;
     const int2* ent = reinterpret_cast<const int2*>(q.entries);
     int e = e0;
-    for (; e + 1 < e1; e += 2) {                       // two entries (4 x LDG.128) in flight
-      const int2 a = __ldg(ent + e), c = __ldg(ent + e + 1);
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH + 4));
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)c.x * CH));
-      const float4 c1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)c.x * CH + 4));
-      const float wa = __int_as_float(a.y), wc = __int_as_float(c.y);
-      acc[0] += wa * a0.x; acc[1] += wa * a0.y; acc[2] += wa * a0.z; acc[3] += wa * a0.w;
-      acc[4] += wa * a1.x; acc[5] += wa * a1.y; acc[6] += wa * a1.z; acc[7] += wa * a1.w;
-      acc[0] += wc * c0.x; acc[1] += wc * c0.y; acc[2] += wc * c0.z; acc[3] += wc * c0.w;
-      acc[4] += wc * c1.x; acc[5] += wc * c1.y; acc[6] += wc * c1.z; acc[7] += wc * c1.w;
+    for (; e + GB <= e1; e += GB) {                    // GB entries (2 x LDG.128 each) in flight
+      int2 en[GB];
+      float4 ga[GB], gb[GB];
+#pragma unroll
+      for (int k = 0; k < GB; ++k) en[k] = __ldg(ent + e + k);
+#pragma unroll
+      for (int k = 0; k < GB; ++k) {
+        ga[k] = __ldg(reinterpret_cast<const float4*>(gm + (size_t)en[k].x * CH));
+        gb[k] = __ldg(reinterpret_cast<const float4*>(gm + (size_t)en[k].x * CH + 4));
+      }
+#pragma unroll
+      for (int k = 0; k < GB; ++k) fma8w(acc, __int_as_float(en[k].y), ga[k], gb[k]);
     }
-    if (e < e1) {
+    for (; e < e1; ++e) {
       const int2 a = __ldg(ent + e);
       const float4 a0 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH));
       const float4 a1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH + 4));
-      const float wa = __int_as_float(a.y);
-      acc[0] += wa * a0.x; acc[1] += wa * a0.y; acc[2] += wa * a0.z; acc[3] += wa * a0.w;
-      acc[4] += wa * a1.x; acc[5] += wa * a1.y; acc[6] += wa * a1.z; acc[7] += wa * a1.w;
+      fma8w(acc, __int_as_float(a.y), a0, a1);
     }
   }
   float* dst = gs + ((((size_t)bl * p.V + v) * hw + texel) * p.nl + n) * CH + lane * 8;
@@ -366,7 +379,7 @@ __global__ void __launch_bounds__(256) overflow_scatter_kernel(const GatherParam
 // (cta_group::2): a cluster owns a 256-row M tile and a range of 256-texel K blocks; 3 stages of 32 texels; after every
 // K block (32 k-steps: the truncating accumulator is not trusted for more) the 8 epilogue warps fold the accumulator into an
 // fp32 running sum in TMEM columns [256, 512); when the cluster's range leaves the (scale, M tile) segment the running sum is
-// added to dWr with vector atomics (split-K).  Work is dealt in equal contiguous ranges of K blocks over the resident pairs.
+// added to dWr with vector atomics (split-K).  The nl M tiles of one share of the K blocks run side by side.
 namespace dwg {
 
 using namespace umma;
@@ -398,21 +411,19 @@ struct Args {
   const float* f[VFA_MAX_SCALES];      // [T_s][256]
   float* dwr[VFA_MAX_SCALES];          // [nl*256][256], zeroed / accumulated by the caller
   int T[VFA_MAX_SCALES];               // texel rows of the chunk
-  int kblocks[VFA_MAX_SCALES];         // ceil(T / 256)
-  int unit_begin[VFA_MAX_SCALES + 1];  // units (M tile, K block) of scale s: nl * kblocks[s], prefix
-  int nl, S, n_units;
+  int kb_begin[VFA_MAX_SCALES + 1];    // K blocks (256 texels) of scale s: [kb_begin[s], kb_begin[s+1]) of the concatenated list
+  int nl, S, n_kb;
 };
 
+// Work split: cluster c owns M tile (c % nl) and the c / nl -th share of the concatenated K-block list, so the nl
+// clusters of a share stream the same feature rows at the same time (they are re-read from L2, not from HBM).
 struct Unit {
-  int s, mt, kb, kblocks;
+  int s, kb;
 };
 __device__ __forceinline__ Unit decode_unit(const Args& a, int u) {
   Unit r;
-  r.s = (a.S > 2 && u >= a.unit_begin[2]) ? 2 : ((a.S > 1 && u >= a.unit_begin[1]) ? 1 : 0);
-  const int u0 = r.s == 0 ? 0 : (r.s == 1 ? a.unit_begin[1] : a.unit_begin[2]);
-  r.kblocks = r.s == 0 ? a.kblocks[0] : (r.s == 1 ? a.kblocks[1] : a.kblocks[2]);
-  r.mt = (u - u0) / r.kblocks;
-  r.kb = (u - u0) % r.kblocks;
+  r.s = (a.S > 2 && u >= a.kb_begin[2]) ? 2 : ((a.S > 1 && u >= a.kb_begin[1]) ? 1 : 0);
+  r.kb = u - (r.s == 0 ? 0 : (r.s == 1 ? a.kb_begin[1] : a.kb_begin[2]));
   return r;
 }
 
@@ -439,9 +450,10 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cta_rank = cluster_ctarank();
   const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  // this cluster's contiguous range of units
-  const int u_begin = (int)((long long)a.n_units * cluster / n_clusters);
-  const int u_end = (int)((long long)a.n_units * (cluster + 1) / n_clusters);
+  // this cluster's M tile and contiguous range of K blocks
+  const int mt = cluster % a.nl, share = cluster / a.nl, shares = n_clusters / a.nl;
+  const int u_begin = share < shares ? (int)((long long)a.n_kb * share / shares) : 0;
+  const int u_end = share < shares ? (int)((long long)a.n_kb * (share + 1) / shares) : 0;
 
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
         const int t = w.kb * (STAGES_PER_BLOCK * KST) + k * KST + pw * 2 + i;
         va[i] = vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < T) {
-          va[i] = __ldg(reinterpret_cast<const float4*>(gs + (size_t)t * (a.nl * CH) + w.mt * (2 * TILE_M) +
+          va[i] = __ldg(reinterpret_cast<const float4*>(gs + (size_t)t * (a.nl * CH) + mt * (2 * TILE_M) +
                                                         (int)cta_rank * TILE_M + mc * 32 + j * 4));
           vb[i] = __ldg(reinterpret_cast<const float4*>(f + (size_t)t * CH + (int)cta_rank * TILE_M + mc * 32 + j * 4));
         }
@@ -587,15 +599,15 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
         else mbar_arrive(&tail->acc_empty);
       }
       first = false;
-      // leave the segment?  (next unit belongs to another (scale, M tile), or this was the cluster's last unit)
+      // leave the segment?  (the next K block belongs to another scale, or this was the cluster's last one)
       bool flush = u + 1 == u_end;
       if (!flush) {
         const Unit nxt = decode_unit(a, u + 1);
-        flush = nxt.s != w.s || nxt.mt != w.mt;
+        flush = nxt.s != w.s;
       }
       if (flush) {
         float* dwr = w.s == 0 ? a.dwr[0] : (w.s == 1 ? a.dwr[1] : a.dwr[2]);
-        float* dst = dwr + (size_t)(w.mt * (2 * TILE_M) + (int)cta_rank * TILE_M + quarter * 32 + lane) * CH;
+        float* dst = dwr + (size_t)(mt * (2 * TILE_M) + (int)cta_rank * TILE_M + quarter * 32 + lane) * CH;
 #pragma unroll 1
         for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
           float v[32];
@@ -630,19 +642,18 @@ static int launch_dweight(const float* const* gs, const float* const* f, float* 
   Args a;
   a.nl = nl;
   a.S = S;
-  a.unit_begin[0] = 0;
+  a.kb_begin[0] = 0;
   for (int s = 0; s < VFA_MAX_SCALES; ++s) {
     const int ss = s < S ? s : 0;
     a.gs[s] = gs[ss];
     a.f[s] = f[ss];
     a.dwr[s] = dwr[ss];
     a.T[s] = T[ss];
-    a.kblocks[s] = (T[ss] + STAGES_PER_BLOCK * KST - 1) / (STAGES_PER_BLOCK * KST);
-    if (a.kblocks[s] < 1) a.kblocks[s] = 1;
-    if (s < S) a.unit_begin[s + 1] = a.unit_begin[s] + (dwr[s] != nullptr && T[s] > 0 ? nl * a.kblocks[s] : 0);
+    const int kblocks = (dwr[ss] != nullptr && T[ss] > 0) ? (T[ss] + STAGES_PER_BLOCK * KST - 1) / (STAGES_PER_BLOCK * KST) : 0;
+    if (s < S) a.kb_begin[s + 1] = a.kb_begin[s] + kblocks;
   }
-  a.n_units = a.unit_begin[S];
-  if (a.n_units == 0) return VFA_OK;
+  a.n_kb = a.kb_begin[S];
+  if (a.n_kb == 0) return VFA_OK;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
@@ -664,8 +675,10 @@ static int launch_dweight(const float* const* gs, const float* const* f, float* 
     }
     resident_clusters = n;
   }
-  const int clusters = a.n_units < resident_clusters ? a.n_units : resident_clusters;
-  cfg.gridDim = dim3(2 * clusters);
+  int shares = resident_clusters / nl;
+  if (shares < 1) shares = 1;
+  if (shares > a.n_kb) shares = a.n_kb;
+  cfg.gridDim = dim3(2 * shares * nl);
   VFA_CUDA(cudaLaunchKernelEx(&cfg, dweight_kernel, a));
   VFA_LAUNCH_CHECK("dweight_kernel");
   return VFA_OK;
