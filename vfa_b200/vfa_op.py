@@ -309,7 +309,11 @@ class VFA(nn.Module):
     def geometry(self, grid_lw, crange=(-1.0, 0.95)) -> _lib.Geometry:
         if self.args is None:
             raise ValueError('VFA needs `args` with .data and .image_size (reference vfa_op.py:38-43, :75)')
-        layer_z = self.z_corners[:, 0, 0, 2].tolist()
+        # the layer heights live in a (device) buffer; read them back once, not per call (a .tolist() is a stream sync)
+        key = (self.z_corners.data_ptr(), self.z_corners._version)
+        if getattr(self, '_layer_z_key', None) != key:
+            self._layer_z, self._layer_z_key = self.z_corners[:, 0, 0, 2].tolist(), key
+        layer_z = self._layer_z
         return make_geometry(self.num_grid_layer, self.cube_size, layer_z, grid_lw, self.args.data, self.args.image_size,
                              crange)
 
