@@ -543,13 +543,14 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
         const int uy1 = __reduce_max_sync(0xffffffffu, vis ? y0 + ny - 1 : -1);
         const float wx_first = __uint_as_float(r0.z), wx_last = __uint_as_float(r0.w);
         const float wy_first = __uint_as_float(r1.x), wy_last = __uint_as_float(r1.y), wy_mid = __uint_as_float(r1.z);
-        const float* rowp = yplane + ((size_t)uy0 * fw + ux0) * CH;
-        for (int ty = uy0; ty <= uy1; ++ty, rowp += (size_t)fw * CH) {
-          const int ry = ty - y0;
-          const float wy = (vis && ry >= 0 && ry < ny) ? (ry == 0 ? wy_first : (ry == ny - 1 ? wy_last : wy_mid)) : 0.f;
-          for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
-            const int rx = ux0 + cb + jl - x0;
-            const float wx = (rx >= 0 && rx < nx) ? (rx == 0 ? wx_first : (rx == nx - 1 ? wx_last : 1.0f)) : 0.f;
+        // column blocks outermost (nearly always one): the column weight of this lane is computed once per block
+        for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
+          const int rx = ux0 + cb + jl - x0;
+          const float wx = (vis && rx >= 0 && rx < nx) ? (rx == 0 ? wx_first : (rx == nx - 1 ? wx_last : 1.0f)) : 0.f;
+          const float* rowp = yplane + ((size_t)uy0 * fw + ux0) * CH;
+          for (int ty = uy0; ty <= uy1; ++ty, rowp += (size_t)fw * CH) {
+            const int ry = ty - y0;
+            const float wy = (ry >= 0 && ry < ny) ? (ry == 0 ? wy_first : (ry == ny - 1 ? wy_last : wy_mid)) : 0.f;
             float wl = wy * wx;                         // weight of (cell cl, column cb + jl) in this row
             asm volatile("" : "+f"(wl));                // keep it in a register (no rematerialisation per shuffle)
             const uint32_t bm = __ballot_sync(0xffffffffu, wl != 0.f);     // bit 4*j + c
