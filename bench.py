@@ -5,14 +5,15 @@
     python bench.py --impl reference ...                     # the reference algorithm on the box's host cores
 
 One "step" = one pass of the hot path over one batch of synthetic frames:
-    projection table (1 launch) + weight re-layout (3) + tap-recipe table (1) + fused gather/collapse/ReLU/sum kernel (1).
+    projection table (1 launch) + weight re-layout (3) + tap records (1) + image-plane 3xTF32 GEMM (1) + quad pooling with
+    bias / ReLU / view-and-scale sum (1)   [--flags 32: one fused grid-side kernel instead of the last two].
 Default workload: MultiviewC-shaped (7 views, 1280x720 source, stride-8/16/32 maps 90x160 / 45x80 / 23x40, C = 256,
 156x156x5 voxel grid = the shipped config-of-record of "37.5 m x 37.5 m"), B frames per GPU.
 Multi-GPU = batch data parallel (frames are independent: no data-path collective, weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same through the public
 API with pinned-host inputs and a device->host read of the result inside the timed region; `roofline` describes the
-fused kernel; `cpu_baseline` = the oracle's torch-CPU port of the reference timed on the host cores (N = 1 only).
+dominant kernel (pool_quad_kernel; the GEMM under `second_kernel`, the whole step under `step`); `cpu_baseline` = the oracle's torch-CPU port of the reference timed on the host cores (N = 1 only).
 """
 import argparse
 import json
@@ -352,7 +353,7 @@ def main():
                'h2d_bytes_per_step': sum(h.numel() * 4 for h in host_feats),
                'd2h_bytes_per_step': host_out.numel() * 4, 'steps': n_e2e,
                'note': 'vfa_b200.StreamingAggregator: every step copies pinned-host [B,V,C,fH,fW] fp32 features H2D, transposes '
-                       'NCHW->channels-last, rebuilds the table, runs the fused kernel (weights re-laid once: inference) and '
+                       'NCHW->channels-last, rebuilds the table, runs the aggregation kernels (weights re-laid once: inference) and '
                        'copies the full [B,C,L,W] result D2H; copies and compute overlap on 3 streams / 2 device slots'}
 
     cpu_baseline = None
