@@ -102,3 +102,34 @@ def test_synthetic_inputs_are_deterministic():
     assert all(torch.equal(x, y) for x, y in zip(f1, f2)) and float(f1[0].min()) >= 0.0
     p = synthetic.collapse_params(g, channels=4)
     assert p[0][0].shape == (4, 20) and p[0][1].shape == (4,)
+
+
+def test_workspace_sizing_is_host_only(monkeypatch):
+    """vfa_aggregate_workspace_bytes is pure host arithmetic: the default C = 256 forward carries the image-plane
+    intermediate Y of one frame chunk (bounded by the 6 GiB budget), VFA_FLAG_GRID_SIDE does not; the backward adds its
+    CSR / gm / Gs buffers; other channel counts use the generic kernels' small workspace."""
+    g = geometry.MULTIVIEWC
+    L = _lib.lib()
+    zs = list(range(0, g.grid_height, g.cube_size[2]))
+    geom = vfa_b200.make_geometry(len(zs), g.cube_size, zs, g.grid_shape, g.name, g.image_size)
+
+    def shape(batch, channels=256):
+        sh = _lib.Shape()
+        sh.batch, sh.n_views, sh.channels, sh.n_scales = batch, g.n_views, channels, 3
+        for s, (h, w) in enumerate(g.feature_sizes()):
+            sh.feat_h[s], sh.feat_w[s] = h, w
+        return sh
+
+    def ws(batch, flags=0, channels=256):
+        sh = shape(batch, channels)
+        return L.vfa_aggregate_workspace_bytes(ctypes.byref(geom), ctypes.byref(sh), flags)
+
+    monkeypatch.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
+    y_frame = g.n_views * len(zs) * sum(h * w for h, w in g.feature_sizes()) * 256 * 4          # 678 MB
+    one = ws(1)
+    assert one > y_frame                                       # Y of one frame + CSR / gm / Gs of the backward
+    assert ws(4) > one + 3 * y_frame                           # grows with the chunk ...
+    assert ws(64) == ws(32)                                    # ... up to the 6 GiB budget (chunks are looped)
+    assert ws(4, channels=16) < 200 << 20                      # generic kernels: weights + small scratch
+    monkeypatch.setenv('VFA_FSIDE_Y_BUDGET_MB', '700')         # one frame per chunk
+    assert ws(4) == ws(1)
