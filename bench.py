@@ -404,8 +404,8 @@ def main():
                 'algorithmic_bytes_per_launch': pool_bytes,
                 'peak_source': peaks['source'],
                 'note': 'pooling of the per-layer products Y (fp32 [plane, layer, texel, C]): algorithmic bytes = Y once + tap '
-                        'records once + output once; the kernel is bound by the SM-side gather (L1 data pipe 63 %, issue '
-                        'slots 54 % in profiles/r1_fside_ncu_full.json), not by HBM',
+                        'records once + output once; the kernel is bound by the SM-side gather (L1 data pipe 72 % busy, '
+                        'profiles/r1_fside_ncu_full.json), not by HBM',
                 'second_kernel': {
                     'kernel': 'ygemm_kernel', 'bound': 'tensor', 'achieved': gemm_tflops, 'peak': peaks['tflops'],
                     'unit': 'TFLOP/s', 'frac': gemm_tflops / peaks['tflops'], 'kernel_ms': t_gemm,
