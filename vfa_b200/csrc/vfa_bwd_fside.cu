@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(GT * GT * 32, 2) dy_gather_kernel(const Gather
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (e1 <= q.capacity) {
-    const float* gm = q.gm + (((size_t)bl * p.V + v) * p.S + s) * p.LW * CH + lane * 8;
+    // lane l owns channels [4l, 4l+4) and [128 + 4l, 128 + 4l + 4): each LDG.128 of the warp covers 512 contiguous bytes
+    // (4 L1 wavefronts; with 8 consecutive channels per lane the 32-byte lane stride made it 8)
+    const float* gm = q.gm + (((size_t)bl * p.V + v) * p.S + s) * p.LW * CH + lane * 4;
     const int2* ent = reinterpret_cast<const int2*>(q.entries);
     int e = e0;
     for (; e + GB <= e1; e += GB) {                    // GB entries (2 x LDG.128 each) in flight
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(GT * GT * 32, 2) dy_gather_kernel(const Gather
 #pragma unroll
       for (int k = 0; k < GB; ++k) {
         ga[k] = __ldg(reinterpret_cast<const float4*>(gm + (size_t)en[k].x * CH));
-        gb[k] = __ldg(reinterpret_cast<const float4*>(gm + (size_t)en[k].x * CH + 4));
+        gb[k] = __ldg(reinterpret_cast<const float4*>(gm + (size_t)en[k].x * CH + CH / 2));
       }
 #pragma unroll
       for (int k = 0; k < GB; ++k) fma8w(acc, __int_as_float(en[k].y), ga[k], gb[k]);
@@ -323,13 +325,13 @@ __global__ void __launch_bounds__(GT * GT * 32, 2) dy_gather_kernel(const Gather
     for (; e < e1; ++e) {
       const int2 a = __ldg(ent + e);
       const float4 a0 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH + 4));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(gm + (size_t)a.x * CH + CH / 2));
       fma8w(acc, __int_as_float(a.y), a0, a1);
     }
   }
-  float* dst = gs + ((((size_t)bl * p.V + v) * hw + texel) * p.nl + n) * CH + lane * 8;
+  float* dst = gs + ((((size_t)bl * p.V + v) * hw + texel) * p.nl + n) * CH + lane * 4;
   *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  *reinterpret_cast<float4*>(dst + CH / 2) = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
 // Rows the CSR could not hold (offsets[row + 1] > capacity): completed with atomics.  Exits at once when there are none.

@@ -376,6 +376,26 @@ __device__ __forceinline__ void fma8(float (&acc)[8], float w, const float4& a, 
   acc[4] = r2.x; acc[5] = r2.y; acc[6] = r3.x; acc[7] = r3.y;
 }
 
+// Channel <-> lane map of the pooling kernels: lane l owns channels [4l, 4l+4) (acc[0..3]) and [128 + 4l, 128 + 4l + 4)
+// (acc[4..7]), so each of the two LDG.128 of a warp covers 512 contiguous bytes of a texel row = 4 L1 wavefronts (with 8
+// consecutive channels per lane the 32-byte lane stride touches every 128-byte line twice: 8 wavefronts per load).
+__device__ __forceinline__ int chan_of(int lane, int i) { return (i < 4 ? 0 : CH / 2 - 4) + lane * 4 + i; }
+
+// ReLU pass bits of one cell (bit i of `bits` = channel chan_of(lane, i)) -> mask words (word o/32, bit o%32) at
+// words[k * word_stride]: lanes 8k .. 8k+7 hold the eight nibbles of word k (low channels) and of word 4 + k (high)
+__device__ __forceinline__ void store_mask_words(uint32_t* words, size_t word_stride, int lane, uint32_t bits, bool valid) {
+  uint32_t lo = (bits & 0xfu) << (4 * (lane & 7)), hi = (bits >> 4) << (4 * (lane & 7));
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+    lo |= __shfl_xor_sync(0xffffffffu, lo, d);
+    hi |= __shfl_xor_sync(0xffffffffu, hi, d);
+  }
+  if ((lane & 7) == 0 && valid) {
+    words[(size_t)(lane >> 3) * word_stride] = lo;
+    words[(size_t)(4 + (lane >> 3)) * word_stride] = hi;
+  }
+}
+
 template <bool MASK>
 __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolArgs a) {
   const AggParams& p = a.p;
@@ -399,7 +419,7 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
   for (int v = 0; v < p.V; ++v) {
     for (int s = 0; s < p.S; ++s) {
       const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
-      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 8;
+      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -428,7 +448,7 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
               va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (w[k] != 0.f) {                      // taps of weight 0 are never fetched
                 va[k] = __ldg(reinterpret_cast<const float4*>(row + (size_t)t * CH));
-                vb[k] = __ldg(reinterpret_cast<const float4*>(row + (size_t)t * CH + 4));
+                vb[k] = __ldg(reinterpret_cast<const float4*>(row + (size_t)t * CH + CH / 2));
               }
             }
 #pragma unroll
@@ -438,8 +458,8 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
         }
       }
       // + bias, ReLU (vfa_op.py:123-124), sum over scales and views (vfanet.py:79, :82)
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 4));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + CH / 2 + lane * 4));
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       uint32_t bits = 0;
 #pragma unroll
@@ -448,18 +468,13 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
         bits |= (t > 0.f ? 1u : 0u) << i;
         out[i] += fmaxf(t, 0.f);
       }
-      if (MASK) {       // word o/32, bit o%32: lanes 4k .. 4k+3 hold the four bytes of word k
-        bits <<= 8 * (lane & 3);
-        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-        if ((lane & 3) == 0)
-          p.mask[((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (lane >> 2)) * p.LW + cell] = bits;
-      }
+      if (MASK)
+        store_mask_words(p.mask + (((size_t)b * p.V + v) * p.S + s) * (CH / 32) * p.LW + cell, (size_t)p.LW, lane, bits, true);
     }
   }
-  float* o = p.out + ((size_t)b * CH + lane * 8) * p.LW + cell;
+  float* o = p.out + (size_t)b * CH * p.LW + cell;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[(size_t)i * p.LW] = out[i];
+  for (int i = 0; i < 8; ++i) o[(size_t)chan_of(lane, i) * p.LW] = out[i];
 }
 
 
@@ -519,7 +534,7 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
   for (int v = 0; v < p.V; ++v) {
     for (int s = 0; s < p.S; ++s) {
       const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
-      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 8;
+      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
       float acc[4][8];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -563,7 +578,7 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
               for (int k = 0; k < QTB; ++k) {
                 if ((bm >> (4 * (j + k))) & 0xfu) {     // texels no box of the quad covers are never fetched
                   va[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH));
-                  vb[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH + 4));
+                  vb[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH + CH / 2));
 #if VFA_QUAD_PREFETCH
                   // the same column of the next union row: one warp-wide prefetch covers the texel's 8 lines
                   if (ty < uy1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k * CH + (size_t)fw * CH));
@@ -586,8 +601,8 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
         }
       }
       // + bias, ReLU (vfa_op.py:123-124), sum over scales and views (vfanet.py:79, :82)
-      const float4 bi0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8));
-      const float4 bi1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 8 + 4));
+      const float4 bi0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 4));
+      const float4 bi1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + CH / 2 + lane * 4));
       const float bb[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -604,13 +619,11 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
         o1.x += fmaxf(t[4], 0.f); o1.y += fmaxf(t[5], 0.f); o1.z += fmaxf(t[6], 0.f); o1.w += fmaxf(t[7], 0.f);
         *reinterpret_cast<float4*>(outw + c * CH) = o0;
         *reinterpret_cast<float4*>(outw + c * CH + 4) = o1;
-        if (MASK) {     // word o/32, bit o%32: lanes 4k .. 4k+3 hold the four bytes of word k
-          bits <<= 8 * (lane & 3);
-          bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-          bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        if (MASK) {
           const int cy = cy0 + (c >> 1), cx = cx0 + (c & 1);
-          if ((lane & 3) == 0 && cy < p.L && cx < p.W)
-            p.mask[((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (lane >> 2)) * p.LW + cy * p.W + cx] = bits;
+          const bool ok = cy < p.L && cx < p.W;
+          store_mask_words(p.mask + (((size_t)b * p.V + v) * p.S + s) * (CH / 32) * p.LW + (ok ? cy * p.W + cx : 0),
+                           (size_t)p.LW, lane, bits, ok);
         }
       }
     }
@@ -621,15 +634,10 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
     if (cy >= p.L || cx >= p.W) continue;
     const float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
     const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
-    float* o = p.out + ((size_t)b * CH + lane * 8) * p.LW + cy * p.W + cx;
-    o[0] = o0.x;
-    o[(size_t)1 * p.LW] = o0.y;
-    o[(size_t)2 * p.LW] = o0.z;
-    o[(size_t)3 * p.LW] = o0.w;
-    o[(size_t)4 * p.LW] = o1.x;
-    o[(size_t)5 * p.LW] = o1.y;
-    o[(size_t)6 * p.LW] = o1.z;
-    o[(size_t)7 * p.LW] = o1.w;
+    float* o = p.out + (size_t)b * CH * p.LW + cy * p.W + cx;
+    const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[(size_t)chan_of(lane, i) * p.LW] = ov[i];
   }
 }
 
