@@ -266,8 +266,11 @@ struct GatherParams {
 };
 
 constexpr int GT = 4;                            // texel tile side: one warp per texel
+#ifndef VFA_GATHER_MINBLOCKS
+#define VFA_GATHER_MINBLOCKS 3
+#endif
 #ifndef VFA_GATHER_BATCH
-#define VFA_GATHER_BATCH 4
+#define VFA_GATHER_BATCH 3
 #endif
 constexpr int GB = VFA_GATHER_BATCH;             // CSR entries in flight per warp
 
@@ -281,7 +284,7 @@ __device__ __forceinline__ void fma8w(float (&acc)[8], float w, const float4& a,
   acc[4] = r2.x; acc[5] = r2.y; acc[6] = r3.x; acc[7] = r3.y;
 }
 
-__global__ void __launch_bounds__(GT * GT * 32, 2) dy_gather_kernel(const GatherParams q) {
+__global__ void __launch_bounds__(GT * GT * 32, VFA_GATHER_MINBLOCKS) dy_gather_kernel(const GatherParams q) {
   const AggParams& p = q.p;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bx = blockIdx.x, bl = blockIdx.y;
