@@ -310,7 +310,7 @@ def test_bf16_feature_storage():
 
 def test_feature_side_chunking_and_ragged_grids(monkeypatch):
     """Feature-side forward (default, C = 256): frame chunks (Y budget forced down to one frame per chunk), grids whose
-    sides are not multiples of the 2 x 2 quads / 6 x 8 CTA tiles, a texel-row count that is not a multiple of the
+    sides are not multiples of the 2 x 2 quads / 4 x 8 CTA tiles, a texel-row count that is not a multiple of the
     256-row GEMM tile -- all bit-identical to the unchunked run and inside the tolerance of the fp32 FFMA kernel."""
     g = geometry.MULTIVIEWC
     full = geometry.grid_for(g)

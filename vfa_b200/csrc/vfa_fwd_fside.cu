@@ -484,23 +484,23 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
 // (128 B / clk / SM, 80 % busy).  Here a warp owns a 2 x 2 quad of cells: per (view, scale, layer) it walks the UNION of
 // the four boxes once, loads every texel once (2 x LDG.128 per lane = the 1 KB row) and applies it to each cell whose
 // box contains it.  Lane 4*j + c computes the weight of cell c for column j of the current 8-column block; the weight
-// of (cell, texel) then reaches all lanes by one shuffle.  Output partial sums live in shared memory (48 KB per CTA).
+// of (cell, texel) then reaches all lanes by one shuffle.  Output partial sums live in shared memory (32 KB per CTA).
 #ifndef VFA_QUAD_X
 #define VFA_QUAD_X 4
 #endif
 #ifndef VFA_QUAD_Y
-#define VFA_QUAD_Y 3
+#define VFA_QUAD_Y 2
 #endif
 #ifndef VFA_QUAD_BATCH
 #define VFA_QUAD_BATCH 2
 #endif
 #ifndef VFA_QUAD_MINBLOCKS
-#define VFA_QUAD_MINBLOCKS 2
+#define VFA_QUAD_MINBLOCKS 3
 #endif
 #ifndef VFA_QUAD_PREFETCH
 #define VFA_QUAD_PREFETCH 0
 #endif
-constexpr int QX = VFA_QUAD_X, QY = VFA_QUAD_Y;         // quads per CTA: 6 x 8 cells
+constexpr int QX = VFA_QUAD_X, QY = VFA_QUAD_Y;         // quads per CTA: 4 x 8 cells, 3 CTAs (24 warps) per SM
 constexpr int QWARPS = QX * QY;
 constexpr int QTB = VFA_QUAD_BATCH;                     // texels of a union row in flight per warp (2 x LDG.128 each)
 static_assert(8 % QTB == 0, "");
@@ -737,7 +737,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
                                   (int)cudaSharedmemCarveoutMaxL1));
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxL1));
-    // two CTAs x 48 KB of partial sums per SM, the rest of the unified array as L1
+    // three CTAs x 32 KB of partial sums per SM, the rest of the unified array as L1
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     attr_set = true;
