@@ -215,9 +215,12 @@ __global__ void __launch_bounds__(MG_WARPS * 32) mask_grad_kernel(const GradPara
   const int bvs = blockIdx.y;                                  // (bl * V + v) * S + s
   const int s = bvs % p.S, v = (bvs / p.S) % p.V, bl = bvs / (p.S * p.V);
   const int b = q.b0 + bl;
-  const uint32_t* mrow = p.mask + ((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (lane >> 2)) * p.LW;
-  const float* grow = q.gt + (size_t)bl * p.LW * CH + lane * 8;
-  float* out = q.gm + (size_t)bvs * p.LW * CH + lane * 8;
+  // lane l owns channels [4l, 4l+4) and [128 + 4l, 128 + 4l + 4): contiguous 512-byte warp accesses (see pool_quad_kernel);
+  // their ReLU bits are nibble (l & 7) of mask word l >> 3 and of word 4 + (l >> 3)
+  const uint32_t* mlo = p.mask + ((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (lane >> 3)) * p.LW;
+  const uint32_t* mhi = mlo + (size_t)4 * p.LW;
+  const float* grow = q.gt + (size_t)bl * p.LW * CH + lane * 4;
+  float* out = q.gm + (size_t)bvs * p.LW * CH + lane * 4;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -225,26 +228,26 @@ __global__ void __launch_bounds__(MG_WARPS * 32) mask_grad_kernel(const GradPara
   for (int k = 0; k < MG_CELLS; ++k) {
     const int cell = cell0 + k;
     if (cell >= p.LW) break;
-    const uint32_t bits = (__ldg(mrow + cell) >> (8 * (lane & 3))) & 0xffu;
+    const uint32_t blo = (__ldg(mlo + cell) >> (4 * (lane & 7))) & 0xfu, bhi = (__ldg(mhi + cell) >> (4 * (lane & 7))) & 0xfu;
     float4 a = __ldg(reinterpret_cast<const float4*>(grow + (size_t)cell * CH));
-    float4 c = __ldg(reinterpret_cast<const float4*>(grow + (size_t)cell * CH + 4));
-    a.x = (bits & 1u) ? a.x : 0.f;
-    a.y = (bits & 2u) ? a.y : 0.f;
-    a.z = (bits & 4u) ? a.z : 0.f;
-    a.w = (bits & 8u) ? a.w : 0.f;
-    c.x = (bits & 16u) ? c.x : 0.f;
-    c.y = (bits & 32u) ? c.y : 0.f;
-    c.z = (bits & 64u) ? c.z : 0.f;
-    c.w = (bits & 128u) ? c.w : 0.f;
+    float4 c = __ldg(reinterpret_cast<const float4*>(grow + (size_t)cell * CH + CH / 2));
+    a.x = (blo & 1u) ? a.x : 0.f;
+    a.y = (blo & 2u) ? a.y : 0.f;
+    a.z = (blo & 4u) ? a.z : 0.f;
+    a.w = (blo & 8u) ? a.w : 0.f;
+    c.x = (bhi & 1u) ? c.x : 0.f;
+    c.y = (bhi & 2u) ? c.y : 0.f;
+    c.z = (bhi & 4u) ? c.z : 0.f;
+    c.w = (bhi & 8u) ? c.w : 0.f;
     *reinterpret_cast<float4*>(out + (size_t)cell * CH) = a;
-    *reinterpret_cast<float4*>(out + (size_t)cell * CH + 4) = c;
+    *reinterpret_cast<float4*>(out + (size_t)cell * CH + CH / 2) = c;
     acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
     acc[4] += c.x; acc[5] += c.y; acc[6] += c.z; acc[7] += c.w;
   }
   float* gb = s == 0 ? q.gbias[0] : (s == 1 ? q.gbias[1] : q.gbias[2]);
   if (gb == nullptr) return;                                   // uniform per CTA
 #pragma unroll
-  for (int i = 0; i < 8; ++i) bsum[warp][lane * 8 + i] = acc[i];
+  for (int i = 0; i < 8; ++i) bsum[warp][(i < 4 ? 0 : CH / 2 - 4) + lane * 4 + i] = acc[i];
   __syncthreads();
   float t = 0.f;
 #pragma unroll
