@@ -714,7 +714,9 @@ static Plan make_plan(int V, int S, int nl, size_t LW, const int* fh, const int*
     const int v = atoi(e);
     if (v > 0) per_box = v;
   }
-  pl.capacity = (int)((size_t)per_box * V * S * nl * LW);
+  size_t cap = (size_t)per_box * V * S * nl * LW;
+  if (cap > ((size_t)1 << 30)) cap = (size_t)1 << 30;      // entry offsets are 32-bit; rows beyond go to the overflow kernel
+  pl.capacity = (int)cap;
   size_t o = 0;
   pl.off_wprep = o;   o += align256((size_t)S * nl * (CH / KCH) * (2 * B_BYTES));
   pl.off_dwr = o;     o += align256((size_t)S * CH * CH * nl * sizeof(float));
