@@ -1,0 +1,51 @@
+"""bench.py prints ONE JSON line with the keys the driver reads (reference arm on CPU here; our arm needs a B200)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+             'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'cpu_baseline'}
+
+
+def _run(*args, timeout=600):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), *args], capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, out.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    """--impl reference: the reference's operator sequence (oracle port) on the host cores, same metric / config."""
+    d = _run('--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-views', '1')
+    assert BASE_KEYS <= set(d) and d['impl'] == 'reference'
+    assert d['metric'] == 'aggregation_frames_per_s' and d['unit'] == 'frames/s' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['config']['workload'].startswith('MultiviewC')
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+
+
+@pytest.mark.gpu
+def test_our_arm_line():
+    d = _run('--steps', '3', '--warmup', '3', '--cpu-views', '1')
+    assert BASE_KEYS | {'clocks', 'gpu_launches', 'roofline'} <= set(d)
+    assert d['metric'] == 'aggregation_frames_per_s' and d['n_gpus'] == 1 and d['steps'] == 3 and d['value'] > 0
+    assert d['vs_baseline'] is None and d['data'] == 'synthetic' and d['scaling'] == 'weak'
+    assert d['config']['kernel_path'] == 'fside_tf32x3' and 'workload' in d['config']
+    assert d['gpu_launches'] == 7 * 3
+    e = d['e2e']
+    assert e['value'] > 0 and e['h2d_bytes_per_step'] == 4 * 7 * 256 * (90 * 160 + 45 * 80 + 23 * 40) * 4
+    assert e['d2h_bytes_per_step'] == 4 * 256 * 156 * 156 * 4 and e['value'] < d['value']
+    r = d['roofline']
+    assert r['bound'] in ('hbm', 'tensor') and r['unit'] in ('GB/s', 'TFLOP/s')
+    assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9 and 0 < r['frac'] < 1
+    assert r['kernel'] == 'pool_quad_kernel' and r['second_kernel']['kernel'] == 'ygemm_kernel'
+    assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['value'] > 0 and cb['cores'] >= 1
