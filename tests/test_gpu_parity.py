@@ -357,3 +357,59 @@ def test_relu_mask_agrees_between_formulations():
     total = diff.size * 32
     print(f'mask bits that differ: {flipped} of {total}')
     assert flipped <= total * 1e-4
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_table_bit_exact_random_rigs(name):
+    """Randomised cameras (outside, inside and just above the field; looking across, down, and along a grid axis so that
+    corners land behind the camera and on the principal plane), random sub-grids: boxes, area, visibility and tap
+    indices of the CUDA table kernels are bit-identical to the numpy restatement that the golden vectors pin to the
+    reference."""
+    g = geometry.GEOMETRIES[name]
+    full = geometry.grid_for(g).numpy()
+    L, W = full.shape[:2]
+    rng = np.random.RandomState(1234 + NAMES.index(name))
+    # field extent in the dataset's world units (the cameras of synthetic.ring_calibs live in the same frame)
+    ring = synthetic.ring_calibs(g).numpy()
+    world = onp.to_world(full.reshape(-1, 3).astype(np.float64) + 0.0, name).reshape(L, W, 3)
+    lo, hi = world.reshape(-1, 3).min(0), world.reshape(-1, 3).max(0)
+    span = float(max(hi[0] - lo[0], hi[1] - lo[1]))
+    cams = []
+    for k in range(10):
+        where = k % 3
+        if where == 0:      # outside the field, elevated
+            ang = rng.uniform(0, 2 * np.pi)
+            eye = np.array([(lo[0] + hi[0]) / 2 + np.cos(ang) * span * rng.uniform(0.6, 1.2),
+                            (lo[1] + hi[1]) / 2 + np.sin(ang) * span * rng.uniform(0.6, 1.2), span * rng.uniform(0.05, 0.4)])
+        elif where == 1:    # inside the field, low: voxels behind the camera
+            eye = np.array([rng.uniform(lo[0], hi[0]), rng.uniform(lo[1], hi[1]), span * rng.uniform(0.005, 0.05)])
+        else:               # exactly above a grid cell origin, looking straight along +x: corners on the principal plane
+            i, j = rng.randint(L), rng.randint(W)
+            eye = np.array([world[i, j, 0], world[i, j, 1], span * 0.02])
+        if where == 2:
+            target = eye + np.array([1.0, 0.0, 0.0])
+        else:
+            target = np.array([rng.uniform(lo[0], hi[0]), rng.uniform(lo[1], hi[1]), 0.0])
+        cams.append(synthetic.look_at(eye, target, rng.uniform(0.5, 1.6) * g.image_size[1] * 0.7, g.image_size).astype(np.float32))
+    calibs = np.stack(cams)
+    assert calibs.shape[1:] == ring.shape[1:]
+    i0, j0 = rng.randint(0, L // 2), rng.randint(0, W // 2)
+    grid = np.ascontiguousarray(full[i0:i0 + rng.randint(8, 40):1, j0:j0 + rng.randint(8, 40):1])
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), torch.from_numpy(calibs).cuda(), torch.from_numpy(grid).cuda())
+    boxes = table.boxes.cpu().numpy()
+    n_nan = 0
+    for v in range(len(cams)):
+        want = onp.project_boxes(calibs[v], grid, g.grid_height, g.cube_size, name, g.image_size)
+        assert np.array_equal(_bits(boxes[v]), _bits(want)), (name, v)
+        n_nan += int(np.isnan(want).sum())
+    for fh, fw in g.feature_sizes():
+        area, vis, taps = table.scale_table(fh, fw)
+        for v in range(len(cams)):
+            b = boxes[v]
+            a_want, v_want = onp.area_visible(b, fh, fw)
+            assert np.array_equal(_bits(area[v].cpu().numpy()), _bits(a_want))
+            assert np.array_equal(vis[v].cpu().numpy(), v_want)
+            t_want = np.stack([onp.tap_index(b[..., 0], fw), onp.tap_index(b[..., 1], fh),
+                               onp.tap_index(b[..., 2], fw), onp.tap_index(b[..., 3], fh)], -1)
+            assert np.array_equal(taps[v].cpu().numpy(), t_want)
+    print(f'{name}: 10 random cameras on a {grid.shape[0]} x {grid.shape[1]} sub-grid, {n_nan} NaN box edges, all bit-exact')
