@@ -133,3 +133,16 @@ def test_workspace_sizing_is_host_only(monkeypatch):
     assert ws(4, channels=16) < 200 << 20                      # generic kernels: weights + small scratch
     monkeypatch.setenv('VFA_FSIDE_Y_BUDGET_MB', '700')         # one frame per chunk
     assert ws(4) == ws(1)
+
+
+def test_multiscale_module_state_dict_matches_vfanet_keys():
+    """MultiScaleVFA carries the reference network's attribute names, so the vfa8/16/32 entries of a VFANet checkpoint
+    (reference vfanet.py:30-32) load into it unchanged."""
+    g = geometry.MULTIVIEWX
+    m = vfa_b200.MultiScaleVFA(256, g.grid_height, g.cube_size, SimpleNamespace(data=g.name, image_size=g.image_size))
+    keys = list(m.state_dict())
+    want = [f'vfa{s}.{k}' for s in (8, 16, 32) for k in ('z_corners', 'corners_offset', 'collapse.weight', 'collapse.bias')]
+    assert keys == want
+    assert tuple(m.vfa16.collapse.weight.shape) == (256, 256 * g.n_layers)
+    with pytest.raises(ValueError, match='three FPN scales'):
+        m([torch.zeros(1, 1, 256, 4, 4)], torch.zeros(1, 3, 4), geometry.grid_for(g))

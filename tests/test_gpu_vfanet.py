@@ -75,3 +75,28 @@ def test_fused_cameras_train_step_updates_collapse_and_laterals():
     for name, p in m.named_parameters():
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
         assert float(p.grad.abs().max()) > 0, name
+
+
+def test_multiscale_module_equals_module_loop():
+    """MultiScaleVFA(feats [B,V,C,H,W] x 3, calibs, grid) == the reference's loop over cameras and scales of drop-in VFA
+    modules (vfanet.py:64-82), per frame of the batch, and its gradients reach the collapse parameters."""
+    from types import SimpleNamespace
+    from vfa_b200 import geometry, synthetic
+    g = geometry.MULTIVIEWC
+    grid = geometry.grid_for(g)[::2, ::2].contiguous().cuda()
+    V, B = 3, 2
+    calibs = synthetic.ring_calibs(g, n_views=V).cuda()
+    feats = [f.cuda() for f in synthetic.features(g, batch=B, n_views=V, seed=31)]
+    m = vfa_b200.MultiScaleVFA(256, g.grid_height, g.cube_size, SimpleNamespace(data=g.name, image_size=g.image_size)).cuda()
+    out = m(feats, calibs, grid)
+    assert out.shape == (B, 256) + tuple(grid.shape[:2])
+    with torch.no_grad():
+        for b in range(B):
+            want = 0
+            for v in range(V):
+                want = want + sum(mod(f[b, v:v + 1], calibs[v], grid[None])
+                                  for mod, f in zip((m.vfa8, m.vfa16, m.vfa32), feats))
+            torch.testing.assert_close(out[b:b + 1], want, rtol=1e-5, atol=2e-6)
+    out.sum().backward()
+    for mod in (m.vfa8, m.vfa16, m.vfa32):
+        assert mod.collapse.weight.grad is not None and float(mod.collapse.weight.grad.abs().max()) > 0

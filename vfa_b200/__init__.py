@@ -3,7 +3,7 @@
     from vfa_b200 import VFA, aggregate, build_table
 
 `VFA` is a drop-in for the reference module `vfa.model.vfa_op.VFA`; `aggregate` is the fused batched multi-view
-entry.  All arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of include/vfa_b200.h
+entry, `MultiScaleVFA` the same as an nn.Module (feats [B,V,C,H,W] per scale, calibs, grid -> [B,C,L,W]).  All arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of include/vfa_b200.h
 (libvfa_b200.so, loaded with ctypes); there is no CPU, Triton or PyTorch-op fallback.
 """
 from . import geometry, synthetic                                    # noqa: F401
@@ -13,5 +13,6 @@ from .vfa_op import (VFA, ProjectionTable, aggregate, aggregate_forward_raw, bui
                      make_geometry, make_shape, prepare_weights, to_channels_last, workspace_for)
 
 from .streaming import StreamingAggregator                          # noqa: F401
+from .vfanet import MultiScaleVFA                                   # noqa: F401
 
 __version__ = '0.1.0'

@@ -43,3 +43,32 @@ def aggregate_cameras(model, feats8, feats16, feats32, calibs, grid, crange=(-1.
     feats = [x.reshape(batch, V, *x.shape[1:]) for x in lats]
     return aggregate(feats, table, [m.collapse.weight for m in vfas], [m.collapse.bias for m in vfas],
                      flags=vfas[0].flags)
+
+
+class MultiScaleVFA(torch.nn.Module):
+    """The whole aggregation stage of the reference network as ONE module with the batched multi-view signature of
+    BASELINE.json's north_star:  forward(feats, calibs, grid) with feats = list of per-scale `[B, V, C, fH, fW]` lateral
+    maps, calibs `[V, 3, 4]`, grid `[L, W, 3]` or `[1, L, W, 3]`  ->  `[B, C, L, W]`.
+
+    It owns three `VFA` modules under the reference's attribute names (`vfa8`, `vfa16`, `vfa32`, reference
+    vfa/model/vfanet.py:30-32), so the `vfa{8,16,32}.*` entries of a `VFANet` checkpoint load with
+    `load_state_dict(..., strict=False)` filtering, and its result equals the reference's loop
+    `sum_cam (vfa8(lat8[cam]) + vfa16(lat16[cam]) + vfa32(lat32[cam]))` (vfanet.py:64-82) for every frame of the batch.
+    """
+
+    def __init__(self, channel, grid_height, cube_size, args, flags: int = 0):
+        super().__init__()
+        from .vfa_op import VFA
+        self.vfa8 = VFA(channel, grid_height, cube_size, 1 / 8., args)
+        self.vfa16 = VFA(channel, grid_height, cube_size, 1 / 16., args)
+        self.vfa32 = VFA(channel, grid_height, cube_size, 1 / 32., args)
+        self.flags = int(flags)
+
+    def forward(self, feats, calibs, grid, crange=(-1.0, 0.95), channels_last: bool | None = None):
+        vfas = (self.vfa8, self.vfa16, self.vfa32)[:len(feats)]
+        if len(feats) != 3:
+            raise ValueError('MultiScaleVFA aggregates the three FPN scales (stride 8, 16, 32) of the reference network')
+        L, W = grid.shape[-3], grid.shape[-2]
+        table = build_table(vfas[0].geometry((L, W), crange), calibs.reshape(-1, 3, 4), grid)
+        return aggregate(list(feats), table, [m.collapse.weight for m in vfas], [m.collapse.bias for m in vfas],
+                         flags=self.flags, channels_last=channels_last)
