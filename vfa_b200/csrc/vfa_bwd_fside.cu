@@ -25,7 +25,10 @@ namespace vfa {
 // vfa_fwd_umma.cu / vfa_fwd_fside.cu / vfa_bwd.cu / vfa_table.cu
 int launch_taps_table(const AggParams& p, TapRec* recs, cudaStream_t st);
 int launch_ygemm_accum(const float* const* a_rows, float* const* out, const uint8_t* const* wprep_t, const int* rows,
-                       int nl, int S, cudaStream_t st);
+                       int nl, int S, const uint8_t* need, cudaStream_t st);
+size_t fside_cover_bytes(const AggParams& p, int frames);
+int launch_cover_mark(const AggParams& p, const TapRec* recs, void* cover_ws, cudaStream_t st);
+int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8_t** need_out, cudaStream_t st);
 int fs_sgemm_nt_acc(cudaStream_t st, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc);
 int launch_unprep_dweight(const float* dwr, float* dw, int C, int nl, cudaStream_t st);
 int launch_transpose(const float*, float*, long long, int, long long, cudaStream_t);
@@ -420,6 +423,8 @@ struct Args {
   float* dwr[VFA_MAX_SCALES];          // [nl*256][256], zeroed / accumulated by the caller
   int T[VFA_MAX_SCALES];               // texel rows of the chunk
   int kb_begin[VFA_MAX_SCALES + 1];    // K blocks (256 texels) of scale s: [kb_begin[s], kb_begin[s+1]) of the concatenated list
+  int need_tile0[VFA_MAX_SCALES];      // first 256-row tile of scale s in the need bytes (launch_tile_need)
+  const uint8_t* need;                 // [tile][layer]: 0 = Gs of that (tile, layer) is all zero -> the K block is skipped
   int nl, S, n_kb;
 };
 
@@ -433,6 +438,11 @@ __device__ __forceinline__ Unit decode_unit(const Args& a, int u) {
   r.s = (a.S > 2 && u >= a.kb_begin[2]) ? 2 : ((a.S > 1 && u >= a.kb_begin[1]) ? 1 : 0);
   r.kb = u - (r.s == 0 ? 0 : (r.s == 1 ? a.kb_begin[1] : a.kb_begin[2]));
   return r;
+}
+__device__ __forceinline__ bool unit_needed(const Args& a, int u, int mt) {
+  const Unit r = decode_unit(a, u);
+  const int t0 = r.s == 0 ? a.need_tile0[0] : (r.s == 1 ? a.need_tile0[1] : a.need_tile0[2]);
+  return __ldg(a.need + (size_t)(t0 + r.kb) * a.nl + mt) != 0;
 }
 
 __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint32_t off, const float4& v) {
@@ -487,16 +497,19 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
   if (warp == 1) {
     if (lane == 0 && cta_rank != 0) {
       int it = 0;
-      for (int u = u_begin; u < u_end; ++u)
+      for (int u = u_begin; u < u_end; ++u) {
+        if (!unit_needed(a, u, mt)) continue;
         for (int k = 0; k < STAGES_PER_BLOCK; ++k, ++it) {
           const int st = it % STAGES;
           mbar_wait(&tail->full[st], (it / STAGES) & 1);
           mbar_arrive_remote(&tail->peer_full[st], 0);
         }
+      }
     } else if (lane == 0) {
       // ================= MMA issuer (pair leader) =================
       int it = 0, blk = 0;
-      for (int u = u_begin; u < u_end; ++u, ++blk) {
+      for (int u = u_begin; u < u_end; ++u) {
+        if (!unit_needed(a, u, mt)) continue;
         mbar_wait_cluster(&tail->acc_empty, (blk & 1) ^ 1);
         tc_fence_after();
         for (int k = 0; k < STAGES_PER_BLOCK; ++k, ++it) {
@@ -518,6 +531,7 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
           tc_commit_t<true>(&tail->empty[st]);
         }
         tc_commit_t<true>(&tail->acc_full);
+        ++blk;
       }
     }
   } else if (warp >= FIRST_PRODUCER_WARP && warp < FIRST_EPILOGUE_WARP) {
@@ -547,33 +561,47 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
         }
       }
     };
-    if (u_begin < u_end) load_stage(u_begin, 0, ca, cbv);
-    int it = 0;
-    for (int u = u_begin; u < u_end; ++u) {
-      for (int k = 0; k < STAGES_PER_BLOCK; ++k, ++it) {
-        const int st = it % STAGES;
-        int nu = u, nk = k + 1;
-        if (nk == STAGES_PER_BLOCK) {
-          nk = 0;
-          ++nu;
+    // cursor over the stages of the NEEDED K blocks of this cluster
+    auto advance = [&](int& u, int& k) -> bool {
+      ++k;
+      while (true) {
+        if (k >= STAGES_PER_BLOCK) {
+          ++u;
+          k = 0;
         }
-        if (nu < u_end) load_stage(nu, nk, na, nb);
-        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
-        uint8_t* base = smem + (size_t)st * STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          store_split(base, off[i], ca[i]);
-          store_split(base + 2 * OP_BYTES, off[i], cbv[i]);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->full[st]);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          ca[i] = na[i];
-          cbv[i] = nb[i];
-        }
+        if (u >= u_end) return false;
+        if (k != 0 || unit_needed(a, u, mt)) return true;
+        k = STAGES_PER_BLOCK;                             // Gs is all zero here: skip the block
       }
+    };
+    int u = u_begin, k = -1;
+    bool have = u_begin < u_end && advance(u, k);
+    if (have) load_stage(u, k, ca, cbv);
+    int it = 0;
+    while (have) {
+      const int st = it % STAGES;
+      int nu = u, nk = k;
+      const bool more = advance(nu, nk);
+      if (more) load_stage(nu, nk, na, nb);
+      mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+      uint8_t* base = smem + (size_t)st * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        store_split(base, off[i], ca[i]);
+        store_split(base + 2 * OP_BYTES, off[i], cbv[i]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->full[st]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        ca[i] = na[i];
+        cbv[i] = nb[i];
+      }
+      u = nu;
+      k = nk;
+      have = more;
+      ++it;
     }
   } else if (warp >= FIRST_EPILOGUE_WARP) {
     // ================= epilogue: per-K-block drain into the fp32 running sum, split-K flush =================
@@ -581,10 +609,29 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
     const int quarter = warp & 3;
     const int col_begin = (e >> 2) * (CH / 2);
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    int blk = 0;
-    bool first = true;                                    // first K block of the current (scale, M tile) segment
-    for (int u = u_begin; u < u_end; ++u, ++blk) {
+    int blk = 0, cur_s = 0;
+    bool first = true;                                    // the running sum holds nothing yet
+    auto flush = [&](int s_of) {                          // running sum -> dWr of scale s_of (split-K: vector atomics)
+      float* dwr = s_of == 0 ? a.dwr[0] : (s_of == 1 ? a.dwr[1] : a.dwr[2]);
+      float* dst = dwr + (size_t)(mt * (2 * TILE_M) + (int)cta_rank * TILE_M + quarter * 32 + lane) * CH;
+#pragma unroll 1
+      for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
+        float v[32];
+        tc_ld32(lane_addr + CH + c0, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + c0 + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      }
+    };
+    for (int u = u_begin; u < u_end; ++u) {
+      if (!unit_needed(a, u, mt)) continue;
       const Unit w = decode_unit(a, u);
+      if (!first && w.s != cur_s) {                       // the K range moves on to another scale
+        flush(cur_s);
+        first = true;
+      }
+      cur_s = w.s;
       mbar_wait_sleep(&tail->acc_full, blk & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -607,27 +654,9 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
         else mbar_arrive(&tail->acc_empty);
       }
       first = false;
-      // leave the segment?  (the next K block belongs to another scale, or this was the cluster's last one)
-      bool flush = u + 1 == u_end;
-      if (!flush) {
-        const Unit nxt = decode_unit(a, u + 1);
-        flush = nxt.s != w.s;
-      }
-      if (flush) {
-        float* dwr = w.s == 0 ? a.dwr[0] : (w.s == 1 ? a.dwr[1] : a.dwr[2]);
-        float* dst = dwr + (size_t)(mt * (2 * TILE_M) + (int)cta_rank * TILE_M + quarter * 32 + lane) * CH;
-#pragma unroll 1
-        for (int c0 = col_begin; c0 < col_begin + CH / 2; c0 += 32) {
-          float v[32];
-          tc_ld32(lane_addr + CH + c0, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            atomicAdd(reinterpret_cast<float4*>(dst + c0 + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-        }
-        first = true;
-      }
+      ++blk;
     }
+    if (!first) flush(cur_s);
   }
 
   tc_fence_before();
@@ -640,7 +669,7 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
 
 // dwr_s[nl*256][256] += Gs_s^T F_s for the S scales of one frame chunk (one persistent launch)
 static int launch_dweight(const float* const* gs, const float* const* f, float* const* dwr, const int* T, int nl, int S,
-                          cudaStream_t st) {
+                          const uint8_t* need, cudaStream_t st) {
   using namespace dwg;
   static bool attr_set = false;
   if (!attr_set) {
@@ -651,8 +680,12 @@ static int launch_dweight(const float* const* gs, const float* const* f, float* 
   a.nl = nl;
   a.S = S;
   a.kb_begin[0] = 0;
+  a.need = need;
+  int tile0 = 0;
   for (int s = 0; s < VFA_MAX_SCALES; ++s) {
     const int ss = s < S ? s : 0;
+    a.need_tile0[s] = tile0;                               // the need bytes cover every scale's tiles (launch_tile_need)
+    if (s < S) tile0 += (T[s] + STAGES_PER_BLOCK * KST - 1) / (STAGES_PER_BLOCK * KST);
     a.gs[s] = gs[ss];
     a.f[s] = f[ss];
     a.dwr[s] = dwr[ss];
@@ -700,11 +733,11 @@ struct Plan {
   size_t px;                 // texels of one view over all scales
   int rows;                  // CSR rows
   int capacity;
-  size_t off_wprep, off_dwr, off_recs, off_counts, off_offsets, off_bsums, off_entries, off_chunk;
+  size_t off_wprep, off_dwr, off_recs, off_counts, off_offsets, off_bsums, off_entries, off_cover, off_chunk;
   size_t per_frame;          // bytes of (gT + gm + Gs) for one frame
 };
 
-static Plan make_plan(int V, int S, int nl, size_t LW, const int* fh, const int* fw) {
+static Plan make_plan(int B, int V, int S, int nl, size_t LW, const int* fh, const int* fw) {
   Plan pl;
   pl.px = 0;
   for (int s = 0; s < S; ++s) pl.px += (size_t)fh[s] * fw[s];
@@ -725,6 +758,19 @@ static Plan make_plan(int V, int S, int nl, size_t LW, const int* fh, const int*
   pl.off_offsets = o; o += align256(((size_t)pl.rows + 1) * sizeof(int));
   pl.off_bsums = o;   o += align256(((size_t)pl.rows / 1024 + 2) * sizeof(int));
   pl.off_entries = o; o += align256((size_t)pl.capacity * sizeof(CsrEntry));
+  {
+    AggParams q;                                           // coverage bitmap + per-tile need bytes (vfa_fwd_fside.cu)
+    q.B = B;
+    q.V = V;
+    q.S = S;
+    q.nl = nl;
+    for (int s = 0; s < S; ++s) {
+      q.sc[s].fh = fh[s];
+      q.sc[s].fw = fw[s];
+    }
+    pl.off_cover = o;
+    o += align256(fside_cover_bytes(q, B));
+  }
   pl.off_chunk = o;
   pl.per_frame = (LW * CH + (size_t)V * S * LW * CH + (size_t)V * pl.px * nl * CH) * sizeof(float);
   return pl;
@@ -745,7 +791,8 @@ static int chunk_frames(const Plan& pl, int B) {
 }  // namespace bfs
 
 size_t bwd_fside_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh) {
-  const bfs::Plan pl = bfs::make_plan(sh->n_views, sh->n_scales, g->n_layers, (size_t)g->grid_l * g->grid_w, sh->feat_h, sh->feat_w);
+  const bfs::Plan pl = bfs::make_plan(sh->batch, sh->n_views, sh->n_scales, g->n_layers, (size_t)g->grid_l * g->grid_w, sh->feat_h,
+                                      sh->feat_w);
   return pl.off_chunk + (size_t)bfs::chunk_frames(pl, sh->batch) * pl.per_frame + 256;
 }
 
@@ -757,7 +804,7 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
     fh[s] = p.sc[s].fh;
     fwv[s] = p.sc[s].fw;
   }
-  const Plan pl = make_plan(p.V, p.S, p.nl, (size_t)p.LW, fh, fwv);
+  const Plan pl = make_plan(p.B, p.V, p.S, p.nl, (size_t)p.LW, fh, fwv);
   int cb = chunk_frames(pl, p.B);
   if (ws_bytes < pl.off_chunk + pl.per_frame) {
     set_error("backward workspace %zu < required %zu", ws_bytes, pl.off_chunk + pl.per_frame);
@@ -795,6 +842,8 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
 
   // ---- the box -> texel relation, inverted once per call ----
   if (int rc = launch_taps_table(p, recs, st)) return rc;
+  void* cover_ws = w8 + pl.off_cover;
+  if (int rc = launch_cover_mark(p, recs, cover_ws, st)) return rc;
   RowMap rm;
   int base = 0;
   for (int s = 0; s < VFA_MAX_SCALES; ++s) {
@@ -874,11 +923,10 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
       overflow_scatter_kernel<<<148 * 8, 256, 0, st>>>(q, recs, nb);
       VFA_LAUNCH_CHECK("overflow_scatter_kernel");
     }
+    const uint8_t* need = nullptr;                   // (256-row tile, layer) pairs whose Gs is not all zero
+    if (int rc = launch_tile_need(p, cover_ws, nb, &need, st)) return rc;
     if (any_f) {
-      // scales whose dFeature is not wanted get zero rows
-      for (int s = 0; s < p.S; ++s)
-        if (outs[s] == nullptr) rows[s] = 0;
-      if (int rc = launch_ygemm_accum(a_rows, outs, wts, rows, p.nl, p.S, st)) return rc;
+      if (int rc = launch_ygemm_accum(a_rows, outs, wts, rows, p.nl, p.S, need, st)) return rc;
     }
     if (any_w && getenv("VFA_BWD_CUBLAS_DW") == nullptr) {
       const float* gsp[VFA_MAX_SCALES];
@@ -892,7 +940,7 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
         dwp[s] = d_grad_weight[ss] != nullptr ? dwr + ss * per_scale : nullptr;
         Ts[s] = nb * p.V * rm.hw[ss];
       }
-      if (int rc = launch_dweight(gsp, fp, dwp, Ts, p.nl, p.S, st)) return rc;
+      if (int rc = launch_dweight(gsp, fp, dwp, Ts, p.nl, p.S, need, st)) return rc;
     } else if (any_w) {
       for (int s = 0; s < p.S; ++s) {
         if (d_grad_weight[s] == nullptr) continue;

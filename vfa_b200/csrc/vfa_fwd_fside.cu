@@ -80,6 +80,9 @@ struct YGemmArgs {
   int tile_begin[VFA_MAX_SCALES + 1];     // cluster tiles (256 rows) of scale s: [tile_begin[s], tile_begin[s+1])
   int nl, S;
   int n_tiles;                            // tile_begin[S]
+  int need_tile0[VFA_MAX_SCALES];         // first tile of scale s inside `need` (== tile_begin[s] unless a scale has no rows here)
+  const uint8_t* need;                    // [tile][layer] (tiles of all scales concatenated): 0 = no box of that layer touches
+                                          // the tile's texels, the product is never pooled -> the whole (tile, layer) is skipped
 };
 
 __device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const float4& v) {
@@ -121,6 +124,7 @@ struct TileInfo {
   int s, row0, rows, hw;
   const uint8_t* feats;
   const uint8_t* wprep;
+  const uint8_t* need;     // need bytes of this tile: [layer]
   float* y;
 };
 __device__ __forceinline__ TileInfo tile_info(const YGemmArgs& a, int ctile, uint32_t cta_rank) {
@@ -128,6 +132,7 @@ __device__ __forceinline__ TileInfo tile_info(const YGemmArgs& a, int ctile, uin
   t.s = (a.S > 2 && ctile >= a.tile_begin[2]) ? 2 : ((a.S > 1 && ctile >= a.tile_begin[1]) ? 1 : 0);
   const int tile0 = t.s == 0 ? 0 : (t.s == 1 ? a.tile_begin[1] : a.tile_begin[2]);
   t.row0 = (ctile - tile0) * (2 * TILE_M) + (int)cta_rank * TILE_M;      // first texel row of this CTA
+  t.need = a.need + (size_t)(pick(a.need_tile0, t.s) + ctile - tile0) * a.nl;
   t.rows = pick(a.rows, t.s);
   t.hw = pick(a.hw, t.s);
   t.feats = pick(a.feats, t.s);
@@ -179,7 +184,8 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
       int it = 0;
       for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
         const TileInfo t = tile_info(a, ctile, cta_rank);
-        for (int k = 0; k < total; ++k, ++it) {
+        for (int k = 0; k < total; ++k) {
+          if (!__ldg(t.need + k / CHUNKS)) continue;
           const int st = it % STAGES;
           mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
           uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
@@ -187,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
           const uint8_t* src = t.wprep + (size_t)k * (2 * B_BYTES);      // kc = n * CHUNKS + cc == k
           bulk_g2s(dst, src + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
           bulk_g2s(dst + B_LOCAL_BYTES, src + B_BYTES + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+          ++it;
         }
       }
     }
@@ -194,17 +201,23 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
     if (lane == 0 && cta_rank != 0) {
       // pair follower: relays "my stage is full" to the leader
       int it = 0;
-      for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters)
-        for (int k = 0; k < total; ++k, ++it) {
+      for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
+        const TileInfo t = tile_info(a, ctile, cta_rank);
+        for (int k = 0; k < total; ++k) {
+          if (!__ldg(t.need + k / CHUNKS)) continue;
           const int st = it % STAGES;
           mbar_wait(&tail->full[st], (it / STAGES) & 1);
           mbar_arrive_remote(&tail->peer_full[st], 0);
+          ++it;
         }
+      }
     } else if (lane == 0) {
       // ================= MMA issuer (pair leader) =================
       int it = 0, ln = 0;                               // running stage / layer counters
       for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
-        for (int n = 0; n < a.nl; ++n, ++ln) {
+        const TileInfo t = tile_info(a, ctile, cta_rank);
+        for (int n = 0; n < a.nl; ++n) {
+          if (!__ldg(t.need + n)) continue;
           const int slot = ln & 1;
           mbar_wait_cluster(&tail->acc_empty[slot], ((ln >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -227,6 +240,7 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
             tc_commit_t<true>(&tail->empty[st]);
           }
           tc_commit_t<true>(&tail->acc_full[slot]);
+          ++ln;
         }
       }
     }
@@ -250,39 +264,56 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) off[i] = swz((uint32_t)(32 * i + 4 * pw + (lane >> 3)), (uint32_t)j);
     float4 cur[ITEMS], nxt[ITEMS];
-    if (cluster < n_tiles) bind_tile(cluster);
+    // cursor over the NEEDED stages of this cluster's tiles: (tile, k), k = layer * CHUNKS + K chunk
+    auto advance = [&](int& ct, int& k) -> bool {
+      ++k;
+      while (true) {
+        if (k >= total) {
+          ct += n_clusters;
+          k = 0;
+          if (ct >= n_tiles) return false;
+        }
+        if (k % CHUNKS != 0 || __ldg(tile_info(a, ct, cta_rank).need + k / CHUNKS)) return true;
+        k += CHUNKS;                                   // nothing pools from this (tile, layer): skip its 8 stages
+      }
+    };
+    auto load_stage = [&](float4(&v)[ITEMS], int k) {
+      const int cc = MODE == 0 ? k % CHUNKS : k;       // K chunk inside an A row
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      cur[i] = (cluster < n_tiles && ok[i]) ? load_feat4<BF16>(src[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < ITEMS; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[i]) v[i] = load_feat4<BF16>(src[i] + (size_t)cc * KCH * ES);
+      }
+    };
+    int ct = cluster, k = -1;
+    bool have = ct < n_tiles && advance(ct, k);
+    if (have) {
+      bind_tile(ct);
+      load_stage(cur, k);
     }
     int it = 0;
-    for (int ctile = cluster; ctile < n_tiles; ctile += n_clusters) {
-      for (int k = 0; k < total; ++k, ++it) {
-        const int st = it % STAGES;
-        // loads of the next stage (possibly the first stage of the next tile) fly while this one is stored
-        int cc = MODE == 0 ? (k + 1) % CHUNKS : k + 1;       // K chunk of the next stage inside an A row
-        bool more = true;
-        if (k + 1 == total) {
-          more = ctile + n_clusters < n_tiles;
-          if (more) bind_tile(ctile + n_clusters);
-          cc = 0;
-        }
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-          nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (more && ok[i]) nxt[i] = load_feat4<BF16>(src[i] + (size_t)cc * KCH * ES);
-        }
-        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
-        uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) store_split(a_hi, off[i], cur[i]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->full[st]);
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
+    while (have) {
+      const int st = it % STAGES;
+      // loads of the next needed stage (possibly in the next tile) fly while this one is stored
+      int nct = ct, nk = k;
+      const bool more = advance(nct, nk);
+      if (more) {
+        if (nct != ct) bind_tile(nct);
+        load_stage(nxt, nk);
       }
+      mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+      uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) store_split(a_hi, off[i], cur[i]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->full[st]);
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
+      ct = nct;
+      k = nk;
+      have = more;
+      ++it;
     }
   } else if (warp >= FIRST_EPILOGUE_WARP) {
     // ================= epilogue: accumulator of layer n -> Y[plane][n][texel][:] =================
@@ -307,7 +338,9 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
         else
           yrow[rr] = r < t.rows ? (uint32_t)r : 0xffffffffu;
       }
-      for (int n = 0; n < a.nl; ++n, ++ln) {
+      bool first = true;                              // MODE 1: no layer of this tile has been written yet
+      for (int n = 0; n < a.nl; ++n) {
+        if (!__ldg(t.need + n)) continue;
         const int slot = ln & 1;
         mbar_wait_sleep(&tail->acc_full[slot], (ln >> 1) & 1);
         tc_fence_after();
@@ -329,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
             float4 q = *reinterpret_cast<const float4*>(patch + prow * 128 + ((chunk ^ (prow & 7)) << 4));
             if (yrow[rr] != 0xffffffffu) {
               float4* o4 = reinterpret_cast<float4*>(dst + (size_t)yrow[rr] * CH + c0);
-              if (MODE == 1 && n > 0) {               // layer partials summed in fp32 (this thread owns the element)
+              if (MODE == 1 && !first) {              // layer partials summed in fp32 (this thread owns the element)
                 const float4 prev = *o4;
                 q.x += prev.x; q.y += prev.y; q.z += prev.z; q.w += prev.w;
               }
@@ -343,6 +376,17 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_kernel(const YGemmArgs a) {
           if (cta_rank != 0) mbar_arrive_remote(&tail->acc_empty[slot], 0);
           else mbar_arrive(&tail->acc_empty[slot]);
         }
+        first = false;
+        ++ln;
+      }
+      if (MODE == 1 && first) {                       // no layer touches these rows: the sum over layers is zero
+        float* dst = t.y + col_begin + chunk * 4;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CH / 2; c0 += 32)
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr)
+            if (yrow[rr] != 0xffffffffu)
+              *reinterpret_cast<float4*>(dst + (size_t)yrow[rr] * CH + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
@@ -645,6 +689,130 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
 
 using namespace fside;
 
+
+// ---- which (texel tile, layer) products are ever pooled ------------------------------------------------------------
+// A camera looking at the field sees the voxel grid in part of its image only (sky, ground beyond the grid), and every
+// height layer projects to a different band: on the three rigs 54 % / 42 % / 25 % of the (texel, layer) products are
+// pooled by some visible box, 68 % / 64 % / 44 % of the (256-texel tile, layer) pairs.  The tap records give a bitmap of
+// covered texels per (scale, view, layer) plane; from it one byte per (tile, layer) tells ygemm_kernel (and the backward's
+// dFeature / dWeight products) which tiles to skip altogether.  Zero-weight taps are marked too (superset of what the
+// pooling kernels fetch).
+struct CoverMap {
+  int word_base[VFA_MAX_SCALES];     // first 32-bit word of scale s; planes (v * nl + n) follow each other, `words` apart
+  int words[VFA_MAX_SCALES];         // ceil(hw / 32)
+  int hw[VFA_MAX_SCALES], fw[VFA_MAX_SCALES];
+  int total_words;
+};
+
+static CoverMap make_cover_map(const AggParams& p) {
+  CoverMap cm;
+  int base = 0;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+    const int ss = s < p.S ? s : 0;
+    cm.hw[s] = p.sc[ss].fh * p.sc[ss].fw;
+    cm.fw[s] = p.sc[ss].fw;
+    cm.words[s] = (cm.hw[s] + 31) / 32;
+    cm.word_base[s] = base;
+    if (s < p.S) base += p.V * p.nl * cm.words[s];
+  }
+  cm.total_words = base;
+  return cm;
+}
+
+__global__ void __launch_bounds__(256) cover_mark_kernel(AggParams p, const TapRec* __restrict__ recs, CoverMap cm,
+                                                         uint32_t* __restrict__ bits) {
+  const long long total = (long long)p.V * p.S * p.nl * p.LW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const TapRec r = recs[idx];
+    const int nx = r.nxy & 0xffff, ny = r.nxy >> 16;
+    if (nx == 0) continue;
+    const int n = (int)((idx / p.LW) % p.nl);
+    const int s = (int)((idx / ((long long)p.LW * p.nl)) % p.S);
+    const int v = (int)(idx / ((long long)p.LW * p.nl * p.S));
+    const int fw = s == 0 ? cm.fw[0] : (s == 1 ? cm.fw[1] : cm.fw[2]);
+    const int words = s == 0 ? cm.words[0] : (s == 1 ? cm.words[1] : cm.words[2]);
+    const int wbase = s == 0 ? cm.word_base[0] : (s == 1 ? cm.word_base[1] : cm.word_base[2]);
+    uint32_t* plane = bits + wbase + (size_t)(v * p.nl + n) * words;
+    for (int ty = 0; ty < ny; ++ty) {
+      const int t0 = ((r.xy >> 16) + ty) * fw + (r.xy & 0xffff), t1 = t0 + nx - 1;      // inclusive texel range of the row
+      for (int w = t0 >> 5; w <= t1 >> 5; ++w) {
+        const int lo = max(t0, w << 5) & 31, hi = min(t1, (w << 5) + 31) & 31;
+        const uint32_t m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        if ((plane[w] & m) != m) atomicOr(plane + w, m);
+      }
+    }
+  }
+}
+
+struct NeedArgs {
+  CoverMap cm;
+  int rows[VFA_MAX_SCALES];
+  int tile_begin[VFA_MAX_SCALES + 1];
+  int V, nl, S;
+};
+
+// need[tile * nl + n] = any texel row of the 256-row tile (rows = chunk-relative plane * hw + texel) is covered in layer n
+__global__ void __launch_bounds__(256) tile_need_kernel(NeedArgs q, const uint32_t* __restrict__ bits, uint8_t* __restrict__ need) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_tiles = q.S == 1 ? q.tile_begin[1] : (q.S == 2 ? q.tile_begin[2] : q.tile_begin[3]);   // no dynamic indexing
+  if (idx >= n_tiles * q.nl) return;
+  const int tile = idx / q.nl, n = idx % q.nl;
+  const int s = (q.S > 2 && tile >= q.tile_begin[2]) ? 2 : ((q.S > 1 && tile >= q.tile_begin[1]) ? 1 : 0);
+  const int tb = s == 0 ? 0 : (s == 1 ? q.tile_begin[1] : q.tile_begin[2]);
+  const int rows = s == 0 ? q.rows[0] : (s == 1 ? q.rows[1] : q.rows[2]);
+  const int hw = s == 0 ? q.cm.hw[0] : (s == 1 ? q.cm.hw[1] : q.cm.hw[2]);
+  const int words = s == 0 ? q.cm.words[0] : (s == 1 ? q.cm.words[1] : q.cm.words[2]);
+  const int wbase = s == 0 ? q.cm.word_base[0] : (s == 1 ? q.cm.word_base[1] : q.cm.word_base[2]);
+  const int r0 = (tile - tb) * (2 * TILE_M), r1 = min(rows, r0 + 2 * TILE_M);
+  uint32_t any = 0;
+  for (int r = r0; r < r1 && !any; ++r) {
+    const int v = (r / hw) % q.V, t = r % hw;
+    any = (__ldg(bits + wbase + (size_t)(v * q.nl + n) * words + (t >> 5)) >> (t & 31)) & 1u;
+  }
+  need[idx] = (uint8_t)any;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// bytes for the bitmap + the need bytes of a chunk of `frames` frames
+size_t fside_cover_bytes(const AggParams& p, int frames) {
+  const CoverMap cm = make_cover_map(p);
+  size_t tiles = 0;
+  for (int s = 0; s < p.S; ++s) tiles += ((size_t)frames * p.V * cm.hw[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+  return align256((size_t)cm.total_words * sizeof(uint32_t)) + align256(tiles * p.nl);
+}
+
+// bitmap of covered texels from the tap records (once per call)
+int launch_cover_mark(const AggParams& p, const TapRec* recs, void* cover_ws, cudaStream_t st) {
+  const CoverMap cm = make_cover_map(p);
+  VFA_CUDA(cudaMemsetAsync(cover_ws, 0, (size_t)cm.total_words * sizeof(uint32_t), st));
+  cover_mark_kernel<<<148 * 8, 256, 0, st>>>(p, recs, cm, reinterpret_cast<uint32_t*>(cover_ws));
+  VFA_LAUNCH_CHECK("cover_mark_kernel");
+  return VFA_OK;
+}
+
+// need bytes of the 256-row tiles of a chunk of `frames` frames (tiles of the scales concatenated); returns the pointer
+int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8_t** need_out, cudaStream_t st) {
+  NeedArgs q;
+  q.cm = make_cover_map(p);
+  q.V = p.V;
+  q.nl = p.nl;
+  q.S = p.S;
+  q.tile_begin[0] = 0;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+    q.rows[s] = frames * p.V * q.cm.hw[s];
+    if (s < p.S) q.tile_begin[s + 1] = q.tile_begin[s] + (q.rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+    else if (s + 1 <= VFA_MAX_SCALES) q.tile_begin[s + 1] = q.tile_begin[s];
+  }
+  uint8_t* need = reinterpret_cast<uint8_t*>(cover_ws) + align256((size_t)q.cm.total_words * sizeof(uint32_t));
+  const int total = q.tile_begin[p.S] * p.nl;
+  tile_need_kernel<<<(total + 255) / 256, 256, 0, st>>>(q, reinterpret_cast<const uint32_t*>(cover_ws), need);
+  VFA_LAUNCH_CHECK("tile_need_kernel");
+  *need_out = need;
+  return VFA_OK;
+}
+
 // One persistent launch over all cluster tiles of `g` (tile_begin must be filled for g.S scales).
 static int launch_ygemm(YGemmArgs& g, int mode, bool bf16, cudaStream_t st) {
   static bool attr_set = false;
@@ -690,20 +858,27 @@ static int launch_ygemm(YGemmArgs& g, int mode, bool bf16, cudaStream_t st) {
 
 // out_s[rows_s, 256] = sum over the nl*256 columns of a_s[rows_s, nl*256] against the TRANSPOSED prepared weights
 // (prep_weight_umma_T_kernel): the dFeature product of the backward.  3xTF32, layer partials added in fp32.
+// `rows` = texel rows per scale (the tiling the need bytes were built for); scales with out[s] == nullptr are skipped.
 int launch_ygemm_accum(const float* const* a_rows, float* const* out, const uint8_t* const* wprep_t, const int* rows,
-                       int nl, int S, cudaStream_t st) {
+                       int nl, int S, const uint8_t* need, cudaStream_t st) {
   YGemmArgs g;
   g.nl = nl;
   g.S = S;
+  g.need = need;
   g.tile_begin[0] = 0;
+  int tile0 = 0;
   for (int s = 0; s < VFA_MAX_SCALES; ++s) {
     const int ss = s < S ? s : 0;
     g.feats[s] = reinterpret_cast<const uint8_t*>(a_rows[ss]);
     g.y[s] = out[ss];
     g.wprep[s] = wprep_t[ss];
-    g.rows[s] = rows[ss];
+    g.rows[s] = out[ss] != nullptr ? rows[ss] : 0;
     g.hw[s] = 1;
-    if (s < S) g.tile_begin[s + 1] = g.tile_begin[s] + (rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+    g.need_tile0[s] = tile0;
+    if (s < S) {
+      tile0 += (rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+      g.tile_begin[s + 1] = g.tile_begin[s] + (g.rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+    }
   }
   return launch_ygemm(g, 1, false, st);
 }
@@ -729,7 +904,13 @@ int fside_chunk_frames(const AggParams& p) {
   return (int)cb;
 }
 
-int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, float* y_ws, size_t y_bytes,
+// workspace of the feature-side forward behind the prepared weights and tap records: [cover bitmap + need bytes][Y]
+size_t fside_workspace_bytes(const AggParams& p) {
+  const int cb = fside_chunk_frames(p);
+  return fside_cover_bytes(p, cb) + (size_t)cb * fside_y_bytes_per_frame(p);
+}
+
+int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
                      bool bf16, int variant, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -744,11 +925,14 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
   }
   const size_t per_frame = fside_y_bytes_per_frame(p);
   int cb = fside_chunk_frames(p);
-  if ((size_t)cb * per_frame > y_bytes) cb = (int)(y_bytes / per_frame);
-  if (cb < 1) {
-    set_error("feature-side forward: workspace holds %zu bytes for Y, one frame needs %zu", y_bytes, per_frame);
+  while (cb > 1 && fside_cover_bytes(p, cb) + (size_t)cb * per_frame > fs_bytes) --cb;
+  const size_t cover_bytes = fside_cover_bytes(p, cb);
+  if (cover_bytes + per_frame > fs_bytes) {
+    set_error("feature-side forward: workspace holds %zu bytes for Y, one frame needs %zu", fs_bytes, cover_bytes + per_frame);
     return VFA_ERR_WORKSPACE;
   }
+  float* y_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fs_ws) + cover_bytes);
+  if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
   const size_t es = bf16 ? 2 : 4;
   for (int b0 = 0; b0 < p.B; b0 += cb) {
     const int nb = p.B - b0 < cb ? p.B - b0 : cb;
@@ -771,12 +955,14 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       g.wprep[s] = wprep[ss];
       g.y[s] = y_ws + (s < p.S ? y_off : 0);
       q.y[s] = g.y[s];
+      g.need_tile0[s] = g.tile_begin[s < p.S ? s : 0];
       if (s < p.S) {
         y_off += (size_t)cb * p.V * p.nl * hw * CH;
         g.tile_begin[s + 1] = g.tile_begin[s] + (g.rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
       }
     }
     if (!(variant & 128)) {
+      if (int rc = launch_tile_need(p, fs_ws, nb, &g.need, st)) return rc;
       if (int rc = launch_ygemm(g, 0, bf16, st)) return rc;
     }
     if (!(variant & 64)) {

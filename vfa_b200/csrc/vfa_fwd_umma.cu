@@ -810,7 +810,8 @@ bool umma_supported(const vfa_geometry_t* g, const vfa_shape_t* sh, uint32_t fla
 // feature-side forward (vfa_fwd_fside.cu)
 size_t fside_y_bytes_per_frame(const AggParams& p);
 int fside_chunk_frames(const AggParams& p);
-int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, float* y_ws, size_t y_bytes,
+size_t fside_workspace_bytes(const AggParams& p);
+int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
                      bool bf16, int variant, cudaStream_t st);
 
 static bool grid_side_requested(uint32_t flags) {
@@ -837,7 +838,7 @@ size_t umma_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh, uint
       p.sc[s].fh = sh->feat_h[s];
       p.sc[s].fw = sh->feat_w[s];
     }
-    bytes += (size_t)fside_chunk_frames(p) * fside_y_bytes_per_frame(p);
+    bytes += fside_workspace_bytes(p);
   }
   return bytes;
 }
@@ -885,7 +886,7 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, size_t 
       set_error("workspace %zu < required %zu", ws_bytes, fixed);
       return VFA_ERR_WORKSPACE;
     }
-    if (int rc = launch_fwd_fside(p, a.wprep, a.recs, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + fixed),
+    if (int rc = launch_fwd_fside(p, a.wprep, a.recs, reinterpret_cast<uint8_t*>(ws) + fixed,
                                   ws_bytes - fixed, bf16, a.variant, st))
       return rc;
     set_path(bf16 ? "fside_tf32x3_bf16feat" : "fside_tf32x3");
