@@ -269,6 +269,8 @@ struct GatherParams {
   int tile_begin[VFA_MAX_SCALES + 1];   // CTA tiles (4 x 4 texels of one (view, layer) plane) per scale, prefix
   int tiles_x[VFA_MAX_SCALES], tiles[VFA_MAX_SCALES];
   int capacity;
+  const uint8_t* need;              // [256-row tile][layer] (launch_tile_need): rows of tiles nobody reads are not written
+  int need_tile0[VFA_MAX_SCALES];
 };
 
 constexpr int GT = 4;                            // texel tile side: one warp per texel
@@ -309,6 +311,11 @@ __global__ void __launch_bounds__(GT * GT * 32, VFA_GATHER_MINBLOCKS) dy_gather_
   const int texel = ty * fw + tx;
   const int row = base + vn * hw + texel;
   const int e0 = __ldg(q.offsets + row), e1 = __ldg(q.offsets + row + 1);
+  if (e0 == e1) {       // an empty row inside a tile that neither GEMM of the backward reads: nothing to write
+    const int t0 = s == 0 ? q.need_tile0[0] : (s == 1 ? q.need_tile0[1] : q.need_tile0[2]);
+    const int tile256 = ((bl * p.V + v) * hw + texel) >> 8;
+    if (!__ldg(q.need + (size_t)(t0 + tile256) * p.nl + n)) return;
+  }
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -889,9 +896,19 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
       mask_grad_kernel<<<grid, MG_WARPS * 32, 0, st>>>(gq);
       VFA_LAUNCH_CHECK("mask_grad_kernel");
     }
+    const uint8_t* need = nullptr;                   // (256-row tile, layer) pairs whose Gs is not all zero
+    if (int rc = launch_tile_need(p, cover_ws, nb, &need, st)) return rc;
     GatherParams q;
     q.p = p;
     q.rm = rm;
+    q.need = need;
+    {
+      int t0 = 0;
+      for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+        q.need_tile0[s] = t0;
+        if (s < p.S) t0 += (nb * p.V * rm.hw[s] + 255) / 256;
+      }
+    }
     q.offsets = offsets;
     q.entries = entries;
     q.gm = gm;
@@ -923,8 +940,6 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
       overflow_scatter_kernel<<<148 * 8, 256, 0, st>>>(q, recs, nb);
       VFA_LAUNCH_CHECK("overflow_scatter_kernel");
     }
-    const uint8_t* need = nullptr;                   // (256-row tile, layer) pairs whose Gs is not all zero
-    if (int rc = launch_tile_need(p, cover_ws, nb, &need, st)) return rc;
     if (any_f) {
       if (int rc = launch_ygemm_accum(a_rows, outs, wts, rows, p.nl, p.S, need, st)) return rc;
     }
