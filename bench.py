@@ -280,7 +280,9 @@ def main():
         step()
     path = vfa_b200.last_kernel_path()
     # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | per frame chunk: ygemm + pool_quad}
-    launches_per_step = 5 + (2 * nums['fside_chunks'] if path.startswith('fside') else 1)
+    # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | coverage bitmap + per frame chunk: tile need
+    # bytes + ygemm + pool_quad}
+    launches_per_step = 5 + (1 + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -309,8 +311,11 @@ def main():
     if path.startswith('fside') and args.mode == 'dp' and not args.backward:
         table = vfa_b200.build_table(cgeom, calibs, grid)
         per_kernel = {}
-        for kname, bits in (('ygemm_kernel', 64 | 256), ('pool_quad_kernel', 128 | 256)):
+        for kname, bits in (('ygemm_kernel', 64 | 256), ('pool_quad_kernel', 128 | 256), ('ygemm_kernel_all_tiles', 64)):
             os.environ['VFA_UMMA_VARIANT'] = str(bits)
+            if kname == 'ygemm_kernel_all_tiles':        # every (tile, layer) multiplied: the GEMM's own efficiency
+                os.environ['VFA_FSIDE_NO_SKIP'] = '1'
+                table = vfa_b200.build_table(cgeom, calibs, grid)
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
             for i in range(-2, args.steps):
                 if i >= 0:
@@ -322,6 +327,7 @@ def main():
             torch.cuda.synchronize()
             per_kernel[kname] = sum(a.elapsed_time(b) for a, b in evs) / len(evs) / nums['fside_chunks']
         os.environ.pop('VFA_UMMA_VARIANT', None)
+        os.environ.pop('VFA_FSIDE_NO_SKIP', None)
         vfa_b200.aggregate_forward_raw(feats_cl, table, weights, biases, args.flags, out=out, workspace=ws, prepared=True)
         torch.cuda.synchronize()
 
@@ -394,7 +400,10 @@ def main():
             pool_bytes = (nums['y_bytes'] + nums['out_bytes']) / nums['fside_chunks'] + nums['rec_bytes']
             t_pool, t_gemm = per_kernel['pool_quad_kernel'], per_kernel['ygemm_kernel']
             pool_gbs = pool_bytes / (t_pool * 1e-3) / 1e9
-            gemm_tflops = nums['fside_flops'] / nums['fside_chunks'] / (t_gemm * 1e-3) / 1e12
+            # the GEMM skips the (256-row tile, layer) pairs no box pools; its tensor-core efficiency is quoted on the run
+            # that multiplies every tile (VFA_FSIDE_NO_SKIP=1; that run also carries the tap-record / coverage launches)
+            t_gemm_all = per_kernel['ygemm_kernel_all_tiles']
+            gemm_tflops = nums['fside_flops'] / nums['fside_chunks'] / (t_gemm_all * 1e-3) / 1e12
             step_bytes = nums['bytes'] + 2 * nums['y_bytes'] + nums['rec_bytes']
             roofline = {
                 'bound': 'hbm', 'achieved': pool_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
@@ -409,6 +418,7 @@ def main():
                 'second_kernel': {
                     'kernel': 'ygemm_kernel', 'bound': 'tensor', 'achieved': gemm_tflops, 'peak': peaks['tflops'],
                     'unit': 'TFLOP/s', 'frac': gemm_tflops / peaks['tflops'], 'kernel_ms': t_gemm,
+                    'kernel_ms_all_tiles': t_gemm_all, 'tiles_skipped_frac': max(0.0, 1.0 - t_gemm / t_gemm_all),
                     'kernel_share_of_step': t_gemm * nums['fside_chunks'] * args.steps / total_ms,
                     'traffic': traffic_of('ygemm_kernel'),
                     'algorithmic_flops_per_launch': nums['fside_flops'] / nums['fside_chunks'],

@@ -28,7 +28,7 @@ int launch_ygemm_accum(const float* const* a_rows, float* const* out, const uint
                        int nl, int S, const uint8_t* need, cudaStream_t st);
 size_t fside_cover_bytes(const AggParams& p, int frames);
 int launch_cover_mark(const AggParams& p, const TapRec* recs, void* cover_ws, cudaStream_t st);
-int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8_t** need_out, cudaStream_t st);
+int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8_t** need_out, cudaStream_t st, bool run);
 int fs_sgemm_nt_acc(cudaStream_t st, int m, int n, int k, const float* a, int lda, const float* b, int ldb, float* c, int ldc);
 int launch_unprep_dweight(const float* dwr, float* dw, int C, int nl, cudaStream_t st);
 int launch_transpose(const float*, float*, long long, int, long long, cudaStream_t);
@@ -897,7 +897,7 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
       VFA_LAUNCH_CHECK("mask_grad_kernel");
     }
     const uint8_t* need = nullptr;                   // (256-row tile, layer) pairs whose Gs is not all zero
-    if (int rc = launch_tile_need(p, cover_ws, nb, &need, st)) return rc;
+    if (int rc = launch_tile_need(p, cover_ws, nb, &need, st, true)) return rc;
     GatherParams q;
     q.p = p;
     q.rm = rm;

@@ -793,7 +793,9 @@ int launch_cover_mark(const AggParams& p, const TapRec* recs, void* cover_ws, cu
 }
 
 // need bytes of the 256-row tiles of a chunk of `frames` frames (tiles of the scales concatenated); returns the pointer
-int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8_t** need_out, cudaStream_t st) {
+// run = false: only return the pointer (the bytes of an earlier call with the same shapes are still in the workspace).
+// VFA_FSIDE_NO_SKIP=1 marks every tile as needed (measurement of the GEMMs without the skipping).
+int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8_t** need_out, cudaStream_t st, bool run) {
   NeedArgs q;
   q.cm = make_cover_map(p);
   q.V = p.V;
@@ -807,9 +809,15 @@ int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8
   }
   uint8_t* need = reinterpret_cast<uint8_t*>(cover_ws) + align256((size_t)q.cm.total_words * sizeof(uint32_t));
   const int total = q.tile_begin[p.S] * p.nl;
+  *need_out = need;
+  if (!run) return VFA_OK;
+  const char* e = getenv("VFA_FSIDE_NO_SKIP");
+  if (e != nullptr && atoi(e) != 0) {
+    VFA_CUDA(cudaMemsetAsync(need, 1, (size_t)total, st));
+    return VFA_OK;
+  }
   tile_need_kernel<<<(total + 255) / 256, 256, 0, st>>>(q, reinterpret_cast<const uint32_t*>(cover_ws), need);
   VFA_LAUNCH_CHECK("tile_need_kernel");
-  *need_out = need;
   return VFA_OK;
 }
 
@@ -932,7 +940,9 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     return VFA_ERR_WORKSPACE;
   }
   float* y_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fs_ws) + cover_bytes);
-  if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
+  if (!(variant & 256)) {       // (debug bit 256: reuse tap records, coverage bitmap and need bytes of the previous call)
+    if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
+  }
   const size_t es = bf16 ? 2 : 4;
   for (int b0 = 0; b0 < p.B; b0 += cb) {
     const int nb = p.B - b0 < cb ? p.B - b0 : cb;
@@ -962,7 +972,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       }
     }
     if (!(variant & 128)) {
-      if (int rc = launch_tile_need(p, fs_ws, nb, &g.need, st)) return rc;
+      if (int rc = launch_tile_need(p, fs_ws, nb, &g.need, st, !(variant & 256))) return rc;
       if (int rc = launch_ygemm(g, 0, bf16, st)) return rc;
     }
     if (!(variant & 64)) {
