@@ -776,12 +776,32 @@ __global__ void __launch_bounds__(256) tile_need_kernel(NeedArgs q, const uint32
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // bytes for the bitmap + the need bytes of a chunk of `frames` frames
-size_t fside_cover_bytes(const AggParams& p, int frames) {
+// layout of the coverage workspace: [bitmap][need bytes of a chunk][cnt per plane list][row lists][unit table][unit count]
+struct CoverLayout {
+  size_t off_need, off_cnt, off_rowlist, off_tab, off_nunits, total;
+  int planes, max_units;
+};
+static CoverLayout cover_layout(const AggParams& p, int frames) {
   const CoverMap cm = make_cover_map(p);
-  size_t tiles = 0;
-  for (int s = 0; s < p.S; ++s) tiles += ((size_t)frames * p.V * cm.hw[s] + 2 * TILE_M - 1) / (2 * TILE_M);
-  return align256((size_t)cm.total_words * sizeof(uint32_t)) + align256(tiles * p.nl);
+  CoverLayout L;
+  size_t tiles = 0, units = 0;
+  for (int s = 0; s < p.S; ++s) {
+    tiles += ((size_t)frames * p.V * cm.hw[s] + 2 * TILE_M - 1) / (2 * TILE_M);
+    units += (size_t)p.V * p.nl * ((cm.hw[s] + 2 * TILE_M - 1) / (2 * TILE_M));
+  }
+  L.planes = p.S * p.V * p.nl;
+  L.max_units = (int)units;
+  size_t o = align256((size_t)cm.total_words * sizeof(uint32_t));
+  L.off_need = o;    o += align256(tiles * p.nl);
+  L.off_cnt = o;     o += align256((size_t)L.planes * sizeof(int));
+  L.off_rowlist = o; o += align256((size_t)cm.total_words * 32 * sizeof(int));
+  L.off_tab = o;     o += align256(units * 16);                 // RowUnit entries (16 bytes each)
+  L.off_nunits = o;  o += 256;
+  L.total = o;
+  return L;
 }
+
+size_t fside_cover_bytes(const AggParams& p, int frames) { return cover_layout(p, frames).total; }
 
 // bitmap of covered texels from the tap records (once per call)
 int launch_cover_mark(const AggParams& p, const TapRec* recs, void* cover_ws, cudaStream_t st) {
@@ -807,7 +827,7 @@ int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8
     if (s < p.S) q.tile_begin[s + 1] = q.tile_begin[s] + (q.rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
     else if (s + 1 <= VFA_MAX_SCALES) q.tile_begin[s + 1] = q.tile_begin[s];
   }
-  uint8_t* need = reinterpret_cast<uint8_t*>(cover_ws) + align256((size_t)q.cm.total_words * sizeof(uint32_t));
+  uint8_t* need = reinterpret_cast<uint8_t*>(cover_ws) + cover_layout(p, frames).off_need;
   const int total = q.tile_begin[p.S] * p.nl;
   *need_out = need;
   if (!run) return VFA_OK;
@@ -819,6 +839,326 @@ int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8
   tile_need_kernel<<<(total + 255) / 256, 256, 0, st>>>(q, reinterpret_cast<const uint32_t*>(cover_ws), need);
   VFA_LAUNCH_CHECK("tile_need_kernel");
   return VFA_OK;
+}
+
+// ---- row-compacted image-plane GEMM (forward) ----------------------------------------------------------------------------
+// Whole 256-row tiles still carry uncovered texels (70 / 66 / 46 % of the tiles are needed, but only 54 / 42 / 25 % of the
+// texel rows).  The forward therefore multiplies COMPACTED rows: per (scale, view, layer) the covered texels are listed
+// (rowlist_kernel: popcount + block scan over the bitmap, sorted), a unit = 256 consecutive entries of one list for one
+// frame, and the producers / the epilogue go through the list (indirect A rows, indirect Y rows).  Units are uniform
+// (8 stages, one accumulator), so dealing them round-robin over the resident CTA pairs is balanced; Y keeps its layout.
+struct __align__(16) RowUnit {
+  int s, vn, j, cnt;          // scale, view * nl + layer, chunk of 256 list entries, entries in the list
+};
+static_assert(sizeof(RowUnit) == 16, "cover_layout sizes the unit table with 16-byte entries");
+
+__global__ void __launch_bounds__(256) rowlist_kernel(CoverMap cm, int planes_per_scale, const uint32_t* __restrict__ bits,
+                                                      int* __restrict__ rowlist, int* __restrict__ cnt) {
+  __shared__ int warp_sums[8];
+  __shared__ int running_s;
+  const int pl = blockIdx.x, s = pl / planes_per_scale, vn = pl % planes_per_scale;
+  const int words = s == 0 ? cm.words[0] : (s == 1 ? cm.words[1] : cm.words[2]);
+  const int base = (s == 0 ? cm.word_base[0] : (s == 1 ? cm.word_base[1] : cm.word_base[2])) + vn * words;
+  int* out = rowlist + (size_t)base * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running_s = 0;
+  __syncthreads();
+  for (int w0 = 0; w0 < words; w0 += 256) {
+    const int w = w0 + threadIdx.x;
+    uint32_t m = w < words ? __ldg(bits + base + w) : 0u;
+    const int c = __popc(m);
+    int v = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    int before = running_s;
+    for (int k = 0; k < warp; ++k) before += warp_sums[k];
+    int pos = before + v - c;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      out[pos++] = w * 32 + b;
+      m &= m - 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) running_s = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cnt[pl] = running_s;
+}
+
+// per-frame unit table: for every plane list its ceil(cnt / 256) chunks (single block)
+__global__ void __launch_bounds__(256) unit_table_kernel(const int* __restrict__ cnt, int planes, int planes_per_scale,
+                                                         RowUnit* __restrict__ tab, int* __restrict__ n_units_frame) {
+  __shared__ int warp_sums[8];
+  __shared__ int running_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running_s = 0;
+  __syncthreads();
+  for (int p0 = 0; p0 < planes; p0 += 256) {
+    const int pl = p0 + threadIdx.x;
+    const int n = pl < planes ? cnt[pl] : 0;
+    const int c = (n + 2 * TILE_M - 1) / (2 * TILE_M);
+    int v = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    int before = running_s;
+    for (int k = 0; k < warp; ++k) before += warp_sums[k];
+    int pos = before + v - c;
+    for (int j = 0; j < c; ++j) {
+      RowUnit u;
+      u.s = pl / planes_per_scale;
+      u.vn = pl % planes_per_scale;
+      u.j = j;
+      u.cnt = n;
+      tab[pos + j] = u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) running_s = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_units_frame = running_s;
+}
+
+struct YCompactArgs {
+  const uint8_t* feats[VFA_MAX_SCALES];   // [plane][texel][256] of this chunk (fp32 or bf16)
+  float* y[VFA_MAX_SCALES];               // [plane][layer][texel][256]
+  const uint8_t* wprep[VFA_MAX_SCALES];
+  int hw[VFA_MAX_SCALES];
+  int rl_base[VFA_MAX_SCALES];            // first rowlist entry of scale s; lists of plane vn follow `rl_stride` apart
+  int rl_stride[VFA_MAX_SCALES];
+  const int* rowlist;
+  const RowUnit* tab;
+  const int* n_units_frame;
+  int nb, V, nl;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(THREADS, 1) ygemm_compact_kernel(const YCompactArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  SmemTail* tail = reinterpret_cast<SmemTail*>(smem + (size_t)STAGES * STAGE_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int nuf = __ldg(a.n_units_frame);
+  const int n_units = nuf * a.nb;
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&tail->full[i], NUM_PRODUCER_WARPS + 1);
+      mbar_init(&tail->empty[i], 1);
+      mbar_init(&tail->peer_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tail->acc_full[i], 1);
+      mbar_init(&tail->acc_empty[i], 2 * NUM_EPILOGUE_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp == 0) {
+    // ================= weight loader: the 8 K-chunk slabs of the unit's (scale, layer) =================
+    if (lane == 0) {
+      int it = 0;
+      for (int u = cluster; u < n_units; u += n_clusters) {
+        const RowUnit w = a.tab[u % nuf];
+        const uint8_t* wp = pick(a.wprep, w.s) + (size_t)(w.vn % a.nl) * CHUNKS * (2 * B_BYTES);
+        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+          uint8_t* dst = smem + (size_t)st * STAGE_BYTES + 2 * A_BYTES;
+          mbar_arrive_expect_tx(&tail->full[st], 2 * B_LOCAL_BYTES);
+          const uint8_t* src = wp + (size_t)cc * (2 * B_BYTES);
+          bulk_g2s(dst, src + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+          bulk_g2s(dst + B_LOCAL_BYTES, src + B_BYTES + cta_rank * B_LOCAL_BYTES, B_LOCAL_BYTES, &tail->full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta_rank != 0) {
+      int it = 0;
+      for (int u = cluster; u < n_units; u += n_clusters)
+        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->full[st], (it / STAGES) & 1);
+          mbar_arrive_remote(&tail->peer_full[st], 0);
+        }
+    } else if (lane == 0) {
+      // ================= MMA issuer (pair leader): one accumulator slot per unit =================
+      int it = 0, ln = 0;
+      for (int u = cluster; u < n_units; u += n_clusters, ++ln) {
+        const int slot = ln & 1;
+        mbar_wait_cluster(&tail->acc_empty[slot], ((ln >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)slot * CH;
+        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->full[st], (it / STAGES) & 1);
+          mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+          const uint64_t b_hi = make_desc(sa + 2 * A_BYTES), b_lo = make_desc(sa + 2 * A_BYTES + B_LOCAL_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KCH / 8; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+            tc_mma_tf32_t<true>(d_tmem, a_lo + adv, b_hi + adv, IDESC, (cc | ks) ? 1u : 0u);
+            tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+            tc_mma_tf32_t<true>(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+          }
+          tc_commit_t<true>(&tail->empty[st]);
+        }
+        tc_commit_t<true>(&tail->acc_full[slot]);
+      }
+    }
+  } else if (warp >= FIRST_PRODUCER_WARP && warp < FIRST_EPILOGUE_WARP) {
+    // ================= A producers: listed texel rows -> tf32 hi / lo operand tiles =================
+    constexpr int ES = BF16 ? 2 : 4;
+    const int pw = warp - FIRST_PRODUCER_WARP;
+    const int j = lane & 7;
+    const uint8_t* src[ITEMS];
+    uint32_t off[ITEMS];
+    bool ok[ITEMS];
+    int nidx[ITEMS];                                   // list entries (texels) of this thread's rows in the NEXT unit
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) off[i] = swz((uint32_t)(32 * i + 4 * pw + (lane >> 3)), (uint32_t)j);
+    auto fetch_rows = [&](int u, int(&idx)[ITEMS]) {   // texel of each of this thread's rows, -1 beyond the list
+      const RowUnit w = a.tab[u % nuf];
+      const int* rl = a.rowlist + pick(a.rl_base, w.s) + (size_t)w.vn * pick(a.rl_stride, w.s);
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int e = w.j * (2 * TILE_M) + (int)cta_rank * TILE_M + 32 * i + 4 * pw + (lane >> 3);
+        idx[i] = e < w.cnt ? __ldg(rl + e) : -1;
+      }
+    };
+    auto bind = [&](int u, const int(&idx)[ITEMS]) {
+      const RowUnit w = a.tab[u % nuf];
+      const int plane = (u / nuf) * a.V + w.vn / a.nl;
+      const uint8_t* f = pick(a.feats, w.s) + ((size_t)plane * pick(a.hw, w.s)) * CH * ES + j * 4 * ES;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        ok[i] = idx[i] >= 0;
+        src[i] = f + (size_t)(ok[i] ? idx[i] : 0) * CH * ES;
+      }
+    };
+    auto load_stage = [&](float4(&v)[ITEMS], int cc) {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[i]) v[i] = load_feat4<BF16>(src[i] + (size_t)cc * KCH * ES);
+      }
+    };
+    float4 cur[ITEMS], nxt[ITEMS];
+    int u = cluster;
+    if (u < n_units) {
+      int idx0[ITEMS];
+      fetch_rows(u, idx0);
+      bind(u, idx0);
+      load_stage(cur, 0);
+      if (u + n_clusters < n_units) fetch_rows(u + n_clusters, nidx);
+    }
+    int it = 0;
+    for (; u < n_units; u += n_clusters) {
+      for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+        const int st = it % STAGES;
+        bool more = true;
+        if (cc + 1 < CHUNKS) {
+          load_stage(nxt, cc + 1);
+        } else if (u + n_clusters < n_units) {           // first stage of the next unit; then look one unit further
+          bind(u + n_clusters, nidx);
+          load_stage(nxt, 0);
+          if (u + 2 * n_clusters < n_units) fetch_rows(u + 2 * n_clusters, nidx);
+        } else {
+          more = false;
+        }
+        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+        uint8_t* a_hi = smem + (size_t)st * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) store_split(a_hi, off[i], cur[i]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->full[st]);
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
+        }
+      }
+    }
+  } else if (warp >= FIRST_EPILOGUE_WARP) {
+    // ================= epilogue: accumulator -> the listed rows of Y[plane][layer] =================
+    const int e = warp - FIRST_EPILOGUE_WARP;
+    const int quarter = warp & 3;
+    const int col_begin = (e >> 2) * (CH / 2);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* patch = smem + (size_t)STAGES * STAGE_BYTES + TAIL_BYTES + (size_t)e * PATCH_BYTES;
+    const int sub = lane >> 3, chunk = lane & 7;
+    int ln = 0;
+    for (int u = cluster; u < n_units; u += n_clusters, ++ln) {
+      const RowUnit w = a.tab[u % nuf];
+      const int hw = pick(a.hw, w.s);
+      const int* rl = a.rowlist + pick(a.rl_base, w.s) + (size_t)w.vn * pick(a.rl_stride, w.s);
+      const int plane = (u / nuf) * a.V + w.vn / a.nl;
+      // 1 KB row of Y of patch row 4*rr + sub; ~0u = beyond the list
+      uint32_t yrow[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        const int en = w.j * (2 * TILE_M) + (int)cta_rank * TILE_M + quarter * 32 + 4 * rr + sub;
+        yrow[rr] = en < w.cnt ? (uint32_t)((plane * a.nl + w.vn % a.nl) * hw + __ldg(rl + en)) : 0xffffffffu;
+      }
+      const int slot = ln & 1;
+      mbar_wait_sleep(&tail->acc_full[slot], (ln >> 1) & 1);
+      tc_fence_after();
+      float* dst = pick(a.y, w.s) + col_begin + chunk * 4;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CH / 2; c0 += 32) {
+        float v[32];
+        tc_ld32(lane_addr + (uint32_t)(slot * CH + col_begin + c0), v);
+        tc_wait_ld();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(patch + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int prow = 4 * rr + sub;
+          const float4 q = *reinterpret_cast<const float4*>(patch + prow * 128 + ((chunk ^ (prow & 7)) << 4));
+          if (yrow[rr] != 0xffffffffu) *reinterpret_cast<float4*>(dst + (size_t)yrow[rr] * CH + c0) = q;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank != 0) mbar_arrive_remote(&tail->acc_empty[slot], 0);
+        else mbar_arrive(&tail->acc_empty[slot]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 // One persistent launch over all cluster tiles of `g` (tile_begin must be filled for g.S scales).
@@ -891,6 +1231,77 @@ int launch_ygemm_accum(const float* const* a_rows, float* const* out, const uint
   return launch_ygemm(g, 1, false, st);
 }
 
+// covered-texel lists and the per-frame unit table from the bitmap (once per call, after launch_cover_mark)
+static int launch_rowlists(const AggParams& p, void* cover_ws, int frames, cudaStream_t st) {
+  const CoverMap cm = make_cover_map(p);
+  const CoverLayout L = cover_layout(p, frames);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(cover_ws);
+  rowlist_kernel<<<L.planes, 256, 0, st>>>(cm, p.V * p.nl, reinterpret_cast<const uint32_t*>(cover_ws),
+                                           reinterpret_cast<int*>(w8 + L.off_rowlist), reinterpret_cast<int*>(w8 + L.off_cnt));
+  VFA_LAUNCH_CHECK("rowlist_kernel");
+  unit_table_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const int*>(w8 + L.off_cnt), L.planes, p.V * p.nl,
+                                       reinterpret_cast<RowUnit*>(w8 + L.off_tab), reinterpret_cast<int*>(w8 + L.off_nunits));
+  VFA_LAUNCH_CHECK("unit_table_kernel");
+  return VFA_OK;
+}
+
+static int launch_ygemm_compact(const AggParams& p, const YGemmArgs& g, void* cover_ws, int frames_layout, int nb, bool bf16,
+                                cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  const CoverMap cm = make_cover_map(p);
+  const CoverLayout L = cover_layout(p, frames_layout);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(cover_ws);
+  YCompactArgs a;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+    a.feats[s] = g.feats[s];
+    a.y[s] = g.y[s];
+    a.wprep[s] = g.wprep[s];
+    a.hw[s] = cm.hw[s];
+    a.rl_base[s] = cm.word_base[s] * 32;
+    a.rl_stride[s] = cm.words[s] * 32;
+  }
+  a.rowlist = reinterpret_cast<const int*>(w8 + L.off_rowlist);
+  a.tab = reinterpret_cast<const RowUnit*>(w8 + L.off_tab);
+  a.n_units_frame = reinterpret_cast<const int*>(w8 + L.off_nunits);
+  a.nb = nb;
+  a.V = p.V;
+  a.nl = p.nl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int resident_clusters = 0;
+  if (resident_clusters == 0) {
+    cfg.gridDim = dim3(2 * 148);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, ygemm_compact_kernel<false>, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = 64;
+    }
+    resident_clusters = n;
+  }
+  long long max_units = (long long)L.max_units * nb;     // the real count lives on the device; this bounds the grid
+  cfg.gridDim = dim3(2 * (int)(max_units < resident_clusters ? max_units : resident_clusters));
+  if (bf16)
+    VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_compact_kernel<true>, a));
+  else
+    VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_compact_kernel<false>, a));
+  VFA_LAUNCH_CHECK("ygemm_compact_kernel");
+  return VFA_OK;
+}
+
 // bytes of Y for one frame
 size_t fside_y_bytes_per_frame(const AggParams& p) {
   size_t texels = 0;
@@ -940,8 +1351,14 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     return VFA_ERR_WORKSPACE;
   }
   float* y_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fs_ws) + cover_bytes);
-  if (!(variant & 256)) {       // (debug bit 256: reuse tap records, coverage bitmap and need bytes of the previous call)
+  // row-compacted GEMM unless VFA_FSIDE_COMPACT=0 (whole 256-row tiles, skipped by the need bytes) or VFA_FSIDE_NO_SKIP=1
+  const char* ec = getenv("VFA_FSIDE_COMPACT");
+  const char* en = getenv("VFA_FSIDE_NO_SKIP");
+  const bool compact = !(ec != nullptr && atoi(ec) == 0) && !(en != nullptr && atoi(en) != 0);
+  if (!(variant & 256)) {       // (debug bit 256: reuse tap records, coverage bitmap, lists and need bytes of the previous call)
     if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
+    if (compact)
+      if (int rc = launch_rowlists(p, fs_ws, cb, st)) return rc;
   }
   const size_t es = bf16 ? 2 : 4;
   for (int b0 = 0; b0 < p.B; b0 += cb) {
@@ -972,8 +1389,12 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       }
     }
     if (!(variant & 128)) {
-      if (int rc = launch_tile_need(p, fs_ws, nb, &g.need, st, !(variant & 256))) return rc;
-      if (int rc = launch_ygemm(g, 0, bf16, st)) return rc;
+      if (compact) {
+        if (int rc = launch_ygemm_compact(p, g, fs_ws, cb, nb, bf16, st)) return rc;
+      } else {
+        if (int rc = launch_tile_need(p, fs_ws, nb, &g.need, st, !(variant & 256))) return rc;
+        if (int rc = launch_ygemm(g, 0, bf16, st)) return rc;
+      }
     }
     if (!(variant & 64)) {
       static int quad = -1;            // VFA_POOL_QUAD=0 selects the one-cell-per-warp kernel (debug / comparison)
