@@ -280,9 +280,9 @@ def main():
         step()
     path = vfa_b200.last_kernel_path()
     # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | per frame chunk: ygemm + pool_quad}
-    # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | coverage bitmap + per frame chunk: tile need
-    # bytes + ygemm + pool_quad}
-    launches_per_step = 5 + (1 + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
+    # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | coverage bitmap + row lists + unit table +
+    # per frame chunk: compacted ygemm + pool_quad}
+    launches_per_step = 5 + (3 + 2 * nums['fside_chunks'] if path.startswith('fside') else 1)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -400,8 +400,9 @@ def main():
             pool_bytes = (nums['y_bytes'] + nums['out_bytes']) / nums['fside_chunks'] + nums['rec_bytes']
             t_pool, t_gemm = per_kernel['pool_quad_kernel'], per_kernel['ygemm_kernel']
             pool_gbs = pool_bytes / (t_pool * 1e-3) / 1e9
-            # the GEMM skips the (256-row tile, layer) pairs no box pools; its tensor-core efficiency is quoted on the run
-            # that multiplies every tile (VFA_FSIDE_NO_SKIP=1; that run also carries the tap-record / coverage launches)
+            # the GEMM multiplies only the texel rows some box pools (compacted row lists); its tensor-core efficiency is quoted
+            # on the run that multiplies every row (VFA_FSIDE_NO_SKIP=1, ygemm_kernel; that run also carries the tap-record /
+            # coverage launches)
             t_gemm_all = per_kernel['ygemm_kernel_all_tiles']
             gemm_tflops = nums['fside_flops'] / nums['fside_chunks'] / (t_gemm_all * 1e-3) / 1e12
             step_bytes = nums['bytes'] + 2 * nums['y_bytes'] + nums['rec_bytes']
@@ -416,16 +417,17 @@ def main():
                         'records once + output once; the kernel is bound by the SM-side gather (L1 data pipe 72 % busy, '
                         'profiles/r1_fside_ncu_full.json), not by HBM',
                 'second_kernel': {
-                    'kernel': 'ygemm_kernel', 'bound': 'tensor', 'achieved': gemm_tflops, 'peak': peaks['tflops'],
+                    'kernel': 'ygemm_compact_kernel', 'bound': 'tensor', 'achieved': gemm_tflops, 'peak': peaks['tflops'],
                     'unit': 'TFLOP/s', 'frac': gemm_tflops / peaks['tflops'], 'kernel_ms': t_gemm,
-                    'kernel_ms_all_tiles': t_gemm_all, 'tiles_skipped_frac': max(0.0, 1.0 - t_gemm / t_gemm_all),
+                    'kernel_ms_all_rows': t_gemm_all, 'rows_skipped_frac_est': max(0.0, 1.0 - t_gemm / t_gemm_all),
                     'kernel_share_of_step': t_gemm * nums['fside_chunks'] * args.steps / total_ms,
                     'traffic': traffic_of('ygemm_kernel'),
                     'algorithmic_flops_per_launch': nums['fside_flops'] / nums['fside_chunks'],
                     'tf32x3_ceiling_tflops': peaks['tflops'] / 6.0,
                     'frac_of_tf32x3_ceiling': gemm_tflops / (peaks['tflops'] / 6.0),
-                    'note': 'image-plane contraction 2*B*V*fH*fW*C*(C*nl); fp32 parity needs 3 TF32 passes at half the bf16 '
-                            'rate: the ceiling of a 3xTF32 GEMM is peak/6'},
+                    'note': 'image-plane contraction 2*B*V*fH*fW*C*(C*nl), quoted on the all-rows run; fp32 parity needs 3 TF32 '
+                            'passes at half the bf16 rate: the ceiling of a 3xTF32 GEMM is peak/6. The shipped kernel '
+                            '(kernel_ms) multiplies only the covered texel rows of every layer'},
                 'step': {
                     'fused_ms': kern, 'algorithmic_bytes': step_bytes,
                     'hbm_frac': step_bytes / (kern * 1e-3) / 1e9 / peaks['hbm_gbs'],
