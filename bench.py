@@ -421,7 +421,7 @@ def main():
                     'unit': 'TFLOP/s', 'frac': gemm_tflops / peaks['tflops'], 'kernel_ms': t_gemm,
                     'kernel_ms_all_rows': t_gemm_all, 'rows_skipped_frac_est': max(0.0, 1.0 - t_gemm / t_gemm_all),
                     'kernel_share_of_step': t_gemm * nums['fside_chunks'] * args.steps / total_ms,
-                    'traffic': traffic_of('ygemm_kernel'),
+                    'traffic': traffic_of('ygemm_compact_kernel'),
                     'algorithmic_flops_per_launch': nums['fside_flops'] / nums['fside_chunks'],
                     'tf32x3_ceiling_tflops': peaks['tflops'] / 6.0,
                     'frac_of_tf32x3_ceiling': gemm_tflops / (peaks['tflops'] / 6.0),
