@@ -129,7 +129,8 @@ def test_workspace_sizing_is_host_only(monkeypatch):
     one = ws(1)
     assert one > y_frame                                       # Y of one frame + CSR / gm / Gs of the backward
     assert ws(4) > one + 3 * y_frame                           # grows with the chunk ...
-    assert ws(64) == ws(32)                                    # ... up to the 6 GiB budget (chunks are looped)
+    assert 0 <= ws(64) - ws(32) < 1 << 20                      # ... up to the 6 GiB budget (chunks are looped; only the
+                                                               # per-tile need bytes of the backward still grow with B)
     assert ws(4, channels=16) < 200 << 20                      # generic kernels: weights + small scratch
     monkeypatch.setenv('VFA_FSIDE_Y_BUDGET_MB', '700')         # one frame per chunk
     assert ws(4) == ws(1)
