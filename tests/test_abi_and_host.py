@@ -133,7 +133,7 @@ def test_workspace_sizing_is_host_only(monkeypatch):
                                                                # per-tile need bytes of the backward still grow with B)
     assert ws(4, channels=16) < 200 << 20                      # generic kernels: weights + small scratch
     monkeypatch.setenv('VFA_FSIDE_Y_BUDGET_MB', '700')         # one frame per chunk
-    assert ws(4) == ws(1)
+    assert 0 <= ws(4) - ws(1) < 1 << 20
 
 
 def test_multiscale_module_state_dict_matches_vfanet_keys():
