@@ -413,3 +413,30 @@ def test_table_bit_exact_random_rigs(name):
                                onp.tap_index(b[..., 2], fw), onp.tap_index(b[..., 3], fh)], -1)
             assert np.array_equal(taps[v].cpu().numpy(), t_want)
     print(f'{name}: 10 random cameras on a {grid.shape[0]} x {grid.shape[1]} sub-grid, {n_nan} NaN box edges, all bit-exact')
+
+
+def test_cameras_that_see_nothing():
+    """Every box invisible (cameras looking past the field): no texel is covered, the compacted GEMM has zero units,
+    and every cell gets relu(bias) per view and scale -- both C = 256 formulations and the fp32 kernel."""
+    g = geometry.MULTIVIEWC
+    grid = geometry.grid_for(g)[::4, ::4].contiguous()
+    world_c = np.array([1950.0, 1950.0, 0.0])
+    cams = []
+    for k in range(2):
+        # beside the field, looking ALONG its edge: every corner projects beyond the left / right image border (or, behind
+        # the camera, wraps to the other side), so boxes clamp to zero width or exceed the area cap -- none is visible
+        eye = world_c + np.array([6000.0 * (1 if k == 0 else -1), 0.0, 400.0])
+        cams.append(synthetic.look_at(eye, eye + np.array([0.0, 1.0, 0.0]), 900.0, g.image_size).astype(np.float32))
+    calibs = torch.from_numpy(np.stack(cams)).cuda()
+    table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs, grid.cuda())
+    for fh, fw in g.feature_sizes():
+        _, vis, _ = table.scale_table(fh, fw)
+        assert not bool(vis.any())
+    feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=2, seed=17)]
+    params = synthetic.collapse_params(g, seed=17)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    want = sum(torch.relu(b) for b in bs) * 2
+    for path, flags in PATH_FLAGS.items():
+        out = vfa_b200.aggregate(feats, table, ws, bs, flags=flags)
+        assert vfa_b200.last_kernel_path() == path
+        torch.testing.assert_close(out, want[None, :, None, None].expand_as(out), rtol=0, atol=1e-6)
