@@ -440,3 +440,27 @@ def test_cameras_that_see_nothing():
         out = vfa_b200.aggregate(feats, table, ws, bs, flags=flags)
         assert vfa_b200.last_kernel_path() == path
         torch.testing.assert_close(out, want[None, :, None, None].expand_as(out), rtol=0, atol=1e-6)
+
+
+def test_cameras_that_see_nothing_backward():
+    """Same rig through the backward: no CSR entries, every tile skipped -> dFeature = dWeight = 0, dBias = the masked
+    cotangent summed over frames, views and cells."""
+    g = geometry.MULTIVIEWC
+    grid = geometry.grid_for(g)[::4, ::4].contiguous()
+    world_c = np.array([1950.0, 1950.0, 0.0])
+    cams = [synthetic.look_at(world_c + np.array([6000.0 * sgn, 0.0, 400.0]),
+                              world_c + np.array([6000.0 * sgn, 1.0, 400.0]), 900.0, g.image_size).astype(np.float32)
+            for sgn in (1, -1)]
+    calibs = torch.from_numpy(np.stack(cams)).cuda()
+    table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs, grid.cuda())
+    feats = [f.cuda().requires_grad_(True) for f in synthetic.features(g, batch=2, n_views=2, seed=18)]
+    params = synthetic.collapse_params(g, seed=18)
+    ws = [w.cuda().requires_grad_(True) for w, _ in params]
+    bs = [b.cuda().requires_grad_(True) for _, b in params]
+    gout = torch.randn(2, 256, *grid.shape[:2], generator=torch.Generator().manual_seed(5)).cuda()
+    vfa_b200.aggregate(feats, table, ws, bs).backward(gout)
+    for f, w in zip(feats, ws):
+        assert float(f.grad.abs().max()) == 0.0 and float(w.grad.abs().max()) == 0.0
+    for b in bs:
+        want = (gout.sum(dim=(0, 2, 3)) * 2) * (b.detach() > 0)           # 2 views; relu passes where bias > 0
+        torch.testing.assert_close(b.grad, want, rtol=1e-5, atol=1e-4)
