@@ -45,9 +45,10 @@ def parse():
     ap.add_argument('--flags', type=int, default=0, help='vfa_aggregate_fwd flags (1 = force SIMT path)')
     ap.add_argument('--cpu-views', type=int, default=2, help='views of one frame timed for cpu_baseline')
     ap.add_argument('--ref-views', type=int, default=1, help='views of one frame per step of --impl reference')
-    ap.add_argument('--mode', choices=['dp', 'slab'], default='dp',
+    ap.add_argument('--mode', choices=['dp', 'slab', 'train'], default='dp',
                     help='dp: frames sharded over GPUs, no data-path collective (weak scaling, default); slab: BEV row '
-                         'slabs over GPUs, features broadcast from rank 0 + output all-gather per step (strong scaling)')
+                         'slabs over GPUs, features broadcast from rank 0 + output all-gather per step (strong scaling); '
+                         'train: full detector training step, DDP over GPUs (BASELINE config 5; --batch frames per GPU)')
     ap.add_argument('--backward', action='store_true', help='time forward + backward (BASELINE config 4)')
     ap.add_argument('--features', choices=['f32', 'bf16'], default='f32',
                     help='feature-map storage: f32 (parity path, default) or bf16 (half the gather bytes, stated tolerance)')
@@ -182,10 +183,154 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args):
+    """`--mode train` (BASELINE config 5): one optimiser step of the whole detector -- GroupNorm ResNet-18 trunk, batched
+    laterals, the fused aggregation (forward + backward kernels of this repo), `fuse` and the four heads, a stand-in
+    detection loss, SGD -- on synthetic camera images, data parallel over the GPUs of one box (DistributedDataParallel:
+    gradients of every parameter, the collapse weights included, all-reduced over NCCL during the backward).  The
+    backbone, heads and loss are stock PyTorch / cuDNN (torch default precision settings, as the reference trains);
+    they are outside the hand-written path and are here so the aggregation is measured inside its real consumer."""
+    import torch.nn.functional as F
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import vfa_b200
+    from types import SimpleNamespace
+    from vfa_b200 import geometry, synthetic
+    from vfa_b200.network import VFANet
+    geom = geometry.GEOMETRIES[args.workload]
+    B, V = args.batch, geom.n_views
+    H, W = geom.resize_size
+    torch.manual_seed(0)                                  # identical initial weights on every rank
+    net = VFANet(SimpleNamespace(data=geom.name, image_size=geom.image_size), 'resnet18', geom.grid_height,
+                 geom.cube_size, 360, '3D', False, flags=args.flags).to(dev).to(memory_format=torch.channels_last)
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
+    opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.9, weight_decay=1e-4)   # reference train.py:256
+    grid = geometry.grid_for(geom)[None].to(dev)
+    calibs = synthetic.ring_calibs(geom).to(dev)
+    L, Wg = grid.shape[1:3]
+    gen = torch.Generator().manual_seed(77 + rank)        # every rank trains on its own frames
+    host_images = torch.rand(B * V, 3, H, W, generator=gen).pin_memory()
+    images = host_images.to(dev)
+    tgt = {'heatmap': (torch.rand(B, 1, L, Wg, generator=gen) > 0.98).float().to(dev),
+           'loc_offset': torch.rand(B, L, Wg, 2, generator=gen).to(dev),
+           'dim_offset': torch.randn(B, L, Wg, 3, generator=gen).to(dev),
+           'rotation': torch.randint(0, 360, (B, L, Wg), generator=gen).to(dev)}
+
+    def train_step(x):
+        pred = model(x, calibs, grid, batch=B)
+        obj = tgt['heatmap'].permute(0, 2, 3, 1)          # regression / orientation terms count on object cells only
+        loss = (F.binary_cross_entropy_with_logits(pred['heatmap'], tgt['heatmap'])
+                + (obj * (pred['loc_offset'] - tgt['loc_offset']).abs()).mean()
+                + (obj * (pred['dim_offset'] - tgt['dim_offset']).abs()).mean()
+                + (obj[..., 0] * F.cross_entropy(pred['rotation'].reshape(-1, 360), tgt['rotation'].reshape(-1),
+                                                 reduction='none').view(B, L, Wg)).mean())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(3, args.warmup)):
+        loss = train_step(images)
+    path = vfa_b200.last_kernel_path()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms = timed(lambda: train_step(images), args.steps)
+    clocks = sampler.stop()
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    def e2e_step():
+        x = host_images.to(dev, non_blocking=True)        # pinned host -> device, every step
+        return float(train_step(x).item())                # the loss read back on the host, every step
+    n_e2e = max(3, min(args.steps, 10))
+    e2e_ms = timed(e2e_step, n_e2e)
+
+    # where the step goes: forward of the whole network, and of the aggregation stage alone, on the same inputs
+    net.eval()
+    with torch.no_grad():
+        fwd_ms = timed(lambda: net(images, calibs, grid, batch=B), 5) / 5
+        x = (images - net.mean.view(3, 1, 1)) / net.std.view(3, 1, 1)
+        f8, f16, f32_ = net.base(x.contiguous(memory_format=torch.channels_last))
+        from vfa_b200 import vfanet
+        lats = vfanet.lateral_features(net, f8, f16, f32_)
+        feats = [t.reshape(B, V, *t.shape[1:]) for t in lats]
+        table = vfa_b200.build_table(net.vfa8.geometry((L, Wg)), calibs, grid)
+        wts, bs = [m.collapse.weight for m in (net.vfa8, net.vfa16, net.vfa32)], [m.collapse.bias for m in (net.vfa8, net.vfa16, net.vfa32)]
+        agg_ms = timed(lambda: vfa_b200.aggregate(feats, table, wts, bs, flags=args.flags), 5) / 5
+    net.train()
+    with torch.enable_grad():
+        fg = [t.detach().requires_grad_(True) for t in feats]
+        gout = torch.randn(B, 256, L, Wg, device=dev)
+
+        def agg_fb():
+            vfa_b200.aggregate(fg, table, wts, bs, flags=args.flags).backward(gout)
+        agg_fb()
+        agg_fb_ms = timed(agg_fb, 5) / 5
+    if rank == 0:
+        n_params = sum(p.numel() for p in net.parameters())
+        line = {
+            'metric': 'training_frames_per_s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None,
+            'dtype': 'f32 (aggregation: 3xTF32 tcgen05 + fp32 sums; backbone / heads: cuDNN with torch default settings)',
+            'data': 'synthetic',
+            'config': {'workload': f'full VFA training step on synthetic {args.workload}-shaped frames (GroupNorm ResNet-18 '
+                                   f'trunk + laterals + fused aggregation + fuse/heads + stand-in loss + SGD)',
+                       'batch_per_gpu': B, 'views': V, 'image': [H, W], 'grid': [L, Wg, geom.n_layers], 'parameters': n_params,
+                       'parallelism': f'ddp{world}', 'kernel_path': path,
+                       'l2': f'images {host_images.numel() * 4 / 1e6:.0f} MB/step/GPU and every activation exceed the 126 MB L2'},
+            'clocks': clocks,
+            'e2e': {'value': world * B * n_e2e / (e2e_ms * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': host_images.numel() * 4, 'd2h_bytes_per_step': 4, 'steps': n_e2e,
+                    'note': 'pinned-host fp32 images copied H2D and the loss read back with .item() every step'},
+            'breakdown_ms': {'train_step': total_ms / args.steps, 'network_forward_eval': fwd_ms,
+                             'aggregation_forward': agg_ms, 'aggregation_forward_backward': agg_fb_ms,
+                             'note': 'aggregation = table + fused forward (+ backward kernels) on the lateral maps of this '
+                                     'batch; the rest of the step is cuDNN convolutions / GroupNorm / optimiser'},
+            'final_loss': float(loss.item()),
+            # this repo's kernels per step: forward 10 (table, 3 weight re-layouts, tap records, coverage / row lists / unit
+            # table, compacted GEMM, pooling) + backward >= 16 (3 transposed weight re-layouts, tap records, tile needs, 5 CSR
+            # launches, mask_grad, dy_gather, overflow, dFeature GEMM, dWeight GEMM, layout); cuDNN / ATen launches not counted
+            'gpu_launches': 26 * args.steps,
+            'roofline': None, 'cpu_baseline': None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+        return
+    if args.mode == 'train':
+        if '--batch' not in sys.argv:
+            args.batch = 1
+        run_train(args)
         return
 
     world = int(os.environ.get('WORLD_SIZE', '1'))

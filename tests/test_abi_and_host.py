@@ -147,3 +147,30 @@ def test_multiscale_module_state_dict_matches_vfanet_keys():
     assert tuple(m.vfa16.collapse.weight.shape) == (256, 256 * g.n_layers)
     with pytest.raises(ValueError, match='three FPN scales'):
         m([torch.zeros(1, 1, 256, 4, 4)], torch.zeros(1, 3, 4), geometry.grid_for(g))
+
+
+def test_network_module_has_the_reference_checkpoint_layout():
+    """vfa_b200.network.VFANet: key names / shapes of the reference checkpoint (vfanet.py:27-56, resnet.py:100-110); the
+    key-for-key comparison with the reference class itself is in test_reference_compat.py (build container only)."""
+    from types import SimpleNamespace
+    from vfa_b200.network import VFANet, procedural_state
+    args = SimpleNamespace(data='MultiviewC', image_size=(720, 1280))
+    net = VFANet(args, 'resnet18', 160, (25, 25, 32), 360, '3D', False)
+    sd = net.state_dict()
+    assert len(sd) == 112
+    want = {'base.conv1.weight': (64, 3, 7, 7), 'base.layer2.0.downsample.0.weight': (128, 64, 1, 1),
+            'base.layer4.1.bn2.bias': (512,), 'lat32.weight': (256, 512, 1, 1), 'bn16.weight': (256,),
+            'vfa8.collapse.weight': (256, 1280), 'vfa16.z_corners': (5, 1, 1, 3), 'vfa32.corners_offset': (1, 1, 1, 1, 8, 3),
+            'fuse.4.running_var': (256,), 'map_classifier.0.weight': (1, 256, 3, 3), 'tytx_pred.3.weight': (2, 256, 3, 3),
+            'orient_pred.0.weight': (360, 256, 3, 3), 'thtwtl_pred.1.weight': (256,), 'mean': (3,), 'std': (3,)}
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == shp, k
+    assert 'orient_pred.0.weight' not in VFANet(args, 'resnet34', 160, (25, 25, 32), 360, '2D', False).state_dict()
+    # procedural weights: a function of the key names only
+    a, b = procedural_state(sd), procedural_state(dict(reversed(list(sd.items()))))
+    assert all(torch.equal(a[k], b[k]) for k in sd)
+    assert torch.equal(a['vfa16.z_corners'], sd['vfa16.z_corners']) and torch.equal(a['mean'], sd['mean'])
+    net.load_state_dict(a)
+    # no CPU path: the aggregation raises on host tensors
+    with pytest.raises(Exception):
+        net(torch.rand(1, 3, 704, 704), torch.rand(1, 3, 4), torch.zeros(1, 4, 4, 3))

@@ -46,3 +46,26 @@ def test_reference_vfanet_builds_on_the_drop_in_module():
     assert {'vfa8.collapse.weight', 'vfa8.collapse.bias', 'vfa16.collapse.weight', 'vfa32.collapse.bias'} <= names
     for n in [k for k in sys.modules if k == 'vfa' or k.startswith('vfa.')]:
         del sys.modules[n]
+
+
+def test_own_network_module_has_the_reference_state_dict():
+    """vfa_b200.network.VFANet (the batched, fused network of BASELINE config 5) against the reference class: same keys in
+    the same order, same shapes / dtypes, for both backbones and both modes; the trunks are bit-identical on CPU."""
+    from vfa_b200.network import VFANet, procedural_state
+    args = SimpleNamespace(data='Wildtrack', image_size=(1080, 1920))
+    ref_mod = _import_vfanet(False)
+    for base, mode in (('resnet18', '3D'), ('resnet34', '2D')):
+        ref = ref_mod.VFANet(args, base, 32, (4, 4, 4), 360, mode, False)
+        ours = VFANet(args, base, 32, (4, 4, 4), 360, mode, False)
+        a = [(k, tuple(v.shape), v.dtype) for k, v in ref.state_dict().items()]
+        b = [(k, tuple(v.shape), v.dtype) for k, v in ours.state_dict().items()]
+        assert a == b
+    sd = procedural_state(ref.state_dict())
+    ref.load_state_dict(sd)
+    ours.load_state_dict(sd)
+    x = torch.rand(2, 3, 64, 96)
+    with torch.no_grad():
+        for r, o in zip(ref.base(x), ours.base(x)):
+            assert torch.equal(r, o)
+    for n in [k for k in sys.modules if k == 'vfa' or k.startswith('vfa.')]:
+        del sys.modules[n]
