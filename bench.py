@@ -45,10 +45,15 @@ def parse():
     ap.add_argument('--flags', type=int, default=0, help='vfa_aggregate_fwd flags (1 = force SIMT path)')
     ap.add_argument('--cpu-views', type=int, default=2, help='views of one frame timed for cpu_baseline')
     ap.add_argument('--ref-views', type=int, default=1, help='views of one frame per step of --impl reference')
-    ap.add_argument('--mode', choices=['dp', 'slab', 'train'], default='dp',
+    ap.add_argument('--mode', choices=['dp', 'slab', 'views', 'train'], default='dp',
                     help='dp: frames sharded over GPUs, no data-path collective (weak scaling, default); slab: BEV row '
                          'slabs over GPUs, features broadcast from rank 0 + output all-gather per step (strong scaling); '
+                         'views: cameras sharded over GPUs (features stay on the rank that owns the camera), partial BEV '
+                         'maps all-reduced, frame chunks pipelined (strong scaling); '
                          'train: full detector training step, DDP over GPUs (BASELINE config 5; --batch frames per GPU)')
+    ap.add_argument('--view-chunk', type=int, default=0,
+                    help='--mode views: frames per all-reduce chunk (0 = the whole batch in one call; smaller chunks overlap '
+                         'the all-reduce with the next chunk at the price of per-call table / weight / record launches)')
     ap.add_argument('--backward', action='store_true', help='time forward + backward (BASELINE config 4)')
     ap.add_argument('--features', choices=['f32', 'bf16'], default='f32',
                     help='feature-map storage: f32 (parity path, default) or bf16 (half the gather bytes, stated tolerance)')
@@ -360,12 +365,18 @@ def main():
     # synthetic features, generated on the device (seed differs per rank: every GPU owns different frames);
     # logical [B,V,C,fH,fW], stored channels-last = the layout the lateral convs emit in torch.channels_last
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    feats_cl = [torch.randn(B, V, h, w, C, generator=gen, device=dev).relu_() for (h, w) in geom.feature_sizes()]
+    v0, v1 = (0, V)
+    if args.mode == 'views':
+        from vfa_b200 import distributed as _vd
+        v0, v1 = _vd.view_bounds(V, world, rank)
+    feats_cl = [torch.randn(B, v1 - v0, h, w, C, generator=gen, device=dev).relu_() for (h, w) in geom.feature_sizes()]
     if args.features == 'bf16':
         feats_cl = [f.to(torch.bfloat16) for f in feats_cl]
         args.no_e2e = True
-    shape = vfa_b200.make_shape(feats_cl, cgeom.n_layers)
-    ws = vfa_b200.workspace_for(cgeom, shape, args.flags, dev)
+    shape = ws = None
+    if args.mode != 'views':
+        shape = vfa_b200.make_shape(feats_cl, cgeom.n_layers)
+        ws = vfa_b200.workspace_for(cgeom, shape, args.flags, dev)
     out = torch.empty(B, C, grid.shape[0], grid.shape[1], device=dev)
     nums = workload_numbers(geom, B, 2 if args.features == 'bf16' else 4)
 
@@ -384,11 +395,20 @@ def main():
                 return vfa_b200.aggregate(f, table, w, b_, flags=args.flags, channels_last=True)
             return vfa_b200.aggregate_forward_raw(f, table, w, b_, args.flags)
 
+    def views_compute(f, c, g_, w, b_):
+        table = vfa_b200.build_table(cgeom, c, g_)
+        if args.backward:
+            return vfa_b200.aggregate(f, table, w, b_, flags=args.flags, channels_last=True)
+        return vfa_b200.aggregate_forward_raw(f, table, w, b_, args.flags)
+
     def step_general(timed_events=None):
-        """slab mode and/or backward: through the autograd-capable public entry points."""
+        """slab / views mode and/or backward: through the autograd-capable public entry points."""
         if timed_events is not None:
             timed_events[0].record()
-        if args.mode == 'slab':
+        if args.mode == 'views':
+            res = vd.aggregate_views(feats_cl, calibs[v0:v1], grid, weights, biases, views_compute, out_channels=C,
+                                     frames_per_chunk=args.view_chunk)
+        elif args.mode == 'slab':
             vd.broadcast_features([f.detach() for f in feats_cl], src=0)
             res = vd.aggregate_slab(feats_cl, calibs, grid, weights, biases, slab_compute)
         else:
@@ -404,7 +424,7 @@ def main():
             timed_events[1].record()
 
     def step(timed_events=None):
-        if args.mode == 'slab' or args.backward:
+        if args.mode in ('slab', 'views') or args.backward:
             return step_general(timed_events)
         table = vfa_b200.build_table(cgeom, calibs, grid)                           # 1 launch
         vfa_b200.prepare_weights(cgeom, shape, weights, args.flags, workspace=ws)    # 3 launches
@@ -428,6 +448,8 @@ def main():
     # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | coverage bitmap + row lists + unit table +
     # per frame chunk: compacted ygemm + pool_quad}
     launches_per_step = 5 + (3 + 2 * nums['fside_chunks'] if path.startswith('fside') else 1)
+    if args.mode == 'views':                          # every frame chunk is a complete call (table and weights included)
+        launches_per_step *= -(-B // (args.view_chunk or B))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -446,7 +468,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    frames_per_step = B if args.mode == 'slab' else world * B
+    frames_per_step = B if args.mode in ('slab', 'views') else world * B
     value = frames_per_step * args.steps / (total_ms * 1e-3)
     kern = sum(kernel_ms) / len(kernel_ms)
 
@@ -520,7 +542,7 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        work_scale = (3.0 if args.backward else 1.0) / (world if args.mode == 'slab' else 1)
+        work_scale = (3.0 if args.backward else 1.0) / (world if args.mode in ('slab', 'views') else 1)
         tflops = nums['flops'] * work_scale / (kern * 1e-3) / 1e12
         gbs = nums['bytes'] / (kern * 1e-3) / 1e9
         traffic = None
@@ -600,7 +622,7 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'strong' if args.mode == 'slab' else 'weak', 'vs_baseline': None,
+            'scaling': 'strong' if args.mode in ('slab', 'views') else 'weak', 'vs_baseline': None,
             'dtype': 'f32' if path == 'simt_fp32' else 'f32 (3xTF32 tcgen05 contraction, fp32 pooling and sums)',
             'data': 'synthetic',
             'config': {'workload': f'{args.workload}-shaped aggregation forward' + ('+backward' if args.backward else ''),

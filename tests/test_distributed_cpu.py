@@ -1,5 +1,5 @@
-"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: slab partition + all-gather reassembly + gradient
-all-reduce, and data-parallel collapse-gradient reduction.  The per-rank compute is the oracle port here (the CUDA
+"""World-size-2 / 3 gloo tests (CPU) of the multi-GPU host logic: slab partition + all-gather reassembly + gradient
+all-reduce, camera sharding + all-reduce of the partial maps, and data-parallel collapse-gradient reduction.  The per-rank compute is the oracle port here (the CUDA
 kernels need a GPU); on GPUs the same functions run with vfa_b200.distributed.cuda_compute."""
 import os
 import socket
@@ -90,3 +90,61 @@ def test_slab_sharding_equals_single_process_gloo(name):
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), name, results), nprocs=world, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def _views_worker(rank, world, port, name, results):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        g = geometry.GEOMETRIES[name]
+        V, B, C = 2, 3, 4                                              # world 3 > V: the last rank owns no camera
+        grid = geometry.grid_for(g)[::12, ::9].contiguous()
+        calibs = synthetic.ring_calibs(g, n_views=V)
+        sizes = [(30, 52), (23, 40)]
+        feats = [f.double() for f in synthetic.features(g, batch=B, n_views=V, channels=C, seed=9, sizes=sizes)]
+        params = synthetic.collapse_params(g, channels=C, seed=9)[:2]
+        v0, v1 = vd.view_bounds(V, world, rank)
+        local = [f[:, v0:v1].clone().requires_grad_(True) for f in feats]
+        ws = [w.double().requires_grad_(True) for w, _ in params]
+        bs = [b.double().requires_grad_(True) for _, b in params]
+        compute = _port_compute(name)
+        full = vd.aggregate_views(local, calibs[v0:v1], grid, ws, bs, compute, out_channels=C, frames_per_chunk=2)
+        gout = torch.randn(full.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+        full.backward(gout)
+        f2 = [f.detach().clone().requires_grad_(True) for f in feats]
+        w2 = [w.detach().clone().requires_grad_(True) for w in ws]
+        b2 = [b.detach().clone().requires_grad_(True) for b in bs]
+        want = compute(f2, calibs, grid, w2, b2)
+        want.backward(gout)
+        ok = tuple(full.shape) == (B, C) + tuple(grid.shape[:2]) and torch.allclose(full, want, rtol=1e-12, atol=1e-12)
+        for a, b in zip(local, f2):                                      # dFeature: complete on the owner, no exchange
+            if v1 > v0:
+                ok = ok and torch.allclose(a.grad, b.grad[:, v0:v1], rtol=1e-10, atol=1e-12)
+            else:
+                ok = ok and a.grad is None                               # a rank without cameras has no features
+        for a, b in zip(ws + bs, w2 + b2):                               # dWeight / dBias: summed over ranks
+            ok = ok and a.grad is not None and torch.allclose(a.grad, b.grad, rtol=1e-10, atol=1e-12)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_camera_sharding_equals_single_process_gloo(world):
+    assert [vd.view_bounds(7, 8, r) for r in (0, 6, 7)] == [(0, 1), (6, 7), (7, 7)]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_views_worker, args=(world, _free_port(), 'MultiviewX', results), nprocs=world, join=True)
+    assert dict(results) == {r: True for r in range(world)}
+
+
+def test_camera_sharding_without_a_process_group_is_the_plain_call():
+    g = geometry.GEOMETRIES['MultiviewC']
+    grid = geometry.grid_for(g)[::12, ::12].contiguous()
+    calibs = synthetic.ring_calibs(g, n_views=2)
+    feats = [f.double() for f in synthetic.features(g, batch=3, n_views=2, channels=4, seed=2, sizes=[(30, 52)])]
+    w, b = synthetic.collapse_params(g, channels=4, seed=2)[0]
+    compute = _port_compute('MultiviewC')
+    got = vd.aggregate_views(feats, calibs, grid, [w.double()], [b.double()], compute, out_channels=4, frames_per_chunk=2)
+    assert torch.equal(got, compute(feats, calibs, grid, [w.double()], [b.double()]))

@@ -1,5 +1,5 @@
-"""Two-GPU checks (skipped on a 1-GPU box): BEV row-slab sharding over NCCL reproduces the single-GPU result and
-gradients; data-parallel ranks reduce the collapse gradients."""
+"""Two-GPU checks (skipped on a 1-GPU box): BEV row-slab sharding and camera sharding over NCCL reproduce the single-GPU
+result and gradients; data-parallel ranks reduce the collapse gradients."""
 import os
 import socket
 
@@ -63,4 +63,55 @@ def test_slab_sharding_two_gpus_matches_single_gpu():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+def _views_worker(rank, world, port, results):
+    import torch.distributed as dist
+    import vfa_b200
+    from vfa_b200 import distributed as vd
+    from vfa_b200 import geometry, synthetic
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        g = geometry.WILDTRACK
+        V, B = 3, 3
+        zs = list(range(0, g.grid_height, g.cube_size[2]))
+        grid = geometry.grid_for(g).to(dev)
+        cgeom = vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid.shape[:2], g.name, g.image_size)
+        calibs = synthetic.ring_calibs(g, n_views=V).to(dev)
+        feats = [f.to(dev) for f in synthetic.features(g, batch=B, n_views=V, seed=21)]
+        params = synthetic.collapse_params(g, seed=21)
+        ws = [w.to(dev).requires_grad_(True) for w, _ in params]
+        bs = [b.to(dev).requires_grad_(True) for _, b in params]
+        v0, v1 = vd.view_bounds(V, world, rank)                          # 2 + 1 cameras
+        local = [f[:, v0:v1].contiguous().requires_grad_(True) for f in feats]
+
+        def compute(f, c, grid_, w, b_):
+            return vfa_b200.aggregate(f, vfa_b200.build_table(cgeom, c, grid_), w, b_)
+        full = vd.aggregate_views(local, calibs[v0:v1], grid, ws, bs, compute, out_channels=256, frames_per_chunk=1)
+        gout = torch.randn(full.shape, generator=torch.Generator(device=dev).manual_seed(1), device=dev)
+        full.backward(gout)
+        f2 = [f.detach().clone().requires_grad_(True) for f in feats]
+        w2 = [w.detach().clone().requires_grad_(True) for w in ws]
+        b2 = [b.detach().clone().requires_grad_(True) for b in bs]
+        want = compute(f2, calibs, grid, w2, b2)
+        want.backward(gout)
+        ok = torch.allclose(full, want, rtol=1e-5, atol=1e-5)
+        pairs = [(a.grad, b.grad[:, v0:v1]) for a, b in zip(local, f2)] + [(a.grad, b.grad) for a, b in zip(ws + bs, w2 + b2)]
+        for a, b in pairs:
+            ok = ok and float((a - b).abs().max()) / (float(b.abs().max()) + 1e-30) < 1e-4
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_camera_sharding_two_gpus_matches_single_gpu():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_views_worker, args=(2, _free_port(), results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
