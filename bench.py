@@ -40,7 +40,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
-    ap.add_argument('--workload', choices=['MultiviewC', 'MultiviewX', 'Wildtrack'], default='MultiviewC')
+    ap.add_argument('--workload', choices=['MultiviewC', 'MultiviewX', 'Wildtrack', 'MultiviewC-37.5m'], default='MultiviewC',
+                    help='dataset geometry (config-of-record); MultiviewC-37.5m = the literal 150 x 150 cell reading')
     ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step')
     ap.add_argument('--flags', type=int, default=0, help='vfa_aggregate_fwd flags (1 = force SIMT path)')
     ap.add_argument('--cpu-views', type=int, default=2, help='views of one frame timed for cpu_baseline')
@@ -165,7 +166,7 @@ def run_reference(args):
     if rank != 0:
         return
     from vfa_b200 import geometry
-    geom = geometry.GEOMETRIES[args.workload]
+    geom = geometry.BENCH_WORKLOADS[args.workload]
     views = max(1, min(args.ref_views, geom.n_views))
     for _ in range(args.warmup):
         cpu_port_time(geom, views)
@@ -207,7 +208,7 @@ def run_train(args):
     from types import SimpleNamespace
     from vfa_b200 import geometry, synthetic
     from vfa_b200.network import VFANet
-    geom = geometry.GEOMETRIES[args.workload]
+    geom = geometry.BENCH_WORKLOADS[args.workload]
     B, V = args.batch, geom.n_views
     H, W = geom.resize_size
     torch.manual_seed(0)                                  # identical initial weights on every rank
@@ -353,7 +354,7 @@ def main():
     import vfa_b200
     from vfa_b200 import geometry
     from vfa_b200 import synthetic
-    geom = geometry.GEOMETRIES[args.workload]
+    geom = geometry.BENCH_WORKLOADS[args.workload]
     B, V, C = args.batch, geom.n_views, geom.channels
     zs = list(range(0, geom.grid_height, geom.cube_size[2]))
     grid = geometry.grid_for(geom).to(dev)

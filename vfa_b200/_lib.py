@@ -18,7 +18,9 @@ FLAG_WEIGHTS_PREPARED = 8
 FLAG_BF16_FEATURES = 16
 FLAG_GRID_SIDE = 32
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libvfa_b200.so')
+# VFA_B200_LIB: another build of the same library (A/B timing of compile-time kernel variants, scripts/build_variant.sh)
+LIB_PATH = os.environ.get('VFA_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
+                                                           'libvfa_b200.so')
 
 EXPORTS = ['vfa_version', 'vfa_last_error', 'vfa_last_path', 'vfa_table_build', 'vfa_table_scale',
            'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_workspace_bytes', 'vfa_prepare_weights', 'vfa_aggregate_fwd',

@@ -408,7 +408,14 @@ struct PoolArgs {
   const TapRec* recs;        // [V][S][nl][LW]
   int b0;                    // first frame of this chunk (output / mask index); Y planes are chunk-relative
   int tiles_x;
+  // texel lists of the quads (pool_list_kernel; nullptr = not built)
+  const uint32_t* seg_off;   // [quads][V*S + 1] first entry of segment (view, scale) of a quad; last = end of the quad's list,
+                             // or LIST_OVERFLOW when the quad's texels did not fit its slot
+  const uint32_t* ent_off;   // [quads * slot] texel index inside the (view, scale) stack of nl planes
+  const float4* ent_w;       // [quads * slot] weights of the four cells of the quad
+  int quads_x;
 };
+constexpr uint32_t LIST_OVERFLOW = 0xffffffffu;
 
 __device__ __forceinline__ void fma8(float (&acc)[8], float w, const float4& a, const float4& b) {
   const float2 w2 = make_float2(w, w);
@@ -549,7 +556,9 @@ constexpr int QWARPS = QX * QY;
 constexpr int QTB = VFA_QUAD_BATCH;                     // texels of a union row in flight per warp (2 x LDG.128 each)
 static_assert(8 % QTB == 0, "");
 
-template <bool MASK>
+// OVF = true: the completion pass behind pool_list_kernel -- only the quads whose texel list did not fit its slot are
+// walked (normally none: the warp returns at once); the list kernel leaves exactly those quads alone.
+template <bool MASK, bool OVF = false>
 __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_kernel(const PoolArgs a) {
   __shared__ float out_s[QWARPS][4][CH];
   const AggParams& p = a.p;
@@ -557,6 +566,7 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
   const int cy0 = (blockIdx.x / a.tiles_x) * (2 * QY) + 2 * (warp / QX);
   const int cx0 = (blockIdx.x % a.tiles_x) * (2 * QX) + 2 * (warp % QX);
   if (cy0 >= p.L || cx0 >= p.W) return;                 // no block-level synchronisation below
+  if (OVF && __ldg(a.seg_off + (size_t)((cy0 >> 1) * a.quads_x + (cx0 >> 1)) * (p.V * p.S + 1) + p.V * p.S) != LIST_OVERFLOW) return;
   const int bl = blockIdx.y;
   const int b = a.b0 + bl;
   const int cl = lane & 3, jl = lane >> 2;              // this lane's cell (records, weights) and block column
@@ -644,6 +654,209 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
           }
         }
       }
+      // + bias, ReLU (vfa_op.py:123-124), sum over scales and views (vfanet.py:79, :82)
+      const float4 bi0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 4));
+      const float4 bi1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + CH / 2 + lane * 4));
+      const float bb[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
+        float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
+        float t[8];
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          t[i] = acc[c][i] + bb[i];
+          bits |= (t[i] > 0.f ? 1u : 0u) << i;
+        }
+        o0.x += fmaxf(t[0], 0.f); o0.y += fmaxf(t[1], 0.f); o0.z += fmaxf(t[2], 0.f); o0.w += fmaxf(t[3], 0.f);
+        o1.x += fmaxf(t[4], 0.f); o1.y += fmaxf(t[5], 0.f); o1.z += fmaxf(t[6], 0.f); o1.w += fmaxf(t[7], 0.f);
+        *reinterpret_cast<float4*>(outw + c * CH) = o0;
+        *reinterpret_cast<float4*>(outw + c * CH + 4) = o1;
+        if (MASK) {
+          const int cy = cy0 + (c >> 1), cx = cx0 + (c & 1);
+          const bool ok = cy < p.L && cx < p.W;
+          store_mask_words(p.mask + (((size_t)b * p.V + v) * p.S + s) * (CH / 32) * p.LW + (ok ? cy * p.W + cx : 0),
+                           (size_t)p.LW, lane, bits, ok);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int cy = cy0 + (c >> 1), cx = cx0 + (c & 1);
+    if (cy >= p.L || cx >= p.W) continue;
+    const float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
+    const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
+    float* o = p.out + (size_t)b * CH * p.LW + cy * p.W + cx;
+    const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[(size_t)chan_of(lane, i) * p.LW] = ov[i];
+  }
+}
+
+// ---- pooling of Y from precomputed texel lists ------------------------------------------------------------------------
+// pool_quad_kernel spends ~60 instructions per texel it loads -- records, union bounds, row / column weights, ballots and
+// shuffles around 2 loads and 16 packed FMAs -- and every pass over (at most) two texels of a union row waits for a full
+// memory round trip.  The projection is static, so that bookkeeping is done ONCE per table by qlist_walk_kernel: per
+// (quad, view, scale) segment the covered texels of all layers in the order pool_quad_kernel visits them, each with its
+// texel index and the four cell weights (qlist_walk_kernel).  The hot kernel is then a flat loop -- uniform loads of (index, weights), two
+// 128-bit loads of the texel row, 16 packed FMAs -- with LIST_BATCH texels in flight whatever the shape of the union,
+// and its sums are bit-identical to the walking kernel's (same weights, same order).
+#ifndef VFA_LIST_BATCH
+#define VFA_LIST_BATCH 3
+#endif
+#ifndef VFA_LIST_MINBLOCKS
+#define VFA_LIST_MINBLOCKS 3
+#endif
+constexpr int LB = VFA_LIST_BATCH;
+constexpr uint32_t LIST_PER_ITER = 16;      // slot of a quad: entries per (view, scale, layer) on average
+
+// The walk of one (quad, view): FILL = false counts the entries of its S * nl iterations, FILL = true writes them from
+// absolute index `first` on and the starts of the view's S segments.  Up to the ballot this is the arithmetic of
+// pool_quad_kernel, instruction for instruction.
+template <bool FILL>
+__device__ __forceinline__ uint32_t qlist_walk_view(const AggParams& p, const uint4* rp, size_t rec_stride, bool my_valid, int lane,
+                                                    uint32_t first, uint32_t* __restrict__ so_v, uint32_t* __restrict__ ent_off,
+                                                    float* __restrict__ ent_w) {
+  const int cl = lane & 3, jl = lane >> 2;
+  uint4 n0 = __ldg(rp), n1 = __ldg(rp + 1);             // record of (s, n) = (0, 0), prefetched one step ahead
+  const int iters = p.S * p.nl;
+  int j_rec = 0;
+  uint32_t total = 0;
+  for (int s = 0; s < p.S; ++s) {
+    const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
+    if (FILL && lane == 0) so_v[s] = first + total;
+    for (int n = 0; n < p.nl; ++n, ++j_rec) {
+      const uint4 r0 = n0, r1 = n1;
+      if (j_rec + 1 < iters) {
+        rp += rec_stride;
+        n0 = __ldg(rp);
+        n1 = __ldg(rp + 1);
+      }
+      const int nx = my_valid ? ((int)r0.y & 0xffff) : 0, ny = (int)r0.y >> 16;
+      const int x0 = (int)r0.x & 0xffff, y0 = (int)r0.x >> 16;
+      const bool vis = nx != 0;
+      const int ux1 = __reduce_max_sync(0xffffffffu, vis ? x0 + nx - 1 : -1);
+      if (ux1 < 0) continue;
+      const int ux0 = __reduce_min_sync(0xffffffffu, vis ? x0 : 0x7fff);
+      const int uy0 = __reduce_min_sync(0xffffffffu, vis ? y0 : 0x7fff);
+      const int uy1 = __reduce_max_sync(0xffffffffu, vis ? y0 + ny - 1 : -1);
+      const float wx_first = __uint_as_float(r0.z), wx_last = __uint_as_float(r0.w);
+      const float wy_first = __uint_as_float(r1.x), wy_last = __uint_as_float(r1.y), wy_mid = __uint_as_float(r1.z);
+      for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
+        const int rx = ux0 + cb + jl - x0;
+        const float wx = (vis && rx >= 0 && rx < nx) ? (rx == 0 ? wx_first : (rx == nx - 1 ? wx_last : 1.0f)) : 0.f;
+        for (int ty = uy0; ty <= uy1; ++ty) {
+          const int ry = ty - y0;
+          const float wy = (ry >= 0 && ry < ny) ? (ry == 0 ? wy_first : (ry == ny - 1 ? wy_last : wy_mid)) : 0.f;
+          const float wl = __fmul_rn(wy, wx);
+          const uint32_t bm = __ballot_sync(0xffffffffu, wl != 0.f);     // bit 4*j + c
+          const uint32_t cov = (bm | (bm >> 1) | (bm >> 2) | (bm >> 3)) & 0x11111111u;     // bit 4*j: texel j is pooled
+          if (FILL && ((cov >> (4 * jl)) & 1u)) {
+            const size_t k = (size_t)first + total + __popc(cov & ((1u << (4 * jl)) - 1u));
+            ent_w[k * 4 + cl] = wl;
+            if (cl == 0) ent_off[k] = (uint32_t)(n * hw + ty * fw + ux0 + cb + jl);
+          }
+          total += __popc(cov);
+        }
+      }
+    }
+  }
+  return total;
+}
+
+// One CTA per quad, one warp per view: count, exchange the counts through shared memory, fill.  The quad's entries go into
+// its own slot of `slot` entries (no global scan); a quad whose texels do not fit is marked LIST_OVERFLOW, gets no entries
+// and is pooled by pool_quad_kernel<.., OVF> -- exact for any rig, no host synchronisation, static workspace.
+__global__ void __launch_bounds__(1024) qlist_walk_kernel(const AggParams p, const TapRec* __restrict__ recs, int quads_x,
+                                                          uint32_t slot, uint32_t* __restrict__ seg_off,
+                                                          uint32_t* __restrict__ ent_off, float* __restrict__ ent_w) {
+  __shared__ uint32_t cnt_s[32];
+  const int lane = threadIdx.x & 31, v = threadIdx.x >> 5;          // blockDim.x = 32 * V
+  const int q = blockIdx.x;
+  const int VS = p.V * p.S;
+  const int cy0 = 2 * (q / quads_x), cx0 = 2 * (q % quads_x);
+  const int cl = lane & 3;
+  const bool my_valid = cy0 + (cl >> 1) < p.L && cx0 + (cl & 1) < p.W;
+  const int my_cell = my_valid ? (cy0 + (cl >> 1)) * p.W + cx0 + (cl & 1) : cy0 * p.W + cx0;
+  const size_t rec_stride = (size_t)p.LW * (sizeof(TapRec) / sizeof(uint4));
+  const uint4* rp = reinterpret_cast<const uint4*>(recs + my_cell) + (size_t)v * p.S * p.nl * rec_stride;
+  uint32_t* const so = seg_off + (size_t)q * (VS + 1);
+  const uint32_t mine = qlist_walk_view<false>(p, rp, rec_stride, my_valid, lane, 0u, nullptr, nullptr, nullptr);
+  if (lane == 0) cnt_s[v] = mine;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+  for (int u = 0; u < p.V; ++u) {
+    const uint32_t c = cnt_s[u];
+    before += u < v ? c : 0u;
+    all += c;
+  }
+  if (all > slot) {
+    if (threadIdx.x == 0) so[VS] = LIST_OVERFLOW;
+    return;
+  }
+  const uint32_t base = (uint32_t)q * slot;
+  qlist_walk_view<true>(p, rp, rec_stride, my_valid, lane, base + before, so + v * p.S, ent_off, ent_w);
+  if (threadIdx.x == 0) so[VS] = base + all;
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(QWARPS * 32, VFA_LIST_MINBLOCKS) pool_list_kernel(const PoolArgs a) {
+  __shared__ float out_s[QWARPS][4][CH];
+  const AggParams& p = a.p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cy0 = (blockIdx.x / a.tiles_x) * (2 * QY) + 2 * (warp / QX);
+  const int cx0 = (blockIdx.x % a.tiles_x) * (2 * QX) + 2 * (warp % QX);
+  if (cy0 >= p.L || cx0 >= p.W) return;                 // no block-level synchronisation below
+  const uint32_t* so = a.seg_off + (size_t)((cy0 >> 1) * a.quads_x + (cx0 >> 1)) * (p.V * p.S + 1);
+  if (__ldg(so + p.V * p.S) == LIST_OVERFLOW) return;   // pooled by the completion pass (pool_quad_kernel<.., OVF>)
+  const int bl = blockIdx.y;
+  const int b = a.b0 + bl;
+
+  float* const outw = &out_s[warp][0][lane * 8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    *reinterpret_cast<float4*>(outw + c * CH) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(outw + c * CH + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  uint32_t e = __ldg(so);
+  for (int v = 0; v < p.V; ++v) {
+    for (int s = 0; s < p.S; ++s) {
+      const uint32_t end = __ldg(++so);
+      const int hw = p.sc[s].fh * p.sc[s].fw;
+      const float* ybase = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
+      float acc[4][8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+      for (; e < end; e += LB) {
+        uint32_t off[LB];
+        float4 va[LB], vb[LB];
+#pragma unroll
+        for (int k = 0; k < LB; ++k) off[k] = e + k < end ? __ldg(a.ent_off + e + k) : 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < LB; ++k) {
+          if (off[k] != 0xffffffffu) {
+            const float* tp = ybase + (size_t)off[k] * CH;
+            va[k] = __ldg(reinterpret_cast<const float4*>(tp));
+            vb[k] = __ldg(reinterpret_cast<const float4*>(tp + CH / 2));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < LB; ++k) {
+          if (off[k] != 0xffffffffu) {
+            const float4 w = __ldg(a.ent_w + e + k);
+            fma8(acc[0], w.x, va[k], vb[k]);
+            fma8(acc[1], w.y, va[k], vb[k]);
+            fma8(acc[2], w.z, va[k], vb[k]);
+            fma8(acc[3], w.w, va[k], vb[k]);
+          }
+        }
+      }
+      e = end;
       // + bias, ReLU (vfa_op.py:123-124), sum over scales and views (vfanet.py:79, :82)
       const float4 bi0 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + lane * 4));
       const float4 bi1 = __ldg(reinterpret_cast<const float4*>(p.bias[s] + CH / 2 + lane * 4));
@@ -1323,10 +1536,63 @@ int fside_chunk_frames(const AggParams& p) {
   return (int)cb;
 }
 
-// workspace of the feature-side forward behind the prepared weights and tap records: [cover bitmap + need bytes][Y]
+// ---- texel lists of the quads (pool_list_kernel) --------------------------------------------------------------------------
+// VFA_POOL_LIST=0 selects the walking kernel (pool_quad_kernel) for the whole grid; VFA_POOL_LIST_CAP = list capacity in
+// entries per (view, scale, layer) of a quad's slot (default 16: 2.8 - 4.4 x the rigs' average; tests force overflows with 1).
+struct ListLayout {
+  size_t off_segoff, off_entoff, off_entw, total;
+  int n_quads, quads_x;
+  uint32_t slot;
+};
+static bool pool_list_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VFA_POOL_LIST");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    const char* q = getenv("VFA_POOL_QUAD");             // the one-cell-per-warp comparison kernel has no lists
+    if (q != nullptr && atoi(q) == 0) on = 0;
+  }
+  return on != 0;
+}
+static ListLayout list_layout(const AggParams& p) {
+  ListLayout L = {};
+  if (!pool_list_enabled() || p.V > 32) return L;        // the list builder runs one warp per view in one CTA
+  L.quads_x = (p.W + 1) / 2;
+  L.n_quads = L.quads_x * ((p.L + 1) / 2);
+  unsigned long long per = LIST_PER_ITER;
+  if (const char* e = getenv("VFA_POOL_LIST_CAP")) {
+    const long long c = atoll(e);
+    if (c > 0) per = (unsigned long long)c;
+  }
+  unsigned long long slot = per * (unsigned long long)(p.V * p.S * p.nl);
+  const unsigned long long most = 0xfffffff0ull / (unsigned long long)(L.n_quads > 0 ? L.n_quads : 1);
+  if (slot > most) slot = most;                          // entry indices are 32-bit
+  L.slot = (uint32_t)slot;
+  const size_t entries = (size_t)L.slot * L.n_quads;
+  size_t o = 0;
+  L.off_segoff = o; o += align256((size_t)L.n_quads * (p.V * p.S + 1) * sizeof(uint32_t));
+  L.off_entoff = o; o += align256(entries * sizeof(uint32_t));
+  L.off_entw = o;   o += align256(entries * sizeof(float4));
+  L.total = o;
+  return L;
+}
+
+// texel lists from the tap records (once per call: the projection is static, the lists serve every frame)
+static int launch_quad_lists(const AggParams& p, const TapRec* recs, void* list_ws, cudaStream_t st) {
+  const ListLayout L = list_layout(p);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(list_ws);
+  qlist_walk_kernel<<<L.n_quads, 32 * p.V, 0, st>>>(p, recs, L.quads_x, L.slot, reinterpret_cast<uint32_t*>(w8 + L.off_segoff),
+                                                    reinterpret_cast<uint32_t*>(w8 + L.off_entoff),
+                                                    reinterpret_cast<float*>(w8 + L.off_entw));
+  VFA_LAUNCH_CHECK("qlist_walk_kernel");
+  return VFA_OK;
+}
+
+// workspace of the feature-side forward behind the prepared weights and tap records:
+// [cover bitmap + need bytes + row lists][texel lists of the quads][Y]
 size_t fside_workspace_bytes(const AggParams& p) {
   const int cb = fside_chunk_frames(p);
-  return fside_cover_bytes(p, cb) + (size_t)cb * fside_y_bytes_per_frame(p);
+  return fside_cover_bytes(p, cb) + list_layout(p).total + (size_t)cb * fside_y_bytes_per_frame(p);
 }
 
 int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
@@ -1340,17 +1606,24 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     // three CTAs x 32 KB of partial sums per SM, the rest of the unified array as L1
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    VFA_CUDA(cudaFuncSetAttribute(pool_list_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    VFA_CUDA(cudaFuncSetAttribute(pool_list_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     attr_set = true;
   }
   const size_t per_frame = fside_y_bytes_per_frame(p);
+  const ListLayout LL = list_layout(p);
   int cb = fside_chunk_frames(p);
-  while (cb > 1 && fside_cover_bytes(p, cb) + (size_t)cb * per_frame > fs_bytes) --cb;
+  while (cb > 1 && fside_cover_bytes(p, cb) + LL.total + (size_t)cb * per_frame > fs_bytes) --cb;
   const size_t cover_bytes = fside_cover_bytes(p, cb);
-  if (cover_bytes + per_frame > fs_bytes) {
-    set_error("feature-side forward: workspace holds %zu bytes for Y, one frame needs %zu", fs_bytes, cover_bytes + per_frame);
+  if (cover_bytes + LL.total + per_frame > fs_bytes) {
+    set_error("feature-side forward: workspace holds %zu bytes for Y, one frame needs %zu", fs_bytes,
+              cover_bytes + LL.total + per_frame);
     return VFA_ERR_WORKSPACE;
   }
-  float* y_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fs_ws) + cover_bytes);
+  uint8_t* list_ws = reinterpret_cast<uint8_t*>(fs_ws) + cover_bytes;
+  float* y_ws = reinterpret_cast<float*>(list_ws + LL.total);
   // row-compacted GEMM unless VFA_FSIDE_COMPACT=0 (whole 256-row tiles, skipped by the need bytes) or VFA_FSIDE_NO_SKIP=1
   const char* ec = getenv("VFA_FSIDE_COMPACT");
   const char* en = getenv("VFA_FSIDE_NO_SKIP");
@@ -1359,6 +1632,8 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
     if (compact)
       if (int rc = launch_rowlists(p, fs_ws, cb, st)) return rc;
+    if (LL.total != 0 && !(variant & 64))
+      if (int rc = launch_quad_lists(p, recs, list_ws, st)) return rc;
   }
   const size_t es = bf16 ? 2 : 4;
   for (int b0 = 0; b0 < p.B; b0 += cb) {
@@ -1402,8 +1677,24 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
         const char* e = getenv("VFA_POOL_QUAD");
         quad = (e == nullptr || atoi(e) != 0) ? 1 : 0;
       }
-      if (quad) {
+      if (quad && LL.total != 0) {
         q.tiles_x = (p.W + 2 * QX - 1) / (2 * QX);
+        q.seg_off = reinterpret_cast<const uint32_t*>(list_ws + LL.off_segoff);
+        q.ent_off = reinterpret_cast<const uint32_t*>(list_ws + LL.off_entoff);
+        q.ent_w = reinterpret_cast<const float4*>(list_ws + LL.off_entw);
+        q.quads_x = LL.quads_x;
+        const dim3 grid(q.tiles_x * ((p.L + 2 * QY - 1) / (2 * QY)), nb);
+        if (p.mask != nullptr) {
+          pool_list_kernel<true><<<grid, QWARPS * 32, 0, st>>>(q);
+          pool_quad_kernel<true, true><<<grid, QWARPS * 32, 0, st>>>(q);
+        } else {
+          pool_list_kernel<false><<<grid, QWARPS * 32, 0, st>>>(q);
+          pool_quad_kernel<false, true><<<grid, QWARPS * 32, 0, st>>>(q);
+        }
+        VFA_LAUNCH_CHECK("pool_list_kernel");
+      } else if (quad) {
+        q.tiles_x = (p.W + 2 * QX - 1) / (2 * QX);
+        q.seg_off = nullptr;
         const dim3 grid(q.tiles_x * ((p.L + 2 * QY - 1) / (2 * QY)), nb);
         if (p.mask != nullptr)
           pool_quad_kernel<true><<<grid, QWARPS * 32, 0, st>>>(q);

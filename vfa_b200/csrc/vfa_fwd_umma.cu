@@ -834,6 +834,9 @@ size_t umma_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh, uint
     p.V = sh->n_views;
     p.nl = g->n_layers;
     p.S = sh->n_scales;
+    p.L = g->grid_l;                    // the quads' texel lists are sized by the grid
+    p.W = g->grid_w;
+    p.LW = g->grid_l * g->grid_w;
     for (int s = 0; s < sh->n_scales; ++s) {
       p.sc[s].fh = sh->feat_h[s];
       p.sc[s].fw = sh->feat_w[s];
