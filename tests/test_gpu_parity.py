@@ -336,6 +336,46 @@ def test_feature_side_chunking_and_ragged_grids(monkeypatch):
     monkeypatch.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
 
 
+def test_list_pooling_equals_walking_pooling_bit_for_bit(monkeypatch):
+    """The default pooling reads precomputed texel lists (pool_list_kernel); quads whose list does not fit its slot are
+    pooled by the walking kernel (pool_quad_kernel, completion pass).  Both apply the same weights in the same order, so
+    any split of the quads between them gives the same bits: default slots (every quad listed), slots of 1 and 3 entries
+    per iteration (most / some quads walked), for inference and for the training variant that writes the ReLU mask, on a
+    rig with an in-field camera (very large boxes) and a ragged grid."""
+    g = geometry.WILDTRACK
+    grid = geometry.grid_for(g)[3:80, 5:132].contiguous()             # 77 x 127 cells: odd on both sides
+    calibs = synthetic.ring_calibs(g, n_views=3, in_field=True)
+    V = calibs.shape[0]
+    params = synthetic.collapse_params(g, seed=8)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=V, seed=8)]
+    table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    monkeypatch.delenv('VFA_POOL_LIST_CAP', raising=False)
+    ref = vfa_b200.aggregate(feats, table, ws, bs)
+    assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
+    simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
+    ok, err = _within(ref.cpu().numpy().astype(np.float64), simt.cpu().numpy().astype(np.float64))
+    assert ok.all(), f'worst {err.max():.2e}'
+    gout = torch.randn(ref.shape, generator=torch.Generator(device='cuda').manual_seed(2), device='cuda')
+
+    def train_run():
+        f = [t.detach().clone().requires_grad_(True) for t in feats]
+        out = vfa_b200.aggregate(f, table, ws, bs)
+        out.backward(gout)
+        return out.detach(), f[0].grad
+
+    out_t, grad_t = train_run()
+    assert torch.equal(out_t, ref)
+    for cap in ('1', '3'):
+        monkeypatch.setenv('VFA_POOL_LIST_CAP', cap)
+        assert torch.equal(vfa_b200.aggregate(feats, table, ws, bs), ref), f'slot of {cap} entries per iteration'
+        out_c, grad_c = train_run()
+        assert torch.equal(out_c, ref)
+        # same ReLU mask -> same masked gradient (the backward's atomics reorder sums: compare to rounding)
+        assert float((grad_c - grad_t).abs().max()) <= 1e-5 * float(grad_t.abs().max())
+    monkeypatch.delenv('VFA_POOL_LIST_CAP', raising=False)
+
+
 def test_relu_mask_agrees_between_formulations():
     """The ReLU pass bits the backward consumes: feature-side and grid-side forwards may only disagree where the
     pre-activation is within rounding of zero."""

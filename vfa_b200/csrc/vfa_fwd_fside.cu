@@ -698,9 +698,9 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
 // ---- pooling of Y from precomputed texel lists ------------------------------------------------------------------------
 // pool_quad_kernel spends ~60 instructions per texel it loads -- records, union bounds, row / column weights, ballots and
 // shuffles around 2 loads and 16 packed FMAs -- and every pass over (at most) two texels of a union row waits for a full
-// memory round trip.  The projection is static, so that bookkeeping is done ONCE per table by qlist_walk_kernel: per
+// memory round trip.  The projection is static, so that bookkeeping is done ONCE per table by qlist_build_kernel: per
 // (quad, view, scale) segment the covered texels of all layers in the order pool_quad_kernel visits them, each with its
-// texel index and the four cell weights (qlist_walk_kernel).  The hot kernel is then a flat loop -- uniform loads of (index, weights), two
+// texel index and the four cell weights (qlist_build_kernel).  The hot kernel is then a flat loop -- uniform loads of (index, weights), two
 // 128-bit loads of the texel row, 16 packed FMAs -- with LIST_BATCH texels in flight whatever the shape of the union,
 // and its sums are bit-identical to the walking kernel's (same weights, same order).
 #ifndef VFA_LIST_BATCH
@@ -712,53 +712,73 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
 constexpr int LB = VFA_LIST_BATCH;
 constexpr uint32_t LIST_PER_ITER = 16;      // slot of a quad: entries per (view, scale, layer) on average
 
-// The walk of one (quad, view): FILL = false counts the entries of its S * nl iterations, FILL = true writes them from
-// absolute index `first` on and the starts of the view's S segments.  Up to the ballot this is the arithmetic of
-// pool_quad_kernel, instruction for instruction.
+// One (quad, view, scale, layer) iteration of the walk, done by ONE thread (the warp-cooperative form of pool_quad_kernel
+// costs ~300 warp instructions per iteration; here a warp instruction serves 32 iterations).  Weights and visiting order
+// are those of pool_quad_kernel: wl = wy * wx per cell, column blocks of 8, rows, columns; a texel is listed when any of
+// the four weights is non-zero.  FILL = false counts the entries, FILL = true writes them from absolute index `first`.
 template <bool FILL>
-__device__ __forceinline__ uint32_t qlist_walk_view(const AggParams& p, const uint4* rp, size_t rec_stride, bool my_valid, int lane,
-                                                    uint32_t first, uint32_t* __restrict__ so_v, uint32_t* __restrict__ ent_off,
-                                                    float* __restrict__ ent_w) {
-  const int cl = lane & 3, jl = lane >> 2;
-  uint4 n0 = __ldg(rp), n1 = __ldg(rp + 1);             // record of (s, n) = (0, 0), prefetched one step ahead
-  const int iters = p.S * p.nl;
-  int j_rec = 0;
+__device__ __forceinline__ uint32_t qlist_iter(const AggParams& p, const TapRec* __restrict__ recs, int quads_x, int q, int it,
+                                               uint32_t first, uint32_t* __restrict__ ent_off, float4* __restrict__ ent_w) {
+  const int n = it % p.nl, s = (it / p.nl) % p.S;
+  const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
+  const int cy0 = 2 * (q / quads_x), cx0 = 2 * (q % quads_x);
+  int nx[4], ny[4], x0[4], y0[4];
+  float wxf[4], wxl[4], wyf[4], wyl[4], wym[4];
+  int ux0 = 0x7fff, uy0 = 0x7fff, ux1 = -1, uy1 = -1;
+  bool odd = false;                                      // a non-finite row weight: no shortcut on the columns
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const bool valid = cy0 + (c >> 1) < p.L && cx0 + (c & 1) < p.W;
+    const int cell = valid ? (cy0 + (c >> 1)) * p.W + cx0 + (c & 1) : cy0 * p.W + cx0;
+    const uint4* rp = reinterpret_cast<const uint4*>(recs + (size_t)it * p.LW + cell);      // recs[v][s][n][cell]
+    const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    nx[c] = valid ? ((int)r0.y & 0xffff) : 0;
+    ny[c] = (int)r0.y >> 16;
+    x0[c] = (int)r0.x & 0xffff;
+    y0[c] = (int)r0.x >> 16;
+    wxf[c] = __uint_as_float(r0.z);
+    wxl[c] = __uint_as_float(r0.w);
+    wyf[c] = __uint_as_float(r1.x);
+    wyl[c] = __uint_as_float(r1.y);
+    wym[c] = __uint_as_float(r1.z);
+    odd = odd || !(isfinite(wyf[c]) && isfinite(wyl[c]) && isfinite(wym[c]));
+    if (nx[c] != 0) {
+      ux0 = min(ux0, x0[c]);
+      uy0 = min(uy0, y0[c]);
+      ux1 = max(ux1, x0[c] + nx[c] - 1);
+      uy1 = max(uy1, y0[c] + ny[c] - 1);
+    }
+  }
+  if (ux1 < 0) return 0u;
   uint32_t total = 0;
-  for (int s = 0; s < p.S; ++s) {
-    const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
-    if (FILL && lane == 0) so_v[s] = first + total;
-    for (int n = 0; n < p.nl; ++n, ++j_rec) {
-      const uint4 r0 = n0, r1 = n1;
-      if (j_rec + 1 < iters) {
-        rp += rec_stride;
-        n0 = __ldg(rp);
-        n1 = __ldg(rp + 1);
+  for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
+    // past ux1 every column weight is 0, so a finite row weight gives wl = 0: those columns hold no entry
+    const int jmax = odd ? 7 : min(7, ux1 - ux0 - cb);
+    for (int ty = uy0; ty <= uy1; ++ty) {
+      float wy[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ry = ty - y0[c];
+        wy[c] = (ry >= 0 && ry < ny[c]) ? (ry == 0 ? wyf[c] : (ry == ny[c] - 1 ? wyl[c] : wym[c])) : 0.f;
       }
-      const int nx = my_valid ? ((int)r0.y & 0xffff) : 0, ny = (int)r0.y >> 16;
-      const int x0 = (int)r0.x & 0xffff, y0 = (int)r0.x >> 16;
-      const bool vis = nx != 0;
-      const int ux1 = __reduce_max_sync(0xffffffffu, vis ? x0 + nx - 1 : -1);
-      if (ux1 < 0) continue;
-      const int ux0 = __reduce_min_sync(0xffffffffu, vis ? x0 : 0x7fff);
-      const int uy0 = __reduce_min_sync(0xffffffffu, vis ? y0 : 0x7fff);
-      const int uy1 = __reduce_max_sync(0xffffffffu, vis ? y0 + ny - 1 : -1);
-      const float wx_first = __uint_as_float(r0.z), wx_last = __uint_as_float(r0.w);
-      const float wy_first = __uint_as_float(r1.x), wy_last = __uint_as_float(r1.y), wy_mid = __uint_as_float(r1.z);
-      for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
-        const int rx = ux0 + cb + jl - x0;
-        const float wx = (vis && rx >= 0 && rx < nx) ? (rx == 0 ? wx_first : (rx == nx - 1 ? wx_last : 1.0f)) : 0.f;
-        for (int ty = uy0; ty <= uy1; ++ty) {
-          const int ry = ty - y0;
-          const float wy = (ry >= 0 && ry < ny) ? (ry == 0 ? wy_first : (ry == ny - 1 ? wy_last : wy_mid)) : 0.f;
-          const float wl = __fmul_rn(wy, wx);
-          const uint32_t bm = __ballot_sync(0xffffffffu, wl != 0.f);     // bit 4*j + c
-          const uint32_t cov = (bm | (bm >> 1) | (bm >> 2) | (bm >> 3)) & 0x11111111u;     // bit 4*j: texel j is pooled
-          if (FILL && ((cov >> (4 * jl)) & 1u)) {
-            const size_t k = (size_t)first + total + __popc(cov & ((1u << (4 * jl)) - 1u));
-            ent_w[k * 4 + cl] = wl;
-            if (cl == 0) ent_off[k] = (uint32_t)(n * hw + ty * fw + ux0 + cb + jl);
+      for (int j = 0; j <= jmax; ++j) {
+        const int tx = ux0 + cb + j;
+        float wl[4];
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int rx = tx - x0[c];
+          const float wx = (nx[c] != 0 && rx >= 0 && rx < nx[c]) ? (rx == 0 ? wxf[c] : (rx == nx[c] - 1 ? wxl[c] : 1.0f)) : 0.f;
+          wl[c] = __fmul_rn(wy[c], wx);
+          any = any || wl[c] != 0.f;
+        }
+        if (any) {
+          if (FILL) {
+            const size_t k = (size_t)first + total;
+            ent_off[k] = (uint32_t)(n * hw + ty * fw + tx);
+            ent_w[k] = make_float4(wl[0], wl[1], wl[2], wl[3]);
           }
-          total += __popc(cov);
+          ++total;
         }
       }
     }
@@ -766,39 +786,56 @@ __device__ __forceinline__ uint32_t qlist_walk_view(const AggParams& p, const ui
   return total;
 }
 
-// One CTA per quad, one warp per view: count, exchange the counts through shared memory, fill.  The quad's entries go into
-// its own slot of `slot` entries (no global scan); a quad whose texels do not fit is marked LIST_OVERFLOW, gets no entries
-// and is pooled by pool_quad_kernel<.., OVF> -- exact for any rig, no host synchronisation, static workspace.
-__global__ void __launch_bounds__(1024) qlist_walk_kernel(const AggParams p, const TapRec* __restrict__ recs, int quads_x,
+// LIST_QPB consecutive quads per CTA, one thread per (iteration, quad) with the quad index fastest -- the records of one
+// iteration are contiguous along a BEV row, so a warp's record loads coalesce (walking one quad per warp reads a different
+// 32-byte record 0.8 MB apart in every iteration): count, per-quad exclusive scan in shared memory, segment table, fill.
+// The quad's entries go into its own slot of `slot` entries (no global scan); a quad whose texels do not fit is marked
+// LIST_OVERFLOW, gets no entries and is pooled by pool_quad_kernel<.., OVF> -- exact for any rig, no host synchronisation,
+// static workspace.
+constexpr int LIST_QPB = 16;
+constexpr int LIST_PAD = LIST_QPB + 1;                   // row stride of the counters: conflict-free both ways
+__global__ void __launch_bounds__(256) qlist_build_kernel(const AggParams p, const TapRec* __restrict__ recs, int quads_x, int n_quads,
                                                           uint32_t slot, uint32_t* __restrict__ seg_off,
-                                                          uint32_t* __restrict__ ent_off, float* __restrict__ ent_w) {
-  __shared__ uint32_t cnt_s[32];
-  const int lane = threadIdx.x & 31, v = threadIdx.x >> 5;          // blockDim.x = 32 * V
-  const int q = blockIdx.x;
-  const int VS = p.V * p.S;
-  const int cy0 = 2 * (q / quads_x), cx0 = 2 * (q % quads_x);
-  const int cl = lane & 3;
-  const bool my_valid = cy0 + (cl >> 1) < p.L && cx0 + (cl & 1) < p.W;
-  const int my_cell = my_valid ? (cy0 + (cl >> 1)) * p.W + cx0 + (cl & 1) : cy0 * p.W + cx0;
-  const size_t rec_stride = (size_t)p.LW * (sizeof(TapRec) / sizeof(uint4));
-  const uint4* rp = reinterpret_cast<const uint4*>(recs + my_cell) + (size_t)v * p.S * p.nl * rec_stride;
-  uint32_t* const so = seg_off + (size_t)q * (VS + 1);
-  const uint32_t mine = qlist_walk_view<false>(p, rp, rec_stride, my_valid, lane, 0u, nullptr, nullptr, nullptr);
-  if (lane == 0) cnt_s[v] = mine;
+                                                          uint32_t* __restrict__ ent_off, float4* __restrict__ ent_w) {
+  extern __shared__ uint32_t pre_s[];                    // [iters][LIST_PAD] counts -> exclusive prefixes, [LIST_QPB] totals
+  const int VS = p.V * p.S, iters = VS * p.nl;
+  uint32_t* const tot_s = pre_s + iters * LIST_PAD;
+  const int q0 = blockIdx.x * LIST_QPB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int item = threadIdx.x; item < LIST_QPB * iters; item += blockDim.x) {
+    const int ql = item % LIST_QPB, it = item / LIST_QPB, q = q0 + ql;
+    pre_s[it * LIST_PAD + ql] = q < n_quads ? qlist_iter<false>(p, recs, quads_x, q, it, 0u, nullptr, nullptr) : 0u;
+  }
   __syncthreads();
-  uint32_t before = 0, all = 0;
-  for (int u = 0; u < p.V; ++u) {
-    const uint32_t c = cnt_s[u];
-    before += u < v ? c : 0u;
-    all += c;
+  for (int ql = warp; ql < LIST_QPB; ql += blockDim.x >> 5) {        // a warp scans the iterations of one quad
+    uint32_t* c = pre_s + ql;
+    uint32_t carry = 0;
+    for (int i0 = 0; i0 < iters; i0 += 32) {
+      const int i = i0 + lane;
+      const uint32_t x = i < iters ? c[i * LIST_PAD] : 0u;
+      uint32_t inc = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (i < iters) c[i * LIST_PAD] = carry + inc - x;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) tot_s[ql] = carry;
   }
-  if (all > slot) {
-    if (threadIdx.x == 0) so[VS] = LIST_OVERFLOW;
-    return;
+  __syncthreads();
+  for (int item = threadIdx.x; item < LIST_QPB * (VS + 1); item += blockDim.x) {
+    const int ql = item / (VS + 1), i = item % (VS + 1), q = q0 + ql;
+    if (q >= n_quads) continue;
+    const uint32_t base = (uint32_t)q * slot, tot = tot_s[ql];
+    seg_off[(size_t)q * (VS + 1) + i] = i < VS ? base + pre_s[i * p.nl * LIST_PAD + ql] : (tot <= slot ? base + tot : LIST_OVERFLOW);
   }
-  const uint32_t base = (uint32_t)q * slot;
-  qlist_walk_view<true>(p, rp, rec_stride, my_valid, lane, base + before, so + v * p.S, ent_off, ent_w);
-  if (threadIdx.x == 0) so[VS] = base + all;
+  for (int item = threadIdx.x; item < LIST_QPB * iters; item += blockDim.x) {
+    const int ql = item % LIST_QPB, it = item / LIST_QPB, q = q0 + ql;
+    if (q >= n_quads || tot_s[ql] > slot) continue;
+    qlist_iter<true>(p, recs, quads_x, q, it, (uint32_t)q * slot + pre_s[it * LIST_PAD + ql], ent_off, ent_w);
+  }
 }
 
 template <bool MASK>
@@ -1556,7 +1593,8 @@ static bool pool_list_enabled() {
 }
 static ListLayout list_layout(const AggParams& p) {
   ListLayout L = {};
-  if (!pool_list_enabled() || p.V > 32) return L;        // the list builder runs one warp per view in one CTA
+  // the builder keeps LIST_PAD * V * S * nl counters in (default-sized) shared memory
+  if (!pool_list_enabled() || ((size_t)LIST_PAD * p.V * p.S * p.nl + LIST_QPB) * sizeof(uint32_t) > 40960) return L;
   L.quads_x = (p.W + 1) / 2;
   L.n_quads = L.quads_x * ((p.L + 1) / 2);
   unsigned long long per = LIST_PER_ITER;
@@ -1581,10 +1619,11 @@ static ListLayout list_layout(const AggParams& p) {
 static int launch_quad_lists(const AggParams& p, const TapRec* recs, void* list_ws, cudaStream_t st) {
   const ListLayout L = list_layout(p);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(list_ws);
-  qlist_walk_kernel<<<L.n_quads, 32 * p.V, 0, st>>>(p, recs, L.quads_x, L.slot, reinterpret_cast<uint32_t*>(w8 + L.off_segoff),
-                                                    reinterpret_cast<uint32_t*>(w8 + L.off_entoff),
-                                                    reinterpret_cast<float*>(w8 + L.off_entw));
-  VFA_LAUNCH_CHECK("qlist_walk_kernel");
+  const size_t smem = ((size_t)LIST_PAD * p.V * p.S * p.nl + LIST_QPB) * sizeof(uint32_t);
+  qlist_build_kernel<<<(L.n_quads + LIST_QPB - 1) / LIST_QPB, 256, smem, st>>>(
+      p, recs, L.quads_x, L.n_quads, L.slot, reinterpret_cast<uint32_t*>(w8 + L.off_segoff),
+      reinterpret_cast<uint32_t*>(w8 + L.off_entoff), reinterpret_cast<float4*>(w8 + L.off_entw));
+  VFA_LAUNCH_CHECK("qlist_build_kernel");
   return VFA_OK;
 }
 
