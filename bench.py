@@ -5,15 +5,16 @@
     python bench.py --impl reference ...                     # the reference algorithm on the box's host cores
 
 One "step" = one pass of the hot path over one batch of synthetic frames:
-    projection table (1 launch) + weight re-layout (3) + tap records (1) + image-plane 3xTF32 GEMM (1) + quad pooling with
-    bias / ReLU / view-and-scale sum (1)   [--flags 32: one fused grid-side kernel instead of the last two].
+    projection table (1 launch) + weight re-layout (3) + tap records (1) + coverage / row lists / unit table (3) + texel lists
+    of the quads (1) + image-plane 3xTF32 GEMM over the covered rows (1) + pooling from the lists with bias / ReLU / view-and-
+    scale sum (1) + its completion pass (1)   [--flags 32: one fused grid-side kernel instead of the last seven].
 Default workload: MultiviewC-shaped (7 views, 1280x720 source, stride-8/16/32 maps 90x160 / 45x80 / 23x40, C = 256,
 156x156x5 voxel grid = the shipped config-of-record of "37.5 m x 37.5 m"), B frames per GPU.
 Multi-GPU = batch data parallel (frames are independent: no data-path collective, weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same through the public
 API with pinned-host inputs and a device->host read of the result inside the timed region; `roofline` describes the
-dominant kernel (pool_quad_kernel; the GEMM under `second_kernel`, the whole step under `step`); `cpu_baseline` = the oracle's torch-CPU port of the reference timed on the host cores (N = 1 only).
+dominant kernel (pool_list_kernel; the GEMM under `second_kernel`, the whole step under `step`); `cpu_baseline` = the oracle's torch-CPU port of the reference timed on the host cores (N = 1 only).
 """
 import argparse
 import json
@@ -445,10 +446,9 @@ def main():
     for _ in range(max(3, args.warmup)):
         step()
     path = vfa_b200.last_kernel_path()
-    # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | per frame chunk: ygemm + pool_quad}
     # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | coverage bitmap + row lists + unit table +
-    # per frame chunk: compacted ygemm + pool_quad}
-    launches_per_step = 5 + (3 + 2 * nums['fside_chunks'] if path.startswith('fside') else 1)
+    # texel lists + per frame chunk: compacted ygemm + pool_list + its completion pass (pool_quad_kernel<OVF>)}
+    launches_per_step = 5 + (4 + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
     if args.mode == 'views':                          # every frame chunk is a complete call (table and weights included)
         launches_per_step *= -(-B // (args.view_chunk or B))
     barrier()
@@ -479,7 +479,7 @@ def main():
     if path.startswith('fside') and args.mode == 'dp' and not args.backward:
         table = vfa_b200.build_table(cgeom, calibs, grid)
         per_kernel = {}
-        for kname, bits in (('ygemm_kernel', 64 | 256), ('pool_quad_kernel', 128 | 256), ('ygemm_kernel_all_tiles', 64)):
+        for kname, bits in (('ygemm_kernel', 64 | 256), ('pool_list_kernel', 128 | 256), ('ygemm_kernel_all_tiles', 64)):
             os.environ['VFA_UMMA_VARIANT'] = str(bits)
             if kname == 'ygemm_kernel_all_tiles':        # every (tile, layer) multiplied: the GEMM's own efficiency
                 os.environ['VFA_FSIDE_NO_SKIP'] = '1'
@@ -562,11 +562,12 @@ def main():
             return None if per_frame is None else per_frame * B / nums['fside_chunks']
 
         if per_kernel is not None:
-            # dominant kernel: the pooling of Y.  Its compulsory HBM traffic per launch: Y once, the tap records once,
-            # the output once.  (What actually binds it is the SM-side gather: L1 data pipe and issue slots.)
+            # dominant kernel: the pooling of Y from the quads' texel lists.  Its compulsory HBM traffic per launch: Y once,
+            # the list entries once (taken as the tap records' bytes: 20 B per listed texel is 74 MB on this rig, the records
+            # 82 MB), the output once.  (What actually binds it is the L1 data pipe: two 4-line loads per texel row.)
             frames = B / nums['fside_chunks']
             pool_bytes = (nums['y_bytes'] + nums['out_bytes']) / nums['fside_chunks'] + nums['rec_bytes']
-            t_pool, t_gemm = per_kernel['pool_quad_kernel'], per_kernel['ygemm_kernel']
+            t_pool, t_gemm = per_kernel['pool_list_kernel'], per_kernel['ygemm_kernel']
             pool_gbs = pool_bytes / (t_pool * 1e-3) / 1e9
             # the GEMM multiplies only the texel rows some box pools (compacted row lists); its tensor-core efficiency is quoted
             # on the run that multiplies every row (VFA_FSIDE_NO_SKIP=1, ygemm_kernel; that run also carries the tap-record /
@@ -576,14 +577,15 @@ def main():
             step_bytes = nums['bytes'] + 2 * nums['y_bytes'] + nums['rec_bytes']
             roofline = {
                 'bound': 'hbm', 'achieved': pool_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': pool_gbs / peaks['hbm_gbs'], 'traffic': traffic_of('pool_quad_kernel'),
-                'kernel': 'pool_quad_kernel', 'kernel_ms': t_pool, 'frames_per_launch': frames,
+                'frac': pool_gbs / peaks['hbm_gbs'], 'traffic': traffic_of('pool_list_kernel'),
+                'kernel': 'pool_list_kernel', 'kernel_ms': t_pool, 'frames_per_launch': frames,
                 'kernel_share_of_step': t_pool * nums['fside_chunks'] * args.steps / total_ms,
                 'algorithmic_bytes_per_launch': pool_bytes,
                 'peak_source': peaks['source'],
-                'note': 'pooling of the per-layer products Y (fp32 [plane, layer, texel, C]): algorithmic bytes = Y once + tap '
-                        'records once + output once; the kernel is bound by the SM-side gather (L1 data pipe 72 % busy, '
-                        'profiles/r1_fside_ncu_full.json), not by HBM',
+                'note': 'pooling of the per-layer products Y (fp32 [plane, layer, texel, C]) from precomputed texel lists: '
+                        'algorithmic bytes = Y once + list entries once + output once; the kernel is bound by the L1 data pipe '
+                        '(70 % busy: every texel row is two 4-line loads, L1 hit rate 34 %, 11 GB per launch from L2; '
+                        'profiles/r1_pool_list_ncu_full.json), not by HBM',
                 'second_kernel': {
                     'kernel': 'ygemm_compact_kernel', 'bound': 'tensor', 'achieved': gemm_tflops, 'peak': peaks['tflops'],
                     'unit': 'TFLOP/s', 'frac': gemm_tflops / peaks['tflops'], 'kernel_ms': t_gemm,
