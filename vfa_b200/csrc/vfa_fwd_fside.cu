@@ -786,15 +786,22 @@ __device__ __forceinline__ uint32_t qlist_iter(const AggParams& p, const TapRec*
   return total;
 }
 
-// LIST_QPB consecutive quads per CTA, one thread per (iteration, quad) with the quad index fastest -- the records of one
+// LIST_QPB (8: 761 CTAs of 3 per SM on the MultiviewC grid; 16 quads at 2 CTAs per SM: 0.19 instead of 0.145 ms)
+// consecutive quads per CTA, one thread per (iteration, quad) with the quad index fastest -- the records of one
 // iteration are contiguous along a BEV row, so a warp's record loads coalesce (walking one quad per warp reads a different
 // 32-byte record 0.8 MB apart in every iteration): count, per-quad exclusive scan in shared memory, segment table, fill.
 // The quad's entries go into its own slot of `slot` entries (no global scan); a quad whose texels do not fit is marked
 // LIST_OVERFLOW, gets no entries and is pooled by pool_quad_kernel<.., OVF> -- exact for any rig, no host synchronisation,
 // static workspace.
-constexpr int LIST_QPB = 16;
+#ifndef VFA_LIST_QPB
+#define VFA_LIST_QPB 8
+#endif
+#ifndef VFA_LIST_BUILD_MINBLOCKS
+#define VFA_LIST_BUILD_MINBLOCKS 3
+#endif
+constexpr int LIST_QPB = VFA_LIST_QPB;
 constexpr int LIST_PAD = LIST_QPB + 1;                   // row stride of the counters: conflict-free both ways
-__global__ void __launch_bounds__(256) qlist_build_kernel(const AggParams p, const TapRec* __restrict__ recs, int quads_x, int n_quads,
+__global__ void __launch_bounds__(256, VFA_LIST_BUILD_MINBLOCKS) qlist_build_kernel(const AggParams p, const TapRec* __restrict__ recs, int quads_x, int n_quads,
                                                           uint32_t slot, uint32_t* __restrict__ seg_off,
                                                           uint32_t* __restrict__ ent_off, float4* __restrict__ ent_w) {
   extern __shared__ uint32_t pre_s[];                    // [iters][LIST_PAD] counts -> exclusive prefixes, [LIST_QPB] totals
