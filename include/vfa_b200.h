@@ -76,7 +76,8 @@ typedef struct {
                                         gather bytes; pooling / collapse arithmetic is unchanged (fp32, 3xTF32)    */
 #define VFA_FLAG_GRID_SIDE    32u    /* C = 256: use the fully fused grid-side kernel (pool, then contract; no
                                         intermediate at all) instead of the default feature-side pair of kernels
-                                        (contract on the image plane, then pool; Y of a frame chunk in the workspace) */
+                                        (contract on the image plane, then pool from per-quad texel lists; Y of a
+                                        frame chunk and the lists live in the workspace)                            */
 
 int vfa_version(void);
 const char* vfa_last_error(void);
@@ -102,7 +103,9 @@ int vfa_table_scale(const float* d_boxes, int64_t n_boxes, int32_t feat_h, int32
 int vfa_nchw_to_nhwc(const float* d_src, float* d_dst, int64_t n, int32_t channels, int64_t hw, void* stream);
 int vfa_nhwc_to_nchw(const float* d_src, float* d_dst, int64_t n, int32_t channels, int64_t hw, void* stream);
 
-/* Bytes of scratch vfa_aggregate_fwd / _bwd need for this problem (prepared weights etc.). */
+/* Bytes of scratch vfa_aggregate_fwd / _bwd need for this problem: prepared weights, tap records, coverage bitmap and
+ * row lists, the quads' texel lists, Y of one frame chunk (forward); CSR, masked gradients, Gs (backward).  Pure host
+ * arithmetic on (geom, shape, flags). */
 size_t vfa_aggregate_workspace_bytes(const vfa_geometry_t* geom, const vfa_shape_t* shape, uint32_t flags);
 
 /* Re-lays the collapse weights for the kernel family `flags` selects (column permutation c*nl+n -> n*C+c,
