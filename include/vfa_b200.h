@@ -79,6 +79,10 @@ typedef struct {
                                         (contract on the image plane, then pool from per-quad texel lists; Y of a
                                         frame chunk and the lists live in the workspace)                            */
 
+#define VFA_FLAG_TABLE_PREPARED 64u  /* C = 256 forward: the workspace still holds what the previous vfa_aggregate_fwd
+                                        call derived from the SAME boxes, shapes and flags (tap records, coverage bitmap,
+                                        row lists, the quads' texel lists) -- static cameras: skip rebuilding them      */
+
 int vfa_version(void);
 const char* vfa_last_error(void);
 

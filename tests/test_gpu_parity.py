@@ -504,3 +504,47 @@ def test_cameras_that_see_nothing_backward():
     for b in bs:
         want = (gout.sum(dim=(0, 2, 3)) * 2) * (b.detach() > 0)           # 2 views; relu passes where bias > 0
         torch.testing.assert_close(b.grad, want, rtol=1e-5, atol=1e-4)
+
+
+def test_graphed_aggregator_replays_the_eager_call_bit_for_bit():
+    """GraphedAggregator: table + forward captured once in a CUDA graph; replays with new features and new calibrations
+    (the table is rebuilt inside the graph) equal the eager call sequence exactly."""
+    g = geometry.MULTIVIEWC
+    grid = geometry.grid_for(g)[::3, ::3].contiguous().cuda()
+    calibs = synthetic.ring_calibs(g, n_views=3).cuda()
+    params = synthetic.collapse_params(g, seed=6)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    feats = [f.cuda().permute(0, 1, 3, 4, 2).contiguous() for f in synthetic.features(g, batch=2, n_views=3, seed=6)]
+    geom = _geom(g.name, grid.shape[:2])
+    ga = vfa_b200.GraphedAggregator(geom, [tuple(f.shape) for f in feats], ws, bs)
+    ga.load(feats, calibs, grid)
+    ga.capture()
+    other = [torch.flip(f, dims=[3]).contiguous() for f in feats]
+    for f, c in ((feats, calibs), (other, calibs.roll(1, 0).contiguous()), (feats, calibs)):
+        want = vfa_b200.aggregate(f, vfa_b200.build_table(geom, c, grid), ws, bs, channels_last=True)
+        got = ga(f, c)
+        assert torch.equal(got, want)
+
+
+def test_table_prepared_flag_reuses_the_workspace_bit_for_bit():
+    """VFA_FLAG_TABLE_PREPARED (static cameras): the second call with the same table, shapes, flags and workspace skips
+    the tap records / coverage / row lists / texel lists and must give the bits of a full call, on new features too."""
+    g = geometry.MULTIVIEWX
+    grid = geometry.grid_for(g)[::2, ::2].contiguous().cuda()
+    calibs = synthetic.ring_calibs(g, n_views=3).cuda()
+    params = synthetic.collapse_params(g, seed=12)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    feats = [f.cuda().permute(0, 1, 3, 4, 2).contiguous() for f in synthetic.features(g, batch=2, n_views=3, seed=12)]
+    other = [torch.flip(f, dims=[2]).contiguous() for f in feats]
+    geom = _geom(g.name, grid.shape[:2])
+    table = vfa_b200.build_table(geom, calibs, grid)
+    shape = vfa_b200.make_shape(feats, geom.n_layers)
+    wsp = vfa_b200.workspace_for(geom, shape, 0, feats[0].device)
+    vfa_b200.prepare_weights(geom, shape, ws, 0, workspace=wsp)
+    full = [vfa_b200.aggregate_forward_raw(f, table, ws, bs, 0, workspace=wsp, prepared=True).clone() for f in (feats, other)]
+    assert not torch.equal(full[0], full[1])
+    for f, want in ((other, full[1]), (feats, full[0])):
+        got = vfa_b200.aggregate_forward_raw(f, table, ws, bs, 0, workspace=wsp, prepared=True, table_prepared=True)
+        assert torch.equal(got, want)
+    with pytest.raises(ValueError, match='workspace'):
+        vfa_b200.aggregate_forward_raw(feats, table, ws, bs, 0, table_prepared=True)

@@ -8,11 +8,12 @@ entry, `MultiScaleVFA` the same as an nn.Module (feats [B,V,C,H,W] per scale, ca
 """
 from . import geometry, synthetic                                    # noqa: F401
 from ._lib import (VFAError, FLAG_BF16_MMA, FLAG_FORCE_SIMT, FLAG_FORCE_UMMA,   # noqa: F401
-                   FLAG_WEIGHTS_PREPARED, FLAG_BF16_FEATURES, FLAG_GRID_SIDE)
+                   FLAG_WEIGHTS_PREPARED, FLAG_BF16_FEATURES, FLAG_GRID_SIDE, FLAG_TABLE_PREPARED)
 from .vfa_op import (VFA, ProjectionTable, aggregate, aggregate_forward_raw, build_table, last_kernel_path,  # noqa: F401
                      make_geometry, make_shape, prepare_weights, to_channels_last, workspace_for)
 
 from .streaming import StreamingAggregator                          # noqa: F401
+from .graphed import GraphedAggregator                              # noqa: F401
 from .vfanet import MultiScaleVFA                                   # noqa: F401
 
 __version__ = '0.1.0'

@@ -872,6 +872,7 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, size_t 
   a.p = p;
   const char* var = getenv("VFA_UMMA_VARIANT");
   a.variant = var ? atoi(var) : 0;
+  if (flags & VFA_FLAG_TABLE_PREPARED) a.variant |= 256;      // static cameras: records / coverage / lists are still valid
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   for (int s = 0; s < VFA_MAX_SCALES; ++s) a.wprep[s] = reinterpret_cast<const uint8_t*>(ws) + (s < p.S ? s : 0) * per_scale;
   // gather recipes of every (view, scale, layer, cell): behind the prepared weights in the workspace

@@ -163,9 +163,11 @@ def prepare_weights(geom, shape, weights, flags=0, workspace=None) -> torch.Tens
 
 
 def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, workspace=None, prepared=False,
-                          relu_mask=None):
+                          relu_mask=None, table_prepared=False):
     """No-autograd forward on channels-last features [B,V,fH,fW,C]: one C-ABI call on the current stream.
-    relu_mask: optional int32 tensor [B,V,S,ceil(C/32),L*W] receiving the ReLU pass bits for the backward."""
+    relu_mask: optional int32 tensor [B,V,S,ceil(C/32),L*W] receiving the ReLU pass bits for the backward.
+    table_prepared: `workspace` was used by the previous call with the same table, shapes and flags (static cameras): the
+    tap records, coverage and texel lists in it are reused instead of rebuilt (VFA_FLAG_TABLE_PREPARED)."""
     geom = table.geom
     shape = make_shape(feats_cl, geom.n_layers)
     dev = feats_cl[0].device
@@ -173,6 +175,10 @@ def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, w
         out = torch.empty(shape.batch, shape.channels, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
     ws = workspace if workspace is not None else workspace_for(geom, shape, flags, dev)
     f = int(flags) | (_lib.FLAG_WEIGHTS_PREPARED if prepared else 0)
+    if table_prepared:
+        if workspace is None:
+            raise ValueError('table_prepared=True needs the workspace of the previous call')
+        f |= _lib.FLAG_TABLE_PREPARED
     if feats_cl[0].dtype == torch.bfloat16:
         f |= _lib.FLAG_BF16_FEATURES
     with torch.cuda.device(dev):
