@@ -174,3 +174,24 @@ def test_network_module_has_the_reference_checkpoint_layout():
     # no CPU path: the aggregation raises on host tensors
     with pytest.raises(Exception):
         net(torch.rand(1, 3, 704, 704), torch.rand(1, 3, 4), torch.zeros(1, 4, 4, 3))
+
+
+def test_network_pretrained_trunk_takes_the_matching_checkpoint_entries(monkeypatch):
+    """pretrained=True (reference train.py:90, resnet.py:150-180): entries of the ImageNet checkpoint whose names and
+    shapes the trunk knows are loaded (BatchNorm scale / shift -> GroupNorm), everything else is ignored."""
+    from types import SimpleNamespace
+    from vfa_b200 import network
+    fake = {'conv1.weight': torch.full((64, 3, 7, 7), 0.25), 'bn1.weight': torch.full((64,), 2.0),
+            'bn1.running_mean': torch.zeros(64), 'layer1.0.conv1.weight': torch.full((64, 64, 3, 3), -0.5),
+            'layer2.0.downsample.1.bias': torch.full((128,), 0.125), 'fc.weight': torch.zeros(1000, 512),
+            'layer4.1.conv2.weight': torch.zeros(3, 3)}                       # wrong shape: skipped
+    seen = []
+    monkeypatch.setattr(torch.hub, 'load_state_dict_from_url', lambda url, **kw: (seen.append(url), fake)[1])
+    args = SimpleNamespace(data='MultiviewC', image_size=(720, 1280))
+    net = network.VFANet(args, 'resnet18', 160, (25, 25, 32), 360, '2D', pretrained=True)
+    assert seen == [network._IMAGENET['resnet18']]
+    sd = net.base.state_dict()
+    assert 'fc.weight' not in sd and 'bn1.running_mean' not in sd
+    assert float(sd['conv1.weight'].mean()) == 0.25 and float(sd['bn1.weight'][3]) == 2.0
+    assert float(sd['layer1.0.conv1.weight'][0, 0, 0, 0]) == -0.5 and float(sd['layer2.0.downsample.1.bias'][5]) == 0.125
+    assert tuple(sd['layer4.1.conv2.weight'].shape) == (512, 512, 3, 3) and float(sd['layer4.1.conv2.weight'].abs().sum()) > 0

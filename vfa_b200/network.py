@@ -22,6 +22,9 @@ from .vfa_op import VFA
 from .vfanet import aggregate_cameras
 
 _STAGES = {'resnet18': (2, 2, 2, 2), 'resnet34': (3, 4, 6, 3)}     # reference resnet.py:150-171
+# ImageNet checkpoints the reference initialises the trunk from when `pretrained=True` (reference resnet.py:6-12)
+_IMAGENET = {'resnet18': 'https://download.pytorch.org/models/resnet18-5c106cde.pth',
+             'resnet34': 'https://download.pytorch.org/models/resnet34-333f7ec4.pth'}
 _GN_GROUPS = 16                                                     # every norm of the backbone (resnet.py:33, :36)
 
 
@@ -82,10 +85,10 @@ class VFANet(nn.Module):
             raise ValueError(f'Unrecognized model, expect `resnet18` or `resnet34`, got {base}.')
         if mode not in ('2D', '3D'):
             raise ValueError(f'mode error, expect `2D` or `3D`, got {mode}')
-        if pretrained:
-            raise NotImplementedError('ImageNet weights need network access; load a checkpoint with load_state_dict')
         self.mode = mode
         self.base = _Trunk(_STAGES[base])
+        if pretrained:
+            self.load_imagenet_trunk(base)
         for s in (8, 16, 32):
             vfa = VFA(channel=256, grid_height=grid_height, cube_size=cube_size, feat_scale=1. / s, args=args)
             vfa.flags = int(flags)
@@ -103,6 +106,17 @@ class VFANet(nn.Module):
         if mode == '3D':
             self.orient_pred = nn.Sequential(nn.Conv2d(256, angle_range, 3, padding=4, dilation=4, bias=False))
             self.thtwtl_pred = _head(3)
+
+    def load_imagenet_trunk(self, base: str, state: dict | None = None):
+        """`pretrained=True` of the reference (resnet.py:150-180): take from the torchvision ImageNet checkpoint every
+        entry whose name the trunk knows -- the convolutions, and the BatchNorm scales / shifts, which land in the
+        GroupNorm layers of the same names; running statistics have no counterpart and are dropped.  Needs network
+        access (torch.hub download) unless `state` is given."""
+        if state is None:
+            state = torch.hub.load_state_dict_from_url(_IMAGENET[base], progress=False)
+        own = self.base.state_dict()
+        own.update({k: v for k, v in state.items() if k in own and v.shape == own[k].shape})
+        self.base.load_state_dict(own)
 
     def bev_features(self, images, calibs, grid, batch: int = 1):
         """images [batch*V, 3, iH, iW] -> ortho [batch, 256, L, W]  (reference vfanet.py:61-82)."""
