@@ -69,3 +69,25 @@ def test_own_network_module_has_the_reference_state_dict():
             assert torch.equal(r, o)
     for n in [k for k in sys.modules if k == 'vfa' or k.startswith('vfa.')]:
         del sys.modules[n]
+
+
+def test_compat_install_can_replace_the_whole_network_module():
+    """compat.install(network=True): the reference scripts' `from vfa.model.vfanet import VFANet` resolves to the B200
+    network, the rest of the reference package (vfa.utils, vfa.config ...) stays the reference's own."""
+    import vfa_b200.compat as compat
+    from vfa_b200.network import VFANet as Ours
+    for n in [k for k in sys.modules if k == 'vfa' or k.startswith('vfa.')]:
+        del sys.modules[n]
+    for n in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.patches', 'matplotlib.gridspec'):
+        sys.modules.setdefault(n, types.ModuleType(n))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    compat.install(network=True)
+    from vfa.model.vfanet import VFANet          # what reference train.py:13 / evaluate.py:9 execute
+    from vfa.utils import make_grid               # still the reference's
+    assert VFANet is Ours and 'reference' in make_grid.__code__.co_filename
+    args = SimpleNamespace(data='MultiviewX', image_size=(1080, 1920))
+    net = VFANet(args=args, grid_height=64, cube_size=(4, 4, 8), angle_range=360, mode='2D', pretrained=False)   # train.py:249
+    assert net.vfa8.num_grid_layer == 8 and not hasattr(net, 'orient_pred')
+    for n in [k for k in sys.modules if k == 'vfa' or k.startswith('vfa.')]:
+        del sys.modules[n]

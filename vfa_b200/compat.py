@@ -17,9 +17,13 @@ EPSILON = 1e-6               # reference vfa_op.py:14 (kept for code that import
 MAXIMUM_AREA_RATIO = 0.3     # reference vfa_op.py:15
 
 
-def install(force: bool = False) -> types.ModuleType:
+def install(force: bool = False, network: bool = False) -> types.ModuleType:
     """Register the stand-in.  Call before importing `vfa.model.vfanet`; with force=True an already imported reference
-    `vfa.model.vfa_op` (and `vfa.model.vfanet`'s binding of VFA) is replaced as well."""
+    `vfa.model.vfa_op` (and `vfa.model.vfanet`'s binding of VFA) is replaced as well.
+
+    network=True additionally registers a stand-in `vfa.model.vfanet` whose `VFANet` is `vfa_b200.network.VFANet` (same
+    constructor, forward and checkpoint keys; laterals batched over cameras, one fused aggregation call), so the
+    reference's `from vfa.model.vfanet import VFANet` (train.py:13, evaluate.py:9) picks up the whole B200 network."""
     name = 'vfa.model.vfa_op'
     if name in sys.modules and not force and getattr(sys.modules[name], '__vfa_b200__', False) is False:
         raise RuntimeError(f'{name} is already imported; call install(force=True) to replace it')
@@ -36,4 +40,17 @@ def install(force: bool = False) -> types.ModuleType:
     parent = sys.modules.get('vfa.model')
     if parent is not None:
         parent.vfa_op = mod
+    if network:
+        from .network import VFANet
+        net_name = 'vfa.model.vfanet'
+        if net_name in sys.modules and not force and getattr(sys.modules[net_name], '__vfa_b200__', False) is False:
+            raise RuntimeError(f'{net_name} is already imported; call install(force=True, network=True) to replace it')
+        net_mod = types.ModuleType(net_name)
+        net_mod.__doc__ = 'vfa_b200 stand-in for the reference network module'
+        net_mod.__vfa_b200__ = True
+        net_mod.VFANet = VFANet
+        net_mod.VFA = VFA
+        sys.modules[net_name] = net_mod
+        if parent is not None:
+            parent.vfanet = net_mod
     return mod
