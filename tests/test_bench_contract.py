@@ -49,3 +49,20 @@ def test_our_arm_line():
     assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['value'] > 0 and cb['cores'] >= 1
+
+
+@pytest.mark.gpu
+def test_train_mode_line():
+    """--mode train (BASELINE config 5): one optimiser step of the whole detector; same line format, plus the split of the
+    step into network forward / aggregation forward / aggregation forward + backward."""
+    d = _run('--mode', 'train', '--steps', '3', '--warmup', '3')
+    assert BASE_KEYS | {'clocks', 'gpu_launches', 'breakdown_ms'} <= set(d)
+    assert d['metric'] == 'training_frames_per_s' and d['unit'] == 'frames/s' and d['n_gpus'] == 1 and d['value'] > 0
+    assert d['config']['batch_per_gpu'] == 1 and d['config']['views'] == 7 and d['config']['kernel_path'] == 'fside_tf32x3'
+    assert d['config']['parameters'] == 15597632                  # ResNet-18 trunk + laterals + 3 collapse layers + heads
+    b = d['breakdown_ms']
+    assert 0 < b['aggregation_forward'] < b['aggregation_forward_backward'] < b['train_step']
+    assert b['network_forward_eval'] < b['train_step']
+    e = d['e2e']
+    assert e['h2d_bytes_per_step'] == 7 * 3 * 720 * 1280 * 4 and e['d2h_bytes_per_step'] == 4 and 0 < e['value'] <= d['value'] * 1.05
+    assert d['final_loss'] == d['final_loss'] and d['final_loss'] > 0          # finite
