@@ -83,6 +83,11 @@ typedef struct {
                                         call derived from the SAME boxes, shapes and flags (tap records, coverage bitmap,
                                         row lists, the quads' texel lists) -- static cameras: skip rebuilding them      */
 
+#define VFA_FLAG_OUT_NHWC 128u        /* C = 256 feature-side forward: d_out is [B, L, W, C] (channels-last, what a cuDNN
+                                        head in torch.channels_last reads without a permute; reference consumer:
+                                        vfanet.py:131-139) instead of [B, C, L, W]; the backward reads d_grad_out in the
+                                        layout it is handed with the same flag                                          */
+
 int vfa_version(void);
 const char* vfa_last_error(void);
 

@@ -11,11 +11,11 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 for f in vfa_b200/csrc/*.cu; do
   b=$(basename $f .cu)
   extra=""; [ "$b" = vfa_table ] && extra="-fmad=false"
-  if [ "$b" = vfa_fwd_fside ]; then
+  if [ "$b" = "${TU:-vfa_fwd_fside}" ]; then
     nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC -Xptxas -v "$@" -c $f -o $out/$b.o 2> $out/$b.ptxas.log
   else
     cp build/$b.o $out/$b.o        # unchanged translation units come from the default build
   fi
 done
 nvcc $ARCH -shared -o build/variants/libvfa_$name.so $out/*.o -cudart static -ldl
-grep -A2 "pool_quad_kernelILb0" $out/vfa_fwd_fside.ptxas.log | grep -E "registers|spill" | head -3
+grep -E "registers|spill" $out/${TU:-vfa_fwd_fside}.ptxas.log | sort | uniq -c | sort -rn | head -4

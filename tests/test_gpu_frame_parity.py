@@ -1,0 +1,179 @@
+"""GPU parity of the BENCHED configuration: the default C = 256 path (row-compacted tcgen05 3xTF32 GEMM + staged-tile
+pooling) on whole frames -- every view, all three scales (stride 8 included), full BEV grid -- directly against the
+float64 port of the reference, forward and backward.
+
+The oracle is per-cell independent, so it is evaluated on a strided subset of the cells (grid[r0::sr, c0::sc]) while the
+CUDA path runs the complete grid; the compared values are the CUDA outputs at exactly those cells.  For the backward the
+cotangent is non-zero on the subset only, which makes every gradient a function of the subset cells alone.
+Tolerance: 1e-5 relative + 1e-6 absolute on the forward (north_star); 2e-5 of max|grad| on the gradients.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_port                      # noqa: E402
+import vfa_b200                                   # noqa: E402
+from vfa_b200 import geometry, synthetic          # noqa: E402
+
+NAMES = ['MultiviewC', 'MultiviewX', 'Wildtrack']
+RTOL, ATOL = 1e-5, 1e-6
+SUBSET = {'MultiviewC': (1, 5, 2, 6), 'MultiviewX': (0, 6, 3, 9), 'Wildtrack': (2, 5, 1, 11)}    # r0, sr, c0, sc
+
+
+def _geom(name, grid_lw):
+    g = geometry.GEOMETRIES[name]
+    zs = list(range(0, g.grid_height, g.cube_size[2]))
+    return vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid_lw, name, g.image_size)
+
+
+def _port(name, feats, calibs, grid, params):
+    g = geometry.GEOMETRIES[name]
+    return ref_port.aggregate([t.double() for t in feats], calibs, grid, [(w.double(), b.double()) for w, b in params],
+                              g.grid_height, g.cube_size, name, g.image_size, cache_boxes=True)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_whole_frame_default_path_vs_float64_port(name):
+    """Benched workload shape: all ring cameras x 3 scales x C = 256, batch 2, full grid, default flags."""
+    g = geometry.GEOMETRIES[name]
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g)
+    feats = synthetic.features(g, batch=2, seed=31)
+    params = synthetic.collapse_params(g, seed=31)
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    out = vfa_b200.aggregate([f.cuda() for f in feats], table, [w.cuda() for w, _ in params], [b.cuda() for _, b in params])
+    assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
+    r0, sr, c0, sc = SUBSET[name]
+    sub = grid[r0::sr, c0::sc].contiguous()
+    got = out[1, :, r0::sr, c0::sc].cpu().numpy().astype(np.float64)          # frame 1 of the batch
+    want = _port(name, [f[1:2] for f in feats], calibs, sub, params)[0].numpy()
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    bad = err > ATOL + RTOL * np.abs(want)
+    print(f'{name}: whole frame, {want.size} outputs of {sub.shape[0]}x{sub.shape[1]} cells: outside tol {bad.mean():.2e}, '
+          f'worst abs {err.max():.2e}, max|out| {np.abs(want).max():.3f}')
+    assert not bad.any(), f'{bad.sum()} of {bad.size} outside tolerance (worst {err.max():.3e})'
+
+
+@pytest.mark.parametrize('scale', [0, 1, 2])
+def test_every_scale_single_call_vs_float64_port(scale):
+    """One (view, scale) at C = 256 for EACH of the three feature scales (stride 8 = 90 x 160 included), in-field camera
+    (very large boxes and behind-camera ghosts), full grid on the GPU, every 3rd cell in the oracle."""
+    name = 'MultiviewC'
+    g = geometry.GEOMETRIES[name]
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g, n_views=1, in_field=True)
+    sizes = [g.feature_sizes()[scale]]
+    params = synthetic.collapse_params(g, seed=40 + scale)[:1]
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    feats = synthetic.features(g, batch=1, n_views=2, seed=40 + scale, sizes=sizes)
+    out = vfa_b200.aggregate([feats[0].cuda()], table, [params[0][0].cuda()], [params[0][1].cuda()])
+    assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
+    sub = grid[::3, 1::3].contiguous()
+    want = _port(name, feats, calibs, sub, params)[0].numpy()
+    got = out[0, :, ::3, 1::3].cpu().numpy().astype(np.float64)
+    err = np.abs(got - want)
+    bad = err > ATOL + RTOL * np.abs(want)
+    print(f'scale {scale} {sizes[0]}: outside tol {bad.mean():.2e}, worst abs {err.max():.2e}')
+    assert not bad.any(), f'{bad.sum()} of {bad.size} outside tolerance (worst {err.max():.3e})'
+
+
+@pytest.mark.parametrize('name', ['MultiviewC', 'Wildtrack'])
+def test_whole_frame_backward_vs_float64_port(name):
+    """C = 256 forward + backward of the default path at all three scales on the FULL grid against float64 autograd
+    through the port.  No quantity of the CUDA run enters the oracle: the cotangent is zeroed wherever any (view, scale)
+    pre-activation of the float64 oracle is within 1e-5 of the ReLU kink (where 3xTF32 and float64 may legitimately
+    disagree on the sign), and each side then uses its own ReLU mask."""
+    g = geometry.GEOMETRIES[name]
+    V = 2
+    grid = geometry.grid_for(g)
+    L, W = grid.shape[:2]
+    calibs = synthetic.ring_calibs(g, n_views=V)
+    feats = synthetic.features(g, batch=1, n_views=V, seed=51)
+    params = synthetic.collapse_params(g, seed=51)
+    r0, sr, c0, sc = SUBSET[name]
+    sub = grid[r0::sr, c0::sc].contiguous()
+
+    f64 = [t.double().requires_grad_(True) for t in feats]
+    p64 = [(w.double().requires_grad_(True), b.double().requires_grad_(True)) for w, b in params]
+    out64, near_kink = 0, torch.zeros(1, 256, *sub.shape[:2], dtype=torch.bool)
+    for v in range(V):
+        for s in range(3):
+            pre = ref_port.preactivation(f64[s][0, v], calibs[v], sub, p64[s][0], p64[s][1], g.grid_height, g.cube_size,
+                                         name, g.image_size)
+            near_kink |= pre.detach().abs() <= 1e-5
+            out64 = out64 + torch.relu(pre)
+    gen = torch.Generator().manual_seed(9)
+    gsub = torch.randn(1, 256, *sub.shape[:2], generator=gen) * (~near_kink)
+    out64.backward(gsub.double())
+    print(f'{name}: {int(near_kink.sum())} of {near_kink.numel()} outputs masked out of the cotangent (near the ReLU kink)')
+
+    gout = torch.zeros(1, 256, L, W)
+    gout[:, :, r0::sr, c0::sc] = gsub
+    table = vfa_b200.build_table(_geom(name, (L, W)), calibs.cuda(), grid.cuda())
+    fc = [t.cuda().requires_grad_(True) for t in feats]
+    ws = [w.cuda().requires_grad_(True) for w, _ in params]
+    bs = [b.cuda().requires_grad_(True) for _, b in params]
+    out = vfa_b200.aggregate(fc, table, ws, bs)
+    assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
+    out.backward(gout.cuda())
+    got = out.detach()[:, :, r0::sr, c0::sc].cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got, out64.detach().numpy(), rtol=RTOL, atol=ATOL)
+    for s in range(3):
+        for what, a, b in (('dFeature', fc[s].grad, f64[s].grad), ('dWeight', ws[s].grad, p64[s][0].grad),
+                           ('dBias', bs[s].grad, p64[s][1].grad)):
+            want = b.numpy()
+            err = np.abs(a.cpu().numpy().astype(np.float64) - want).max() / (np.abs(want).max() + 1e-30)
+            print(f'{name} scale {s} {what}: max err / max|grad| = {err:.2e}')
+            assert err < 2e-5, f'{name} scale {s} {what}: {err:.3e}'
+
+
+def test_tile_pooling_overflow_nhwc_and_determinism(monkeypatch):
+    """Staged-tile pooling (pool_tile_kernel, the default): bit-reproducible run to run; with its pools forced to overflow
+    (VFA_POOL_TILE_CAP = 1 %: nearly every tile is left to the walking kernel) and with the quads' list kernel
+    (VFA_POOL_TILE = 0) the sums only change their order (fp32 rounding); the [B, L, W, C] output (VFA_FLAG_OUT_NHWC) holds
+    the same bits as [B, C, L, W]; all on a ragged grid with an in-field camera, inference and training (mask) variants."""
+    g = geometry.WILDTRACK
+    grid = geometry.grid_for(g)[3:80, 5:132].contiguous()             # 77 x 127 cells: partial tiles on both sides
+    calibs = synthetic.ring_calibs(g, n_views=3, in_field=True)
+    V = calibs.shape[0]
+    params = synthetic.collapse_params(g, seed=8)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=V, seed=8)]
+    table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    for k in ('VFA_POOL_TILE_CAP', 'VFA_POOL_TILE'):
+        monkeypatch.delenv(k, raising=False)
+    ref = vfa_b200.aggregate(feats, table, ws, bs)
+    assert torch.equal(vfa_b200.aggregate(feats, table, ws, bs), ref)
+    simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
+    err = (ref - simt).abs()
+    assert bool((err <= ATOL + RTOL * simt.abs()).all()), f'worst {float(err.max()):.2e}'
+    cl = [vfa_b200.to_channels_last(f) for f in feats]
+    nhwc = torch.empty(2, grid.shape[0], grid.shape[1], 256, device='cuda')
+    vfa_b200.aggregate_forward_raw(cl, table, ws, bs, flags=vfa_b200.FLAG_OUT_NHWC, out=nhwc)
+    assert torch.equal(nhwc.permute(0, 3, 1, 2), ref)
+
+    def train_run():
+        f = [t.detach().clone().requires_grad_(True) for t in feats]
+        out = vfa_b200.aggregate(f, table, ws, bs)
+        out.backward(torch.ones_like(out))
+        return out.detach(), f[0].grad
+
+    out_t, grad_t = train_run()
+    assert torch.equal(out_t, ref)
+    for key, val in (('VFA_POOL_TILE_CAP', '1'), ('VFA_POOL_TILE', '0')):
+        monkeypatch.setenv(key, val)
+        other = vfa_b200.aggregate(feats, table, ws, bs)
+        err = (other - ref).abs()
+        assert bool((err <= 1e-6 + 2e-6 * ref.abs()).all()), f'{key}={val}: worst {float(err.max()):.2e}'
+        vfa_b200.aggregate_forward_raw(cl, table, ws, bs, flags=vfa_b200.FLAG_OUT_NHWC, out=nhwc)
+        assert torch.equal(nhwc.permute(0, 3, 1, 2), other)
+        out_c, grad_c = train_run()
+        assert torch.equal(out_c, other)
+        # a pre-activation within rounding of zero may flip its ReLU bit when the summation order changes: a handful of
+        # gradient elements move, everything else agrees to rounding
+        moved = ((grad_c - grad_t).abs() > 2e-5 * float(grad_t.abs().max())).float().mean()
+        assert float(moved) < 1e-4, f'{key}={val}: {float(moved):.2e} of dFeature elements differ'
+        monkeypatch.delenv(key, raising=False)

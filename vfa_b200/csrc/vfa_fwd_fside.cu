@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include "vfa_common.cuh"
+#include "vfa_pool.cuh"
 #include "vfa_umma_ptx.cuh"
 
 namespace vfa {
@@ -34,7 +35,6 @@ namespace fside {
 
 using namespace umma;
 
-constexpr int CH = 256;
 constexpr int TILE_M = 128;              // texel rows per CTA == TMEM lanes
 constexpr int KCH = 32;                  // K elements per stage
 constexpr int STAGES = 3;
@@ -100,13 +100,6 @@ __device__ __forceinline__ void store_split(uint8_t* a_hi, uint32_t off, const f
   lo.w = __float_as_uint(l23.y);
   *reinterpret_cast<uint4*>(a_hi + off) = hi;
   *reinterpret_cast<uint4*>(a_hi + A_BYTES + off) = lo;
-}
-
-// kernel-parameter arrays indexed by a run-time scale: a select chain instead of a local-memory copy of the struct
-template <typename T>
-__device__ __forceinline__ T pick(const T (&arr)[VFA_MAX_SCALES], int s) {
-  static_assert(VFA_MAX_SCALES == 3, "");
-  return s == 0 ? arr[0] : (s == 1 ? arr[1] : arr[2]);
 }
 
 template <bool BF16>
@@ -402,51 +395,6 @@ constexpr int POOL_TW = 4, POOL_TH = 4;                 // cells per CTA: 4 x 4,
 constexpr int POOL_WARPS = POOL_TW * POOL_TH;
 constexpr int TAP_BATCH = 3;                            // taps of a box row in flight per warp
 
-struct PoolArgs {
-  AggParams p;
-  const float* y[VFA_MAX_SCALES];
-  const TapRec* recs;        // [V][S][nl][LW]
-  int b0;                    // first frame of this chunk (output / mask index); Y planes are chunk-relative
-  int tiles_x;
-  // texel lists of the quads (pool_list_kernel; nullptr = not built)
-  const uint32_t* seg_off;   // [quads][V*S + 1] first entry of segment (view, scale) of a quad; last = end of the quad's list,
-                             // or LIST_OVERFLOW when the quad's texels did not fit its slot
-  const uint32_t* ent_off;   // [quads * slot] texel index inside the (view, scale) stack of nl planes
-  const float4* ent_w;       // [quads * slot] weights of the four cells of the quad
-  int quads_x;
-};
-constexpr uint32_t LIST_OVERFLOW = 0xffffffffu;
-
-__device__ __forceinline__ void fma8(float (&acc)[8], float w, const float4& a, const float4& b) {
-  const float2 w2 = make_float2(w, w);
-  const float2 r0 = __ffma2_rn(w2, make_float2(a.x, a.y), make_float2(acc[0], acc[1]));
-  const float2 r1 = __ffma2_rn(w2, make_float2(a.z, a.w), make_float2(acc[2], acc[3]));
-  const float2 r2 = __ffma2_rn(w2, make_float2(b.x, b.y), make_float2(acc[4], acc[5]));
-  const float2 r3 = __ffma2_rn(w2, make_float2(b.z, b.w), make_float2(acc[6], acc[7]));
-  acc[0] = r0.x; acc[1] = r0.y; acc[2] = r1.x; acc[3] = r1.y;
-  acc[4] = r2.x; acc[5] = r2.y; acc[6] = r3.x; acc[7] = r3.y;
-}
-
-// Channel <-> lane map of the pooling kernels: lane l owns channels [4l, 4l+4) (acc[0..3]) and [128 + 4l, 128 + 4l + 4)
-// (acc[4..7]), so each of the two LDG.128 of a warp covers 512 contiguous bytes of a texel row = 4 L1 wavefronts (with 8
-// consecutive channels per lane the 32-byte lane stride touches every 128-byte line twice: 8 wavefronts per load).
-__device__ __forceinline__ int chan_of(int lane, int i) { return (i < 4 ? 0 : CH / 2 - 4) + lane * 4 + i; }
-
-// ReLU pass bits of one cell (bit i of `bits` = channel chan_of(lane, i)) -> mask words (word o/32, bit o%32) at
-// words[k * word_stride]: lanes 8k .. 8k+7 hold the eight nibbles of word k (low channels) and of word 4 + k (high)
-__device__ __forceinline__ void store_mask_words(uint32_t* words, size_t word_stride, int lane, uint32_t bits, bool valid) {
-  uint32_t lo = (bits & 0xfu) << (4 * (lane & 7)), hi = (bits >> 4) << (4 * (lane & 7));
-#pragma unroll
-  for (int d = 1; d < 8; d <<= 1) {
-    lo |= __shfl_xor_sync(0xffffffffu, lo, d);
-    hi |= __shfl_xor_sync(0xffffffffu, hi, d);
-  }
-  if ((lane & 7) == 0 && valid) {
-    words[(size_t)(lane >> 3) * word_stride] = lo;
-    words[(size_t)(4 + (lane >> 3)) * word_stride] = hi;
-  }
-}
-
 template <bool MASK>
 __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolArgs a) {
   const AggParams& p = a.p;
@@ -470,7 +418,7 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
   for (int v = 0; v < p.V; ++v) {
     for (int s = 0; s < p.S; ++s) {
       const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
-      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
+      const float* yplane = static_cast<const float*>(a.y[s]) + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -523,9 +471,8 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, 2) pool_y_kernel(const PoolAr
         store_mask_words(p.mask + (((size_t)b * p.V + v) * p.S + s) * (CH / 32) * p.LW + cell, (size_t)p.LW, lane, bits, true);
     }
   }
-  float* o = p.out + (size_t)b * CH * p.LW + cell;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[(size_t)chan_of(lane, i) * p.LW] = out[i];
+  for (int i = 0; i < 8; ++i) p.out[out_index(a.out_nhwc, b, chan_of(lane, i), cell, p.LW)] = out[i];
 }
 
 
@@ -566,7 +513,13 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
   const int cy0 = (blockIdx.x / a.tiles_x) * (2 * QY) + 2 * (warp / QX);
   const int cx0 = (blockIdx.x % a.tiles_x) * (2 * QX) + 2 * (warp % QX);
   if (cy0 >= p.L || cx0 >= p.W) return;                 // no block-level synchronisation below
-  if (OVF && __ldg(a.seg_off + (size_t)((cy0 >> 1) * a.quads_x + (cx0 >> 1)) * (p.V * p.S + 1) + p.V * p.S) != LIST_OVERFLOW) return;
+  if (OVF) {          // completion pass: only the quads the list / tile kernel left alone
+    if (a.tile_ovf != nullptr) {
+      if (!__ldg(a.tile_ovf + (cy0 >> 3) * a.ptiles_x + (cx0 >> 3))) return;
+    } else if (__ldg(a.seg_off + (size_t)((cy0 >> 1) * a.quads_x + (cx0 >> 1)) * (p.V * p.S + 1) + p.V * p.S) != LIST_OVERFLOW) {
+      return;
+    }
+  }
   const int bl = blockIdx.y;
   const int b = a.b0 + bl;
   const int cl = lane & 3, jl = lane >> 2;              // this lane's cell (records, weights) and block column
@@ -588,7 +541,7 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
   for (int v = 0; v < p.V; ++v) {
     for (int s = 0; s < p.S; ++s) {
       const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
-      const float* yplane = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
+      const float* yplane = static_cast<const float*>(a.y[s]) + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
       float acc[4][8];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -688,6 +641,12 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
     if (cy >= p.L || cx >= p.W) continue;
     const float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
     const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
+    if (a.out_nhwc) {          // 512 contiguous bytes per warp store
+      float* o = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
+      *reinterpret_cast<float4*>(o) = o0;
+      *reinterpret_cast<float4*>(o + CH / 2) = o1;
+      continue;
+    }
     float* o = p.out + (size_t)b * CH * p.LW + cy * p.W + cx;
     const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
@@ -870,7 +829,7 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_LIST_MINBLOCKS) pool_list_ker
     for (int s = 0; s < p.S; ++s) {
       const uint32_t end = __ldg(++so);
       const int hw = p.sc[s].fh * p.sc[s].fw;
-      const float* ybase = a.y[s] + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
+      const float* ybase = static_cast<const float*>(a.y[s]) + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
       float acc[4][8];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -935,6 +894,12 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_LIST_MINBLOCKS) pool_list_ker
     if (cy >= p.L || cx >= p.W) continue;
     const float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
     const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
+    if (a.out_nhwc) {          // 512 contiguous bytes per warp store
+      float* o = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
+      *reinterpret_cast<float4*>(o) = o0;
+      *reinterpret_cast<float4*>(o + CH / 2) = o1;
+      continue;
+    }
     float* o = p.out + (size_t)b * CH * p.LW + cy * p.W + cx;
     const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
@@ -1589,14 +1554,9 @@ struct ListLayout {
   uint32_t slot;
 };
 static bool pool_list_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("VFA_POOL_LIST");
-    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-    const char* q = getenv("VFA_POOL_QUAD");             // the one-cell-per-warp comparison kernel has no lists
-    if (q != nullptr && atoi(q) == 0) on = 0;
-  }
-  return on != 0;
+  const char* e = getenv("VFA_POOL_LIST");
+  const char* q = getenv("VFA_POOL_QUAD");               // the one-cell-per-warp comparison kernel has no lists
+  return (e == nullptr || atoi(e) != 0) && !(q != nullptr && atoi(q) == 0);
 }
 static ListLayout list_layout(const AggParams& p) {
   ListLayout L = {};
@@ -1634,15 +1594,28 @@ static int launch_quad_lists(const AggParams& p, const TapRec* recs, void* list_
   return VFA_OK;
 }
 
+// staged-tile pooling (vfa_pool_tile.cu): the default; 0 bytes = not available for this problem (the quads' lists serve it)
+size_t tile_pool_workspace_bytes(const AggParams& p);
+int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStream_t st);
+int launch_pool_tile(fside::PoolArgs q, void* ws, int nb, bool y_bf16, cudaStream_t st);
+void tile_pool_overflow_view(const AggParams& p, void* ws, const uint8_t** tile_ovf, int* tiles_x);
+
+// bytes of the pooling lists: chunk lists of the tiles, else texel lists of the quads
+static size_t pool_lists_bytes(const AggParams& p) {
+  const size_t t = tile_pool_workspace_bytes(p);
+  return t != 0 ? t : list_layout(p).total;
+}
+
 // workspace of the feature-side forward behind the prepared weights and tap records:
-// [cover bitmap + need bytes + row lists][texel lists of the quads][Y]
+// [cover bitmap + need bytes + row lists][chunk lists of the tiles | texel lists of the quads][Y]
 size_t fside_workspace_bytes(const AggParams& p) {
   const int cb = fside_chunk_frames(p);
-  return fside_cover_bytes(p, cb) + list_layout(p).total + (size_t)cb * fside_y_bytes_per_frame(p);
+  return fside_cover_bytes(p, cb) + pool_lists_bytes(p) + (size_t)cb * fside_y_bytes_per_frame(p);
 }
 
 int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
-                     bool bf16, int variant, cudaStream_t st) {
+                     uint32_t flags, int variant, cudaStream_t st) {
+  const bool bf16 = (flags & VFA_FLAG_BF16_FEATURES) != 0;
   static bool attr_set = false;
   if (!attr_set) {
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1659,17 +1632,20 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     attr_set = true;
   }
   const size_t per_frame = fside_y_bytes_per_frame(p);
-  const ListLayout LL = list_layout(p);
+  const size_t tile_bytes = tile_pool_workspace_bytes(p);
+  ListLayout LL = list_layout(p);
+  if (tile_bytes != 0) LL = ListLayout{};                  // the tiles' chunk lists replace the quads' texel lists
+  const size_t lists_bytes = tile_bytes != 0 ? tile_bytes : LL.total;
   int cb = fside_chunk_frames(p);
-  while (cb > 1 && fside_cover_bytes(p, cb) + LL.total + (size_t)cb * per_frame > fs_bytes) --cb;
+  while (cb > 1 && fside_cover_bytes(p, cb) + lists_bytes + (size_t)cb * per_frame > fs_bytes) --cb;
   const size_t cover_bytes = fside_cover_bytes(p, cb);
-  if (cover_bytes + LL.total + per_frame > fs_bytes) {
+  if (cover_bytes + lists_bytes + per_frame > fs_bytes) {
     set_error("feature-side forward: workspace holds %zu bytes for Y, one frame needs %zu", fs_bytes,
-              cover_bytes + LL.total + per_frame);
+              cover_bytes + lists_bytes + per_frame);
     return VFA_ERR_WORKSPACE;
   }
   uint8_t* list_ws = reinterpret_cast<uint8_t*>(fs_ws) + cover_bytes;
-  float* y_ws = reinterpret_cast<float*>(list_ws + LL.total);
+  float* y_ws = reinterpret_cast<float*>(list_ws + lists_bytes);
   // row-compacted GEMM unless VFA_FSIDE_COMPACT=0 (whole 256-row tiles, skipped by the need bytes) or VFA_FSIDE_NO_SKIP=1
   const char* ec = getenv("VFA_FSIDE_COMPACT");
   const char* en = getenv("VFA_FSIDE_NO_SKIP");
@@ -1678,14 +1654,18 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
     if (compact)
       if (int rc = launch_rowlists(p, fs_ws, cb, st)) return rc;
-    if (LL.total != 0 && !(variant & 64))
+    if (tile_bytes != 0 && !(variant & 64)) {
+      if (int rc = launch_tile_build(p, recs, list_ws, st)) return rc;
+    } else if (LL.total != 0 && !(variant & 64)) {
       if (int rc = launch_quad_lists(p, recs, list_ws, st)) return rc;
+    }
   }
   const size_t es = bf16 ? 2 : 4;
   for (int b0 = 0; b0 < p.B; b0 += cb) {
     const int nb = p.B - b0 < cb ? p.B - b0 : cb;
     YGemmArgs g;
-    PoolArgs q;
+    PoolArgs q = {};
+    q.out_nhwc = (flags & VFA_FLAG_OUT_NHWC) ? 1 : 0;
     q.p = p;
     q.recs = recs;
     q.b0 = b0;
@@ -1718,12 +1698,22 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       }
     }
     if (!(variant & 64)) {
-      static int quad = -1;            // VFA_POOL_QUAD=0 selects the one-cell-per-warp kernel (debug / comparison)
-      if (quad < 0) {
-        const char* e = getenv("VFA_POOL_QUAD");
-        quad = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-      }
-      if (quad && LL.total != 0) {
+      const char* eq = getenv("VFA_POOL_QUAD");     // VFA_POOL_QUAD=0 selects the one-cell-per-warp kernel (debug / comparison)
+      const int quad = (eq == nullptr || atoi(eq) != 0) ? 1 : 0;
+      q.tile_ovf = nullptr;
+      q.ptiles_x = 0;
+      if (quad && tile_bytes != 0) {
+        q.tiles_x = (p.W + 2 * QX - 1) / (2 * QX);
+        q.seg_off = nullptr;
+        if (int rc = launch_pool_tile(q, list_ws, nb, false, st)) return rc;
+        tile_pool_overflow_view(p, list_ws, &q.tile_ovf, &q.ptiles_x);
+        const dim3 grid(q.tiles_x * ((p.L + 2 * QY - 1) / (2 * QY)), nb);
+        if (p.mask != nullptr)
+          pool_quad_kernel<true, true><<<grid, QWARPS * 32, 0, st>>>(q);
+        else
+          pool_quad_kernel<false, true><<<grid, QWARPS * 32, 0, st>>>(q);
+        VFA_LAUNCH_CHECK("pool_quad_kernel (completion pass)");
+      } else if (quad && LL.total != 0) {
         q.tiles_x = (p.W + 2 * QX - 1) / (2 * QX);
         q.seg_off = reinterpret_cast<const uint32_t*>(list_ws + LL.off_segoff);
         q.ent_off = reinterpret_cast<const uint32_t*>(list_ws + LL.off_entoff);

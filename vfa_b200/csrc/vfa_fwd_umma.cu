@@ -812,7 +812,7 @@ size_t fside_y_bytes_per_frame(const AggParams& p);
 int fside_chunk_frames(const AggParams& p);
 size_t fside_workspace_bytes(const AggParams& p);
 int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
-                     bool bf16, int variant, cudaStream_t st);
+                     uint32_t flags, int variant, cudaStream_t st);
 
 static bool grid_side_requested(uint32_t flags) {
   const char* e = getenv("VFA_FWD_GRIDSIDE");
@@ -891,7 +891,7 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, size_t 
       return VFA_ERR_WORKSPACE;
     }
     if (int rc = launch_fwd_fside(p, a.wprep, a.recs, reinterpret_cast<uint8_t*>(ws) + fixed,
-                                  ws_bytes - fixed, bf16, a.variant, st))
+                                  ws_bytes - fixed, flags, a.variant, st))
       return rc;
     set_path(bf16 ? "fside_tf32x3_bf16feat" : "fside_tf32x3");
     return VFA_OK;

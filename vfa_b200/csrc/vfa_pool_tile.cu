@@ -1,0 +1,839 @@
+// Pooling of Y from shared memory: one CTA per 8 x 8 tile of BEV cells, texel rows staged with cp.async.bulk.
+//
+// The list kernel (pool_list_kernel) loads every texel row a 2 x 2 quad touches straight from L2 / L1: on the MultiviewC
+// rig that is 3.7 M row visits (1 KB each) per frame for 1.0 M distinct rows per 8 x 8 tile and 0.36 M distinct rows per
+// frame -- 11 GB per B = 4 launch through the L2 -> SM fabric (its cap is ~6300 B/clk = 12 TB/s: 0.9 ms) and the L1 data
+// pipe (multi-line LDGs replay at ~2 cycles per line).  Here the 16 quads of a tile share the rows:
+//
+//   tile_build_kernel (once per table)  per (tile, view, scale): bitmap of the (layer, texel) rows any box of the tile
+//       covers -> rank of every row -> CHUNKS of TR consecutive ranks.  Per chunk a descriptor (row offsets, blob
+//       address) and a blob: per quad the entries (slot of the row inside the chunk, the four cell weights wy * wx),
+//       ordered by slot -- a deterministic order, whatever the thread schedule of the builder.
+//   pool_tile_kernel  persistent, one CTA per SM: a producer warp walks the chunk descriptors of its tiles and issues
+//       one 1 KB bulk copy per row (+ one for the blob) into a ring of shared-memory stages (mbarrier complete_tx);
+//       16 consumer warps (one per quad, lane l = channels [4l, 4l+4) and [128+4l, ...)) wait for a stage, apply the
+//       rows their entries name with LDS.128 + packed FMAs, release the stage; after the last chunk of a (view, scale):
+//       + bias, ReLU, ReLU mask, sum into the tile's partial sums (64 KB of shared memory, swizzled); after the last
+//       chunk of the tile the 8 x 8 x 256 block is written with full 32-byte sectors ([B,C,L,W]) or 1 KB rows ([B,L,W,C]).
+//
+// L2 -> SM traffic drops 3.5x, the texel rows leave the LSU / L1 path (conflict-free LDS, no replays), and the loads a
+// warp waits for are shared-memory loads.  Tiles whose chunk lists do not fit the pools are flagged and pooled by the
+// walking kernel (pool_quad_kernel<.., OVF>) -- exact for any rig, no host synchronisation, static workspace.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "vfa_common.cuh"
+#include "vfa_pool.cuh"
+#include "vfa_umma_ptx.cuh"
+
+namespace vfa {
+namespace ptile {
+
+using namespace umma;
+using fside::CH;
+using fside::PoolArgs;
+using fside::pick;
+
+#ifndef VFA_TILE_ROWS
+#define VFA_TILE_ROWS 32
+#endif
+#ifndef VFA_TILE_STAGES
+#define VFA_TILE_STAGES 4
+#endif
+constexpr int TC = 8;                       // tile = TC x TC cells
+constexpr int TQ = 16;                      // quads per tile = consumer warps
+constexpr int TR = VFA_TILE_ROWS;           // rows (ranks) per chunk
+constexpr int TSTAGES = VFA_TILE_STAGES;
+#ifndef VFA_TILE_MAXENT
+#define VFA_TILE_MAXENT 384
+#endif
+constexpr int MAX_ENT = VFA_TILE_MAXENT;    // entries of a chunk (a quad lists a row at most once: TR * TQ is the most there
+                                            // can be); a chunk with more -> the tile is left to the walking kernel
+constexpr int BLOB_HDR = 80;                // segpair[16] (begin | end << 16), nent, info, 8 bytes pad
+constexpr int META_CAP = (BLOB_HDR + 17 * MAX_ENT + 127) / 128 * 128;
+constexpr int CAPV = 4096 / TR;              // chunks of one (tile, view, scale) the builder handles; more -> overflow
+#ifndef VFA_TILE_PRODUCERS
+#define VFA_TILE_PRODUCERS 2
+#endif
+constexpr int NPROD = VFA_TILE_PRODUCERS;   // producer warps
+constexpr int CONSUMER_THREADS = TQ * 32;
+constexpr int POOL_THREADS = CONSUMER_THREADS + 32 * NPROD;
+constexpr int PREFETCH = 3;                 // chunk descriptors a producer warp holds in registers ahead of the ring
+static_assert(NPROD >= 1 && NPROD <= VFA_TILE_STAGES, "");
+static_assert(TR <= 32 && TR % 8 == 0, "one producer lane per row; slot masks are 32-bit");
+
+constexpr uint32_t INFO_LAST_VS = 1u, INFO_LAST_TILE = 2u;     // info = flags | s << 8 | v << 16
+
+template <typename YT>
+struct RowBytes {
+  static constexpr int value = CH * (int)sizeof(YT);
+  static constexpr int stage = TR * value + META_CAP;                      // rows + blob of one chunk
+  static constexpr size_t smem = (size_t)TC * TC * CH * 4 + (size_t)TSTAGES * stage + 2 * TSTAGES * 8 + 128 +
+                                 (size_t)VFA_MAX_SCALES * CH * 4;
+};
+static_assert(RowBytes<float>::smem <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
+
+struct TileLists {
+  const uint8_t* tile_ovf;     // [n_tiles]
+  const uint2* tvs;            // [n_tiles][VS]: first chunk id, chunk count (>= 1) of a (tile, view, scale)
+  const uint4* hdr;            // [chunk]: blob offset (16-byte units), blob bytes, nrows | nruns << 8 | nent << 16, info
+  const uint32_t* rowoff;      // [chunk][TR]: the chunk's rows as RUNS of consecutive rows of Y (one bulk copy each):
+                               // first row inside the (frame, view) stack of nl planes | first slot << 22 | (len - 1) << 27
+  const uint8_t* blob;
+  int tiles_x, n_tiles, VS;
+};
+
+// ---- builder ----------------------------------------------------------------------------------------------------------
+struct BuildArgs {
+  AggParams p;
+  const TapRec* recs;
+  uint32_t* cursors;           // [0] chunk ids handed out, [1] blob pool used (16-byte units)
+  uint8_t* tile_ovf;
+  uint2* tvs;
+  uint4* hdr;
+  uint32_t* rowoff;
+  uint8_t* blob;
+  uint32_t desc_cap, blob_cap16;
+  int tiles_x, VS;
+  int max_words;               // bitmap words of the largest scale (shared-memory layout)
+};
+
+// One (quad, layer) of the walk, done by one thread from the tile's records in shared memory.  Weights are those of the
+// walking kernel (wl = wy * wx per cell, zero outside the cell's box); a row is listed when any of the four is non-zero.
+// FILL = false: mark the row's slot in the (chunk, quad) mask.  FILL = true: write the entry at its position (= number of
+// lower slots of the same quad in the chunk).
+template <bool FILL>
+__device__ __forceinline__ void quad_walk(const uint4* __restrict__ recs_s, int q, int n, int sub, int nsub, int fw, int hw,
+                                          const uint32_t* __restrict__ bits, const uint32_t* __restrict__ pref,
+                                          uint32_t* __restrict__ qmask, const uint16_t* __restrict__ segbeg,
+                                          const uint32_t* __restrict__ blob_off16, const uint16_t* __restrict__ nent_s,
+                                          uint8_t* __restrict__ blob) {
+  int nx[4], ny[4], x0[4], y0[4];
+  float wxf[4], wxl[4], wyf[4], wyl[4], wym[4];
+  int ux0 = 0x7fff, uy0 = 0x7fff, ux1 = -1, uy1 = -1;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int cell = (2 * (q >> 2) + (c >> 1)) * TC + 2 * (q & 3) + (c & 1);
+    const uint4 r0 = recs_s[(n * TC * TC + cell) * 2], r1 = recs_s[(n * TC * TC + cell) * 2 + 1];
+    nx[c] = (int)r0.y & 0xffff;
+    ny[c] = (int)r0.y >> 16;
+    x0[c] = (int)r0.x & 0xffff;
+    y0[c] = (int)r0.x >> 16;
+    wxf[c] = __uint_as_float(r0.z);
+    wxl[c] = __uint_as_float(r0.w);
+    wyf[c] = __uint_as_float(r1.x);
+    wyl[c] = __uint_as_float(r1.y);
+    wym[c] = __uint_as_float(r1.z);
+    if (nx[c] != 0) {
+      ux0 = min(ux0, x0[c]);
+      uy0 = min(uy0, y0[c]);
+      ux1 = max(ux1, x0[c] + nx[c] - 1);
+      uy1 = max(uy1, y0[c] + ny[c] - 1);
+    }
+  }
+  if (ux1 < 0) return;
+  for (int ty = uy0 + sub; ty <= uy1; ty += nsub) {       // `nsub` threads share the rows of one (quad, layer)
+    float wy[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ry = ty - y0[c];
+      wy[c] = (nx[c] != 0 && ry >= 0 && ry < ny[c]) ? (ry == 0 ? wyf[c] : (ry == ny[c] - 1 ? wyl[c] : wym[c])) : 0.f;
+    }
+    for (int tx = ux0; tx <= ux1; ++tx) {
+      float wl[4];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int rx = tx - x0[c];
+        const float wx = (nx[c] != 0 && rx >= 0 && rx < nx[c]) ? (rx == 0 ? wxf[c] : (rx == nx[c] - 1 ? wxl[c] : 1.0f)) : 0.f;
+        wl[c] = __fmul_rn(wy[c], wx);
+        any = any || wl[c] != 0.f;
+      }
+      if (!any) continue;
+      const int idx = n * hw + ty * fw + tx;
+      const uint32_t word = bits[idx >> 5], bit = (uint32_t)idx & 31u;
+      if (!((word >> bit) & 1u)) continue;               // cannot happen for finite weights: the row is in some box
+      const uint32_t rank = pref[idx >> 5] + __popc(word & ((1u << bit) - 1u));
+      const uint32_t chunk = rank / TR, slot = rank % TR;
+      if (!FILL) {
+        atomicOr(&qmask[chunk * TQ + q], 1u << slot);
+      } else {
+        const uint32_t pos = segbeg[chunk * TQ + q] + __popc(qmask[chunk * TQ + q] & ((1u << slot) - 1u));
+        uint8_t* b = blob + (size_t)blob_off16[chunk] * 16;
+        reinterpret_cast<float4*>(b + BLOB_HDR)[pos] = make_float4(wl[0], wl[1], wl[2], wl[3]);
+        b[BLOB_HDR + 16 * (uint32_t)nent_s[chunk] + pos] = (uint8_t)slot;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* warp_sums, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+    const uint32_t v = warp_sums[k];
+    if (k < warp) before += v;
+    all += v;
+  }
+  __syncthreads();
+  *total = all;
+  return before + inc - x;
+}
+
+// grid = n_tiles * VS CTAs of 256 threads; dynamic shared memory: records, bitmap, prefix, masks, segment starts.
+__global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
+  extern __shared__ uint4 bsm[];
+  __shared__ uint32_t warp_sums[8];
+  __shared__ uint32_t base_s[2];
+  __shared__ uint32_t blob_off16[CAPV];
+  __shared__ uint16_t nent_s[CAPV];
+  const AggParams& p = a.p;
+  const int tile = blockIdx.x / a.VS, vs = blockIdx.x % a.VS;
+  const int s = vs % p.S;
+  const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
+  const int nbits = p.nl * hw, nwords = (nbits + 31) >> 5;
+  const int ty0 = (tile / a.tiles_x) * TC, tx0 = (tile % a.tiles_x) * TC;
+  uint4* recs_s = bsm;                                                     // [nl * 64] x 32 B
+  uint32_t* bits = reinterpret_cast<uint32_t*>(recs_s + (size_t)p.nl * TC * TC * 2);
+  uint32_t* pref = bits + a.max_words;
+  uint32_t* qmask = pref + a.max_words;                                    // [CAPV][TQ]
+  uint16_t* segbeg = reinterpret_cast<uint16_t*>(qmask + CAPV * TQ);       // [CAPV][TQ]
+  uint32_t* rank_idx = reinterpret_cast<uint32_t*>(segbeg + CAPV * TQ);    // [CAPV * TR] row of every rank
+  const int tid = threadIdx.x;
+
+  for (int w = tid; w < nwords; w += 256) bits[w] = 0u;
+  __syncthreads();
+  // pass 1: the tile's records -> shared memory; rows of every visible box -> bitmap
+  for (int item = tid; item < p.nl * TC * TC; item += 256) {
+    const int n = item / (TC * TC), c = item % (TC * TC);
+    const int cy = ty0 + c / TC, cx = tx0 + c % TC;
+    uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+    if (cy < p.L && cx < p.W) {
+      const uint4* rp = reinterpret_cast<const uint4*>(a.recs + ((size_t)vs * p.nl + n) * p.LW + cy * p.W + cx);
+      r0 = __ldg(rp);
+      r1 = __ldg(rp + 1);
+    }
+    recs_s[item * 2] = r0;
+    recs_s[item * 2 + 1] = r1;
+    const int nx = (int)r0.y & 0xffff, ny = (int)r0.y >> 16;
+    if (nx == 0) continue;
+    const int x0 = (int)r0.x & 0xffff, y0 = (int)r0.x >> 16;
+    for (int ty = 0; ty < ny; ++ty) {
+      const int t0 = n * hw + (y0 + ty) * fw + x0, t1 = t0 + nx - 1;      // inclusive bit range of the box row
+      for (int w = t0 >> 5; w <= t1 >> 5; ++w) {
+        const int lo = max(t0, w << 5) & 31, hi = min(t1, (w << 5) + 31) & 31;
+        const uint32_t m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        if ((bits[w] & m) != m) atomicOr(&bits[w], m);
+      }
+    }
+  }
+  __syncthreads();
+  // pass 2: rank of every covered row = exclusive prefix of the popcounts (a thread scans a contiguous span of words)
+  const int span = (nwords + 255) / 256;
+  uint32_t local = 0;
+  for (int w = tid * span; w < min(nwords, (tid + 1) * span); ++w) local += __popc(bits[w]);
+  uint32_t U = 0;
+  uint32_t run = block_exclusive_scan(local, warp_sums, &U);
+  for (int w = tid * span; w < min(nwords, (tid + 1) * span); ++w) {
+    pref[w] = run;
+    run += __popc(bits[w]);
+  }
+  const uint32_t nchunks = U == 0 ? 1u : (U + TR - 1) / TR;                // an empty (view, scale) still closes with bias + ReLU
+  if (nchunks > CAPV) {                                                    // uniform: U is the same in every thread
+    if (tid == 0) {
+      a.tile_ovf[tile] = 1;
+      a.tvs[(size_t)tile * a.VS + vs] = make_uint2(0u, 0u);
+    }
+    return;
+  }
+  for (int i = tid; i < (int)nchunks * TQ; i += 256) qmask[i] = 0u;
+  __syncthreads();
+  // pass 3: which slots of which chunk every quad lists
+  const int nsub = max(1, 256 / (TQ * p.nl));
+  for (int item = tid; item < TQ * p.nl * nsub; item += 256)
+    quad_walk<false>(recs_s, item % TQ, (item / TQ) % p.nl, item / (TQ * p.nl), nsub, fw, hw, bits, pref, qmask, nullptr,
+                     nullptr, nullptr, nullptr);
+  __syncthreads();
+  // pass 4: entries per chunk, segment starts, blob sizes -> blob offsets; one allocation per CTA
+  uint32_t nent = 0, bytes16 = 0;
+  if (tid < (int)nchunks) {
+    for (int q = 0; q < TQ; ++q) {
+      segbeg[tid * TQ + q] = (uint16_t)nent;
+      nent += __popc(qmask[tid * TQ + q]);
+    }
+    nent_s[tid] = (uint16_t)nent;
+    bytes16 = (BLOB_HDR + 16 * nent + ((nent + 15) & ~15u)) >> 4;
+  }
+  uint32_t total16 = 0;
+  // (a chunk with more than MAX_ENT entries would not fit its stage: flagged through the top bit of the scanned sizes)
+  const uint32_t my_off16 = block_exclusive_scan(bytes16 | (nent > (uint32_t)MAX_ENT ? 0x40000000u : 0u), warp_sums, &total16);
+  if (tid == 0) {
+    base_s[0] = atomicAdd(&a.cursors[0], nchunks);
+    base_s[1] = atomicAdd(&a.cursors[1], total16);
+  }
+  __syncthreads();
+  const uint32_t base_desc = base_s[0], base_blob16 = base_s[1];
+  if (total16 >= 0x40000000u || base_desc + nchunks > a.desc_cap || base_blob16 + total16 > a.blob_cap16) {   // pools exhausted
+    if (tid == 0) {
+      a.tile_ovf[tile] = 1;
+      a.tvs[(size_t)tile * a.VS + vs] = make_uint2(0u, 0u);
+    }
+    return;
+  }
+  // pass 5: descriptors, blob headers, row offsets
+  uint4 hdr_s = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < (int)nchunks) {
+    const uint32_t nrows = U == 0 ? 0u : min((uint32_t)TR, U - (uint32_t)tid * TR);
+    const bool last = tid == (int)nchunks - 1;
+    const uint32_t info = (last ? INFO_LAST_VS : 0u) | ((last && vs == a.VS - 1) ? INFO_LAST_TILE : 0u) |
+                          ((uint32_t)s << 8) | ((uint32_t)(vs / p.S) << 16);
+    blob_off16[tid] = base_blob16 + my_off16;
+    hdr_s = make_uint4(base_blob16 + my_off16, bytes16 << 4, nrows | (nent << 16), info);
+    uint32_t* bh = reinterpret_cast<uint32_t*>(a.blob + (size_t)(base_blob16 + my_off16) * 16);
+    for (int q = 0; q < TQ; ++q) {
+      const uint32_t beg = segbeg[tid * TQ + q];
+      bh[q] = beg | ((beg + __popc(qmask[tid * TQ + q])) << 16);
+    }
+    bh[16] = nent;
+    bh[17] = info;
+    bh[18] = 0u;
+    bh[19] = 0u;
+  }
+  if (tid == 0) a.tvs[(size_t)tile * a.VS + vs] = make_uint2(base_desc, nchunks);
+  for (int w = tid; w < nwords; w += 256) {
+    uint32_t m = bits[w], rank = pref[w];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      rank_idx[rank++] = (uint32_t)(w * 32 + b);
+      m &= m - 1;
+    }
+  }
+  __syncthreads();                                                         // blob_off16 is read by every walker
+  // the chunk's rows as runs of consecutive rows (ranks follow the row index, so a run occupies consecutive slots)
+  if (tid < (int)nchunks) {
+    const uint32_t nrows = hdr_s.z & 0xffffu;
+    uint32_t* runs = a.rowoff + (size_t)(base_desc + tid) * TR;
+    uint32_t nruns = 0, start = 0;
+    for (uint32_t r = 1; r <= nrows; ++r) {
+      if (r == nrows || rank_idx[tid * TR + r] != rank_idx[tid * TR + r - 1] + 1) {
+        runs[nruns++] = rank_idx[tid * TR + start] | (start << 22) | ((r - start - 1) << 27);
+        start = r;
+      }
+    }
+    hdr_s.z |= nruns << 8;
+    a.hdr[base_desc + tid] = hdr_s;
+  }
+  // pass 6: the entries
+  for (int item = tid; item < TQ * p.nl * nsub; item += 256)
+    quad_walk<true>(recs_s, item % TQ, (item / TQ) % p.nl, item / (TQ * p.nl), nsub, fw, hw, bits, pref, qmask, segbeg,
+                    blob_off16, nent_s, a.blob);
+}
+
+// ---- pooling ----------------------------------------------------------------------------------------------------------
+struct TilePoolArgs {
+  PoolArgs q;
+  TileLists t;
+  unsigned long long plane_bytes[VFA_MAX_SCALES];   // bytes of one (frame, view) stack of nl planes of Y
+  int nb;                      // frames of this chunk
+  uint32_t* next_item;         // work counter (zeroed before the launch): items = (frame, tile) pairs handed out in order
+  int variant;                 // debug (VFA_TILE_VARIANT): 1 = no row copies (consumer time alone), 2 = consumers apply no
+                               // entries (producer / memory time alone)
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <typename YT>
+__device__ __forceinline__ void load_row8(const uint8_t* row, int lane, float4& va, float4& vb);
+template <>
+__device__ __forceinline__ void load_row8<float>(const uint8_t* row, int lane, float4& va, float4& vb) {
+  va = *reinterpret_cast<const float4*>(row + lane * 16);
+  vb = *reinterpret_cast<const float4*>(row + CH * 2 + lane * 16);
+}
+template <>
+__device__ __forceinline__ void load_row8<__nv_bfloat16>(const uint8_t* row, int lane, float4& va, float4& vb) {
+  const uint2 a = *reinterpret_cast<const uint2*>(row + lane * 8);         // bf16 -> fp32 is a 16-bit shift (exact)
+  const uint2 b = *reinterpret_cast<const uint2*>(row + CH + lane * 8);
+  va = make_float4(__uint_as_float(a.x << 16), __uint_as_float(a.x & 0xffff0000u), __uint_as_float(a.y << 16),
+                   __uint_as_float(a.y & 0xffff0000u));
+  vb = make_float4(__uint_as_float(b.x << 16), __uint_as_float(b.x & 0xffff0000u), __uint_as_float(b.y << 16),
+                   __uint_as_float(b.y & 0xffff0000u));
+}
+
+// out_s layout: cell (quad q, sub c) at [(q * 4 + c) * CH floats]; inside a cell the 16-byte chunk j sits at j ^ key with
+// key = the cell's column inside the tile (0..7): the owning warp's accesses (fixed cell, 8 consecutive chunks per quarter
+// warp) and the transposed read of the final store (fixed chunk, the 8 cells of a tile row per quarter warp) are both
+// conflict-free.
+__device__ __forceinline__ int cell_key(int q, int c) { return 2 * (q & 3) + (c & 1); }
+
+template <bool MASK, typename YT>
+__global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePoolArgs a) {
+  constexpr int ROWB = RowBytes<YT>::value;
+  constexpr int STAGE = RowBytes<YT>::stage;
+  extern __shared__ uint8_t psm_raw[];
+  uint8_t* psm = psm_raw + ((128u - (smem_u32(psm_raw) & 127u)) & 127u);
+  float* out_s = reinterpret_cast<float*>(psm);
+  uint8_t* stages = psm + (size_t)TC * TC * CH * 4;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(stages + (size_t)TSTAGES * STAGE);
+  unsigned long long* empty = full + TSTAGES;
+  float* bias_s = reinterpret_cast<float*>(empty + TSTAGES);               // [S][CH]
+  const AggParams& p = a.q.p;
+  const TileLists& t = a.t;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_items = t.n_tiles * a.nb;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TSTAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], TQ);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.S * CH; i += blockDim.x) bias_s[i] = __ldg(pick(p.bias, i / CH) + i % CH);
+  // Dynamic tile scheduling: tiles differ 2x in cost, a static deal leaves the SMs idle 25 % of the time.  Thread 0 draws
+  // the NEXT item from a global counter at the start of every tile (the atomic's latency hides behind the tile) and every
+  // warp picks it up behind the CTA-wide barrier that ends the tile.
+  __shared__ int item_s[2];
+  if (threadIdx.x == 0) item_s[0] = (int)atomicAdd(a.next_item, 1u);
+  __syncthreads();
+
+  if (warp >= TQ) {
+    // ================= producers: chunk descriptors -> bulk copies =================
+    // NPROD warps share the chunk stream round-robin (warp j issues the chunks whose CTA-wide running index is j mod
+    // NPROD): a bulk copy is issued from uniform registers, one lane at a time, ~100 cycles each -- one warp alone cannot
+    // feed the ring.  The stage of a chunk is its running index mod TSTAGES, whichever warp issues it.
+    const int pj = warp - TQ;
+    uint32_t seq = (uint32_t)pj;                   // running index of the next chunk this warp issues
+    uint32_t st = (uint32_t)pj % TSTAGES, ph = 1u ^ (((uint32_t)pj / TSTAGES) & 1u);   // parity awaited on empty[st]
+    uint32_t tile_seq0 = 0;                        // running index of the current tile's first chunk
+#ifdef VFA_TILE_PROFILE
+    long long t_desc = 0, t_empty = 0, t_issue = 0, n_chunks = 0;
+    const long long t_begin = clock64();
+#endif
+    for (int round = 0;; ++round) {
+      const int item = item_s[round & 1];
+      if (item >= n_items) break;
+      const int tile = item % t.n_tiles, bl = item / t.n_tiles;
+      if (__ldg(t.tile_ovf + tile)) {
+        named_bar_sync(2, POOL_THREADS);
+        continue;
+      }
+      const uint2 mine = lane < t.VS ? __ldg(t.tvs + (size_t)tile * t.VS + lane) : make_uint2(0u, 0u);
+      uint32_t total = mine.y;                     // chunks of the tile
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+      const uint32_t tile_end = tile_seq0 + total;
+      // cursor of the prefetcher: (view-scale, chunk inside it) of running index pf_seq; it runs PREFETCH of this warp's
+      // chunks ahead of the issue loop
+      uint32_t pf_seq = seq;
+      int pf_vs = 0;
+      uint32_t pf_k = seq - tile_seq0, pf_first = __shfl_sync(0xffffffffu, mine.x, 0), pf_cnt = __shfl_sync(0xffffffffu, mine.y, 0);
+      auto settle = [&]() {                        // carry pf_k over the (view, scale) boundaries
+        while (pf_vs < t.VS && pf_k >= pf_cnt) {
+          pf_k -= pf_cnt;
+          ++pf_vs;
+          const int src = pf_vs < t.VS ? pf_vs : 0;
+          pf_first = __shfl_sync(0xffffffffu, mine.x, src);
+          pf_cnt = __shfl_sync(0xffffffffu, mine.y, src);
+        }
+      };
+      settle();
+      uint4 hq[PREFETCH];
+      uint32_t rq[PREFETCH];
+      auto fetch = [&](uint4& h, uint32_t& r) {
+        if (pf_seq < tile_end) {
+          const uint32_t id = pf_first + pf_k;
+          h = __ldg(t.hdr + id);
+          r = lane < TR ? __ldg(t.rowoff + (size_t)id * TR + lane) : 0u;
+          pf_seq += NPROD;
+          pf_k += NPROD;
+          settle();
+        } else {
+          h = make_uint4(0u, 0u, 0u, 0u);
+          r = 0u;
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < PREFETCH; ++i) fetch(hq[i], rq[i]);
+      // the descriptor ring is indexed statically (unrolled by PREFETCH): slot j is consumed and refilled in place, so no
+      // register that a load in flight will write is ever moved (a rotating copy would wait for the load every chunk)
+      bool more = seq < tile_end;
+      while (more) {
+#pragma unroll
+        for (int j = 0; j < PREFETCH; ++j) {
+#ifdef VFA_TILE_PROFILE
+          const long long c0 = clock64();
+          asm volatile("" ::"r"(hq[j].x), "r"(hq[j].w), "r"(rq[j]) : "memory");      // the descriptor loads have landed
+          const long long c1 = clock64();
+#endif
+          const uint4 h = hq[j];
+          const uint32_t r = rq[j];
+          fetch(hq[j], rq[j]);
+          mbar_wait(&empty[st], ph);
+#ifdef VFA_TILE_PROFILE
+          const long long c2 = clock64();
+#endif
+          uint8_t* sb = stages + (size_t)st * STAGE;
+          const uint32_t nrows = h.z & 0xffu, nruns = (h.z >> 8) & 0xffu;
+          const int s = (int)((h.w >> 8) & 0xffu), v = (int)(h.w >> 16);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[st], h.y + ((a.variant & 1) ? 0u : nrows * ROWB));
+            bulk_g2s(sb + TR * ROWB, t.blob + (size_t)h.x * 16, h.y, &full[st]);
+          }
+          __syncwarp();
+          if (lane < (int)nruns && !(a.variant & 1)) {   // one bulk copy per run of consecutive rows
+            const uint8_t* ybase = reinterpret_cast<const uint8_t*>(pick(a.q.y, s)) +
+                                   (size_t)(bl * p.V + v) * pick(a.plane_bytes, s);
+            bulk_g2s(sb + ((r >> 22) & 31u) * ROWB, ybase + (size_t)(r & 0x3fffffu) * ROWB, ((r >> 27) + 1u) * ROWB, &full[st]);
+          }
+          st += NPROD;
+          if (st >= TSTAGES) {
+            st -= TSTAGES;
+            ph ^= 1u;
+          }
+          seq += NPROD;
+#ifdef VFA_TILE_PROFILE
+          t_desc += c1 - c0;
+          t_empty += c2 - c1;
+          t_issue += clock64() - c2;
+          ++n_chunks;
+#endif
+          if (seq >= tile_end) {
+            more = false;
+            break;
+          }
+        }
+      }
+      tile_seq0 = tile_end;
+      named_bar_sync(2, POOL_THREADS);
+    }
+#ifdef VFA_TILE_PROFILE
+    if (lane == 0 && (blockIdx.x % 37) == 0)
+      printf("cta %3d producer %d: %lld chunks, total %lld cyc; per chunk: descriptor wait %lld, empty wait %lld, issue %lld\n",
+             blockIdx.x, pj, n_chunks, clock64() - t_begin, t_desc / max(n_chunks, 1ll), t_empty / max(n_chunks, 1ll),
+             t_issue / max(n_chunks, 1ll));
+#endif
+  } else {
+    // ================= consumers: one warp per quad =================
+    const int q = warp;
+    const int cy0 = 2 * (q >> 2), cx0 = 2 * (q & 3);              // inside the tile
+    uint32_t st = 0, ph = 0;                       // stage and the parity the consumers wait for on full[st]
+#ifdef VFA_TILE_PROFILE
+    long long t_full = 0, t_work = 0, t_epi = 0, t_out = 0, n_chunks = 0;
+    const long long t_begin = clock64();
+#endif
+    for (int round = 0;; ++round) {
+      const int item = item_s[round & 1];
+      if (item >= n_items) break;
+      if (threadIdx.x == 0) item_s[(round + 1) & 1] = (int)atomicAdd(a.next_item, 1u);
+      const int tile = item % t.n_tiles, bl = item / t.n_tiles;
+      if (__ldg(t.tile_ovf + tile)) {
+        named_bar_sync(2, POOL_THREADS);
+        continue;
+      }
+      const int b = a.q.b0 + bl;
+      const int ty0 = (tile / t.tiles_x) * TC, tx0 = (tile % t.tiles_x) * TC;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float* o = out_s + (q * 4 + c) * CH;
+        *reinterpret_cast<float4*>(o + ((lane ^ cell_key(q, c)) << 2)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(o + CH / 2 + ((lane ^ cell_key(q, c)) << 2)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float acc[4][8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+      while (true) {
+#ifdef VFA_TILE_PROFILE
+        const long long c0 = clock64();
+#endif
+        mbar_wait(&full[st], ph);
+#ifdef VFA_TILE_PROFILE
+        const long long c1 = clock64();
+#endif
+        const uint8_t* sb = stages + (size_t)st * STAGE;
+        const uint8_t* meta = sb + TR * ROWB;
+        const uint32_t seg = *reinterpret_cast<const uint32_t*>(meta + 4 * q);
+        const uint32_t nent = *reinterpret_cast<const uint32_t*>(meta + 64);
+        const uint32_t info = *reinterpret_cast<const uint32_t*>(meta + 68);
+        const float4* wv = reinterpret_cast<const float4*>(meta + BLOB_HDR);
+        const uint8_t* sl = meta + BLOB_HDR + 16 * nent;
+        const uint32_t e1 = (a.variant & 2) ? 0u : seg >> 16;
+        // entries in groups of two, software-pipelined over two static register sets (A / B): the slot, weight and row
+        // loads of the next group are in flight while the packed FMAs of the current one issue
+        for (uint32_t e = seg & 0xffffu; e < e1; e += 2) {
+          const bool two = e + 1 < e1;
+          const uint32_t s0 = sl[e], s1 = two ? sl[e + 1] : s0;
+          const float4 w0 = wv[e];
+          const float4 w1 = wv[two ? e + 1 : e];
+          float4 va0, vb0, va1, vb1;
+          load_row8<YT>(sb + s0 * ROWB, lane, va0, vb0);
+          load_row8<YT>(sb + s1 * ROWB, lane, va1, vb1);
+          fside::fma8(acc[0], w0.x, va0, vb0);
+          fside::fma8(acc[1], w0.y, va0, vb0);
+          fside::fma8(acc[2], w0.z, va0, vb0);
+          fside::fma8(acc[3], w0.w, va0, vb0);
+          if (two) {
+            fside::fma8(acc[0], w1.x, va1, vb1);
+            fside::fma8(acc[1], w1.y, va1, vb1);
+            fside::fma8(acc[2], w1.z, va1, vb1);
+            fside::fma8(acc[3], w1.w, va1, vb1);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == TSTAGES) {
+          st = 0;
+          ph ^= 1u;
+        }
+#ifdef VFA_TILE_PROFILE
+        const long long c2 = clock64();
+        t_full += c1 - c0;
+        t_work += c2 - c1;
+        ++n_chunks;
+#endif
+        if (info & INFO_LAST_VS) {
+          // + bias, ReLU (vfa_op.py:123-124), sum over scales and views (vfanet.py:79, :82)
+          const int s = (int)((info >> 8) & 0xffu), v = (int)(info >> 16);
+          const float4 bi0 = *reinterpret_cast<const float4*>(bias_s + s * CH + lane * 4);
+          const float4 bi1 = *reinterpret_cast<const float4*>(bias_s + s * CH + CH / 2 + lane * 4);
+          const float bb[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float* o = out_s + (q * 4 + c) * CH + ((lane ^ cell_key(q, c)) << 2);
+            float4 o0 = *reinterpret_cast<const float4*>(o);
+            float4 o1 = *reinterpret_cast<const float4*>(o + CH / 2);
+            float tt[8];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              tt[i] = acc[c][i] + bb[i];
+              bits |= (tt[i] > 0.f ? 1u : 0u) << i;
+              acc[c][i] = 0.f;
+            }
+            o0.x += fmaxf(tt[0], 0.f); o0.y += fmaxf(tt[1], 0.f); o0.z += fmaxf(tt[2], 0.f); o0.w += fmaxf(tt[3], 0.f);
+            o1.x += fmaxf(tt[4], 0.f); o1.y += fmaxf(tt[5], 0.f); o1.z += fmaxf(tt[6], 0.f); o1.w += fmaxf(tt[7], 0.f);
+            *reinterpret_cast<float4*>(o) = o0;
+            *reinterpret_cast<float4*>(o + CH / 2) = o1;
+            if (MASK) {
+              const int cy = ty0 + cy0 + (c >> 1), cx = tx0 + cx0 + (c & 1);
+              const bool ok = cy < p.L && cx < p.W;
+              fside::store_mask_words(p.mask + (((size_t)b * p.V + v) * p.S + s) * (CH / 32) * p.LW + (ok ? cy * p.W + cx : 0),
+                                      (size_t)p.LW, lane, bits, ok);
+            }
+          }
+        }
+#ifdef VFA_TILE_PROFILE
+        t_epi += clock64() - c2;
+#endif
+        if (info & INFO_LAST_TILE) break;
+      }
+#ifdef VFA_TILE_PROFILE
+      const long long c3 = clock64();
+#endif
+      // ---- the tile's 8 x 8 x 256 block of partial sums -> global memory ----
+      if (a.q.out_nhwc) {
+        // [B, L, W, C]: a warp writes its own four cells, 2 x 512 contiguous bytes each (no cross-warp exchange)
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cy = ty0 + cy0 + (c >> 1), cx = tx0 + cx0 + (c & 1);
+          if (cy >= p.L || cx >= p.W) continue;
+          const float* o = out_s + (q * 4 + c) * CH + ((lane ^ cell_key(q, c)) << 2);
+          float* g = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
+          *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(o);
+          *reinterpret_cast<float4*>(g + CH / 2) = *reinterpret_cast<const float4*>(o + CH / 2);
+        }
+      } else {
+        // [B, C, L, W]: warp w stores channels [16w, 16w + 16); one store instruction = one channel x 4 tile rows x 8 cells
+        // (four full 32-byte sectors); a lane reads its cell's four channels with one conflict-free LDS.128
+        named_bar_sync(1, CONSUMER_THREADS);
+        const int col = lane & 7;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int row = 4 * half + (lane >> 3);
+          const int cy = ty0 + row, cx = tx0 + col;
+          const bool ok = cy < p.L && cx < p.W;
+          const int cell_s = ((row >> 1) * 4 + (col >> 1)) * 4 + (row & 1) * 2 + (col & 1);      // quad * 4 + sub
+          float* g = p.out + ((size_t)b * CH) * p.LW + (size_t)cy * p.W + cx;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = 4 * warp + j;                                  // logical 16-byte chunk = channels [4 chunk, +4)
+            const float4 o4 = *reinterpret_cast<const float4*>(out_s + cell_s * CH + (((chunk & ~7) | ((chunk ^ col) & 7)) << 2));
+            if (ok) {
+              // logical chunk j' < 32 holds channels [4j', 4j'+4); chunk 32 + j' holds channels [128 + 4j', ...)
+              const int c0 = chunk < 32 ? 4 * chunk : CH / 2 + 4 * (chunk - 32);
+              g[(size_t)(c0 + 0) * p.LW] = o4.x;
+              g[(size_t)(c0 + 1) * p.LW] = o4.y;
+              g[(size_t)(c0 + 2) * p.LW] = o4.z;
+              g[(size_t)(c0 + 3) * p.LW] = o4.w;
+            }
+          }
+        }
+      }
+#ifdef VFA_TILE_PROFILE
+      t_out += clock64() - c3;
+#endif
+      named_bar_sync(2, POOL_THREADS);
+    }
+#ifdef VFA_TILE_PROFILE
+    if (lane == 0 && (blockIdx.x % 37) == 0 && (warp == 0 || warp == 9))
+      printf("cta %3d warp %2d: %lld chunks, total %lld cyc; per chunk: full wait %lld, work %lld, epilogue %lld; tile store total %lld\n",
+             blockIdx.x, warp, n_chunks, clock64() - t_begin, t_full / max(n_chunks, 1ll), t_work / max(n_chunks, 1ll),
+             t_epi / max(n_chunks, 1ll), t_out);
+#endif
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+struct TileLayout {
+  size_t off_cursors, off_ovf, off_tvs, off_hdr, off_rowoff, off_blob, total;
+  int tiles_x, n_tiles, VS, max_words;
+  uint32_t desc_cap, blob_cap16;
+  size_t build_smem;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static bool tile_enabled() {
+  return env_int("VFA_POOL_TILE", 1) != 0 && env_int("VFA_POOL_QUAD", 1) != 0;
+}
+
+static TileLayout tile_layout(const AggParams& p) {
+  TileLayout L = {};
+  L.VS = p.V * p.S;
+  // The chunk lists cost 0.3 ms to build (the quads' texel lists 0.15 ms) and save 0.1 ms of pooling per frame: they pay
+  // from two frames per call on (VFA_POOL_TILE=2 forces them for any batch).
+  if (!tile_enabled() || L.VS > 32 || (p.B < 2 && env_int("VFA_POOL_TILE", 1) < 2)) return L;
+  size_t max_bits = 0;
+  for (int s = 0; s < p.S; ++s) max_bits = max_bits > (size_t)p.nl * p.sc[s].fh * p.sc[s].fw ? max_bits : (size_t)p.nl * p.sc[s].fh * p.sc[s].fw;
+  L.max_words = (int)((max_bits + 31) / 32);
+  L.build_smem = (size_t)p.nl * TC * TC * 32 + (size_t)L.max_words * 8 + (size_t)CAPV * TQ * 4 + (size_t)CAPV * TQ * 2 +
+                 (size_t)CAPV * TR * 4;
+  if (L.build_smem > 200 * 1024 || max_bits >= (1u << 22)) {          // very large feature maps: the list kernel serves them
+    L = {};
+    return L;
+  }
+  L.tiles_x = (p.W + TC - 1) / TC;
+  L.n_tiles = L.tiles_x * ((p.L + TC - 1) / TC);
+  // pools: chunks and blob bytes per (tile, view, scale, layer); VFA_POOL_TILE_CAP scales both (tests force overflows)
+  const int cap = env_int("VFA_POOL_TILE_CAP", 100);
+  const unsigned long long iters = (unsigned long long)L.n_tiles * L.VS * p.nl;
+  unsigned long long dc = iters * 3ull * cap / 100 + L.n_tiles * L.VS, bc16 = iters * (3072ull / 16) * cap / 100 + L.n_tiles * L.VS * 8ull;
+  if (dc > 0x7fffffffull) dc = 0x7fffffffull;
+  if (bc16 > 0x7fffffffull) bc16 = 0x7fffffffull;
+  L.desc_cap = (uint32_t)dc;
+  L.blob_cap16 = (uint32_t)bc16;
+  size_t o = 0;
+  L.off_cursors = o; o += 256;
+  L.off_ovf = o;     o += align256((size_t)L.n_tiles);
+  L.off_tvs = o;     o += align256((size_t)L.n_tiles * L.VS * sizeof(uint2));
+  L.off_hdr = o;     o += align256((size_t)L.desc_cap * sizeof(uint4));
+  L.off_rowoff = o;  o += align256((size_t)L.desc_cap * TR * sizeof(uint32_t));
+  L.off_blob = o;    o += align256((size_t)L.blob_cap16 * 16);
+  L.total = o;
+  return L;
+}
+
+}  // namespace ptile
+
+using namespace ptile;
+
+size_t tile_pool_workspace_bytes(const AggParams& p) { return tile_layout(p).total; }
+
+// chunk lists of every tile from the tap records (once per table; static for fixed cameras)
+int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStream_t st) {
+  const TileLayout L = tile_layout(p);
+  if (L.total == 0) return VFA_OK;
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  VFA_CUDA(cudaMemsetAsync(w8, 0, L.off_tvs, st));                         // cursors + overflow flags
+  BuildArgs a;
+  a.p = p;
+  a.recs = recs;
+  a.cursors = reinterpret_cast<uint32_t*>(w8 + L.off_cursors);
+  a.tile_ovf = w8 + L.off_ovf;
+  a.tvs = reinterpret_cast<uint2*>(w8 + L.off_tvs);
+  a.hdr = reinterpret_cast<uint4*>(w8 + L.off_hdr);
+  a.rowoff = reinterpret_cast<uint32_t*>(w8 + L.off_rowoff);
+  a.blob = w8 + L.off_blob;
+  a.desc_cap = L.desc_cap;
+  a.blob_cap16 = L.blob_cap16;
+  a.tiles_x = L.tiles_x;
+  a.VS = L.VS;
+  a.max_words = L.max_words;
+  VFA_CUDA(cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.build_smem));
+  tile_build_kernel<<<L.n_tiles * L.VS, 256, L.build_smem, st>>>(a);
+  VFA_LAUNCH_CHECK("tile_build_kernel");
+  return VFA_OK;
+}
+
+// pooling of one frame chunk from the chunk lists; `q` carries the problem, Y, the output and the frame offset
+int launch_pool_tile(fside::PoolArgs q, void* ws, int nb, bool y_bf16, cudaStream_t st) {
+  const AggParams& p = q.p;
+  const TileLayout L = tile_layout(p);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  TilePoolArgs a;
+  a.t.tile_ovf = w8 + L.off_ovf;
+  a.t.tvs = reinterpret_cast<const uint2*>(w8 + L.off_tvs);
+  a.t.hdr = reinterpret_cast<const uint4*>(w8 + L.off_hdr);
+  a.t.rowoff = reinterpret_cast<const uint32_t*>(w8 + L.off_rowoff);
+  a.t.blob = w8 + L.off_blob;
+  a.t.tiles_x = L.tiles_x;
+  a.t.n_tiles = L.n_tiles;
+  a.t.VS = L.VS;
+  q.tile_ovf = a.t.tile_ovf;
+  q.ptiles_x = L.tiles_x;
+  a.q = q;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s)
+    a.plane_bytes[s] = (unsigned long long)p.nl * p.sc[s].fh * p.sc[s].fw * CH * (y_bf16 ? 2 : 4);
+  a.nb = nb;
+  a.next_item = reinterpret_cast<uint32_t*>(w8 + L.off_cursors) + 2;
+  VFA_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(uint32_t), st));
+  a.variant = env_int("VFA_TILE_VARIANT", 0);
+  int dev = 0, sms = 148;
+  VFA_CUDA(cudaGetDevice(&dev));
+  VFA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long items = (long long)L.n_tiles * nb;
+  const int grid = (int)(items < sms ? items : sms);
+  const bool mask = p.mask != nullptr;
+#define VFA_LAUNCH_POOL_TILE(M, T)                                                                                   \
+  do {                                                                                                               \
+    VFA_CUDA(cudaFuncSetAttribute(pool_tile_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                  (int)RowBytes<T>::smem));                                                       \
+    pool_tile_kernel<M, T><<<grid, POOL_THREADS, RowBytes<T>::smem, st>>>(a);                                     \
+  } while (0)
+  if (y_bf16) {
+    if (mask) VFA_LAUNCH_POOL_TILE(true, __nv_bfloat16);
+    else VFA_LAUNCH_POOL_TILE(false, __nv_bfloat16);
+  } else {
+    if (mask) VFA_LAUNCH_POOL_TILE(true, float);
+    else VFA_LAUNCH_POOL_TILE(false, float);
+  }
+#undef VFA_LAUNCH_POOL_TILE
+  VFA_LAUNCH_CHECK("pool_tile_kernel");
+  return VFA_OK;
+}
+
+// the flags of the tiles the walking kernel has to complete (and the tile geometry it needs to find them)
+void tile_pool_overflow_view(const AggParams& p, void* ws, const uint8_t** tile_ovf, int* tiles_x) {
+  const TileLayout L = tile_layout(p);
+  *tile_ovf = reinterpret_cast<const uint8_t*>(ws) + L.off_ovf;
+  *tiles_x = L.tiles_x;
+}
+
+}  // namespace vfa

@@ -172,7 +172,10 @@ def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, w
     shape = make_shape(feats_cl, geom.n_layers)
     dev = feats_cl[0].device
     if out is None:
-        out = torch.empty(shape.batch, shape.channels, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
+        if int(flags) & _lib.FLAG_OUT_NHWC:      # [B, L, W, C]: what a channels-last head reads without a permute
+            out = torch.empty(shape.batch, geom.grid_l, geom.grid_w, shape.channels, dtype=torch.float32, device=dev)
+        else:
+            out = torch.empty(shape.batch, shape.channels, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
     ws = workspace if workspace is not None else workspace_for(geom, shape, flags, dev)
     f = int(flags) | (_lib.FLAG_WEIGHTS_PREPARED if prepared else 0)
     if table_prepared:
