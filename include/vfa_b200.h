@@ -88,6 +88,15 @@ typedef struct {
                                         vfanet.py:131-139) instead of [B, C, L, W]; the backward reads d_grad_out in the
                                         layout it is handed with the same flag                                          */
 
+#define VFA_FLAG_OUT_ACCUMULATE 256u  /* with VFA_FLAG_OUT_NHWC: the result is ADDED into d_out (red.global.add.v4.f32, system
+                                        scope) instead of stored; the caller zero-initialises d_out.  d_out may be a PEER
+                                        GPU's memory mapped over NVLink: camera-sharded ranks reduce their partial maps
+                                        inside the pooling kernel, tile by tile, instead of calling a collective afterwards
+                                        (the sum over cameras of reference vfanet.py:82 is taken across GPUs)             */
+#define VFA_FLAG_OUT_MULTICAST 512u   /* as OUT_ACCUMULATE, but d_out is the MULTICAST address of a symmetric allocation
+                                        (cuMulticast / torch symmetric memory): multimem.red.add -- the NVSwitch adds the
+                                        tile into every GPU's replica (in-switch all-reduce fused into the kernel)         */
+
 int vfa_version(void);
 const char* vfa_last_error(void);
 

@@ -115,3 +115,49 @@ def test_camera_sharding_two_gpus_matches_single_gpu():
     results = mgr.dict()
     mp.spawn(_views_worker, args=(2, _free_port(), results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def _fused_views_worker(rank, world, port, results):
+    import torch.distributed as dist
+    import vfa_b200
+    from vfa_b200 import distributed as vd
+    from vfa_b200 import geometry, synthetic
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        g = geometry.MULTIVIEWC
+        V, B = 5, 2
+        zs = list(range(0, g.grid_height, g.cube_size[2]))
+        grid = geometry.grid_for(g).to(dev)
+        cgeom = vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid.shape[:2], g.name, g.image_size)
+        calibs = synthetic.ring_calibs(g, n_views=V).to(dev)
+        params = synthetic.collapse_params(g, seed=23)
+        ws, bs = [w.to(dev) for w, _ in params], [b.to(dev) for _, b in params]
+        v0, v1 = vd.view_bounds(V, world, rank)                          # 3 + 2 cameras
+        agg = vd.FusedViewAggregator(cgeom, B)
+        table_local = vfa_b200.build_table(cgeom, calibs[v0:v1], grid)
+        table_all = vfa_b200.build_table(cgeom, calibs, grid)
+        ok = True
+        for step in range(3):                                            # both buffer slots, and a reuse
+            feats = [vfa_b200.to_channels_last(f.to(dev)) for f in synthetic.features(g, batch=B, n_views=V, seed=40 + step)]
+            local = [f[:, v0:v1].contiguous() for f in feats]
+            got = agg(local, table_local, ws, bs).clone()
+            want = vfa_b200.aggregate_forward_raw(feats, table_all, ws, bs)
+            err = (got - want).abs()
+            ok = ok and bool((err <= 2e-6 + 2e-6 * want.abs()).all())     # the same terms, summed in another order
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_fused_multicast_camera_sharding_two_gpus_matches_single_gpu():
+    """Camera shards reduced inside the pooling kernel through the NVLink multicast address (multimem.red): same map as one
+    GPU aggregating all cameras, on every rank, for three consecutive steps."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_fused_views_worker, args=(2, _free_port(), results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}

@@ -19,6 +19,8 @@ FLAG_BF16_FEATURES = 16
 FLAG_GRID_SIDE = 32
 FLAG_TABLE_PREPARED = 64
 FLAG_OUT_NHWC = 128
+FLAG_OUT_ACCUMULATE = 256
+FLAG_OUT_MULTICAST = 512
 
 # VFA_B200_LIB: another build of the same library (A/B timing of compile-time kernel variants, scripts/build_variant.sh)
 LIB_PATH = os.environ.get('VFA_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',

@@ -199,6 +199,8 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
               "bf16 feature maps are supported by the tcgen05 forward (C = 256) only, without the backward mask");
   VFA_REQUIRE(!(flags & VFA_FLAG_OUT_NHWC) || (use_umma && !(flags & VFA_FLAG_GRID_SIDE)), VFA_ERR_UNSUPPORTED,
               "VFA_FLAG_OUT_NHWC is implemented by the feature-side forward (C = 256, without VFA_FLAG_GRID_SIDE) only");
+  VFA_REQUIRE(!(flags & (VFA_FLAG_OUT_ACCUMULATE | VFA_FLAG_OUT_MULTICAST)) || (flags & VFA_FLAG_OUT_NHWC),
+              VFA_ERR_UNSUPPORTED, "VFA_FLAG_OUT_ACCUMULATE / _MULTICAST need VFA_FLAG_OUT_NHWC (16-byte channel vectors)");
   if ((flags & VFA_FLAG_FORCE_UMMA) && !use_umma) {
     set_error("tcgen05 path requested but unsupported for channels=%d layers=%d", shape->channels, geom->n_layers);
     return VFA_ERR_UNSUPPORTED;

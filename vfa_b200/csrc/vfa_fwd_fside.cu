@@ -643,8 +643,13 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
     const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
     if (a.out_nhwc) {          // 512 contiguous bytes per warp store
       float* o = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
-      *reinterpret_cast<float4*>(o) = o0;
-      *reinterpret_cast<float4*>(o + CH / 2) = o1;
+      if (a.out_mode == 0) {
+        *reinterpret_cast<float4*>(o) = o0;
+        *reinterpret_cast<float4*>(o + CH / 2) = o1;
+      } else {
+        red_add_v4(o, o0, a.out_mode);
+        red_add_v4(o + CH / 2, o1, a.out_mode);
+      }
       continue;
     }
     float* o = p.out + (size_t)b * CH * p.LW + cy * p.W + cx;
@@ -896,8 +901,13 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_LIST_MINBLOCKS) pool_list_ker
     const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
     if (a.out_nhwc) {          // 512 contiguous bytes per warp store
       float* o = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
-      *reinterpret_cast<float4*>(o) = o0;
-      *reinterpret_cast<float4*>(o + CH / 2) = o1;
+      if (a.out_mode == 0) {
+        *reinterpret_cast<float4*>(o) = o0;
+        *reinterpret_cast<float4*>(o + CH / 2) = o1;
+      } else {
+        red_add_v4(o, o0, a.out_mode);
+        red_add_v4(o + CH / 2, o1, a.out_mode);
+      }
       continue;
     }
     float* o = p.out + (size_t)b * CH * p.LW + cy * p.W + cx;
@@ -1666,6 +1676,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     YGemmArgs g;
     PoolArgs q = {};
     q.out_nhwc = (flags & VFA_FLAG_OUT_NHWC) ? 1 : 0;
+    q.out_mode = (flags & VFA_FLAG_OUT_MULTICAST) ? 2 : ((flags & VFA_FLAG_OUT_ACCUMULATE) ? 1 : 0);
     q.p = p;
     q.recs = recs;
     q.b0 = b0;

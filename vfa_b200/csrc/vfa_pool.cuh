@@ -33,6 +33,8 @@ struct PoolArgs {
   const uint8_t* tile_ovf;
   int ptiles_x;
   int out_nhwc;              // 0: out [B, C, L, W]; 1: out [B, L, W, C]
+  int out_mode;              // 0: store; 1: red.add into `out` (own, or a peer GPU's memory over NVLink); 2: multimem.red.add
+                             // on a multicast address (the NVSwitch adds into every GPU's replica).  1 / 2: [B, L, W, C] only
 };
 constexpr uint32_t LIST_OVERFLOW = 0xffffffffu;
 
@@ -64,6 +66,18 @@ __device__ __forceinline__ void store_mask_words(uint32_t* words, size_t word_st
     words[(size_t)(lane >> 3) * word_stride] = lo;
     words[(size_t)(4 + (lane >> 3)) * word_stride] = hi;
   }
+}
+
+// 16-byte reduction into global memory: plain (mode 1) or through the NVLink multicast object (mode 2)
+__device__ __forceinline__ void red_add_v4(float* dst, const float4& v, int mode) {
+  if (mode == 2)
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  else
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
 }
 
 // output element (frame b, channel c, cell) in either layout

@@ -651,8 +651,14 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
           if (cy >= p.L || cx >= p.W) continue;
           const float* o = out_s + (q * 4 + c) * CH + ((lane ^ cell_key(q, c)) << 2);
           float* g = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
-          *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(o);
-          *reinterpret_cast<float4*>(g + CH / 2) = *reinterpret_cast<const float4*>(o + CH / 2);
+          const float4 o0 = *reinterpret_cast<const float4*>(o), o1 = *reinterpret_cast<const float4*>(o + CH / 2);
+          if (a.q.out_mode == 0) {
+            *reinterpret_cast<float4*>(g) = o0;
+            *reinterpret_cast<float4*>(g + CH / 2) = o1;
+          } else {                 // fused collective: this GPU's cameras are ADDED into the (peer / multicast) map
+            fside::red_add_v4(g, o0, a.q.out_mode);
+            fside::red_add_v4(g + CH / 2, o1, a.q.out_mode);
+          }
         }
       } else {
         // [B, C, L, W]: warp w stores channels [16w, 16w + 16); one store instruction = one channel x 4 tile rows x 8 cells

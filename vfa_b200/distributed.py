@@ -186,3 +186,62 @@ def cuda_compute(geom_of, flags: int = 0):
         table = vfa_op.build_table(geom_of(grid_slab.shape[:2]), calibs, grid_slab)
         return vfa_op.aggregate(feats, table, weights, biases, flags=flags)
     return compute
+
+
+class FusedViewAggregator:
+    """Camera-sharded aggregation with the cross-GPU sum fused INTO the pooling kernel (inference / latency mode).
+
+    Rank g owns cameras [v0, v1) (`view_bounds`).  Its pooling kernel does not store the partial BEV map: every finished
+    8 x 8-cell tile is added straight into a symmetric [B, L, W, C] buffer through the NVLink multicast address
+    (`multimem.red.add.v4.f32`, VFA_FLAG_OUT_MULTICAST) -- the NVSwitch performs the reduction and writes the sum into every
+    GPU's replica while the SMs are still pooling the next tiles.  No NCCL call, no separate all-reduce pass, no partial map
+    in HBM: the collective costs one cross-rank barrier per step.  (Sum over cameras: reference vfanet.py:82; every term is
+    already past its ReLU, so partial sums of camera subsets add exactly, up to fp32 summation order.)
+
+    Two buffer slots alternate: the slot of step i + 1 is zeroed before the barrier that ends step i, so one barrier per
+    step orders both "all adds of step i have landed" and "every replica of the next slot is zero".
+
+    Needs torch symmetric memory with multicast support (NVSwitch); `available()` tells.  Results come back as a
+    [B, C, L, W] view with channels-last strides of the local replica (valid until the slot is reused two steps later).
+    """
+
+    def __init__(self, geom, batch: int, channels: int = 256, group=None, flags: int = 0):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.geom, self.B, self.C = geom, int(batch), int(channels)
+        self.flags = int(flags) | _lib.FLAG_OUT_NHWC | _lib.FLAG_OUT_MULTICAST
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.buf = symm_mem.empty(2, self.B, geom.grid_l, geom.grid_w, self.C, dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        if not self.hdl.multicast_ptr:
+            raise RuntimeError('symmetric memory has no multicast address on this system (no NVSwitch multicast support)')
+        self.slot_bytes = self.buf[0].numel() * 4
+        self.buf.zero_()
+        self.hdl.barrier(channel=0)
+        self._step = 0
+        self.workspace = None
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem      # noqa: F401
+        except Exception:
+            return False
+        return dist.is_initialized() and torch.cuda.is_available()
+
+    def __call__(self, feats_local_cl, table_local, weights, biases):
+        """feats_local_cl: S channels-last tensors [B, V_g, fH, fW, C] of this rank's cameras (V_g may be 0);
+        table_local: ProjectionTable of the same cameras (None when V_g == 0).  Collective: every rank calls it."""
+        from . import vfa_op
+        s = self._step & 1
+        self.buf[1 - s].zero_()                                  # the other slot: next step's accumulator
+        if table_local is not None and feats_local_cl[0].shape[1] > 0:
+            if self.workspace is None:
+                shape = vfa_op.make_shape(feats_local_cl, self.geom.n_layers)
+                self.workspace = vfa_op.workspace_for(table_local.geom, shape, self.flags, feats_local_cl[0].device)
+            vfa_op.aggregate_forward_raw(feats_local_cl, table_local, weights, biases, self.flags, workspace=self.workspace,
+                                         out_ptr=self.hdl.multicast_ptr + s * self.slot_bytes)
+        self.hdl.barrier(channel=0)
+        self._step += 1
+        return self.buf[s].permute(0, 3, 1, 2)

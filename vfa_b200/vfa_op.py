@@ -163,15 +163,17 @@ def prepare_weights(geom, shape, weights, flags=0, workspace=None) -> torch.Tens
 
 
 def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, workspace=None, prepared=False,
-                          relu_mask=None, table_prepared=False):
+                          relu_mask=None, table_prepared=False, out_ptr=None):
     """No-autograd forward on channels-last features [B,V,fH,fW,C]: one C-ABI call on the current stream.
     relu_mask: optional int32 tensor [B,V,S,ceil(C/32),L*W] receiving the ReLU pass bits for the backward.
     table_prepared: `workspace` was used by the previous call with the same table, shapes and flags (static cameras): the
-    tap records, coverage and texel lists in it are reused instead of rebuilt (VFA_FLAG_TABLE_PREPARED)."""
+    tap records, coverage and texel lists in it are reused instead of rebuilt (VFA_FLAG_TABLE_PREPARED).
+    out_ptr: raw device address written instead of `out` (a peer GPU's buffer or the multicast address of a symmetric
+    allocation, with FLAG_OUT_ACCUMULATE / FLAG_OUT_MULTICAST); returns None in that case."""
     geom = table.geom
     shape = make_shape(feats_cl, geom.n_layers)
     dev = feats_cl[0].device
-    if out is None:
+    if out is None and out_ptr is None:
         if int(flags) & _lib.FLAG_OUT_NHWC:      # [B, L, W, C]: what a channels-last head reads without a permute
             out = torch.empty(shape.batch, geom.grid_l, geom.grid_w, shape.channels, dtype=torch.float32, device=dev)
         else:
@@ -189,7 +191,8 @@ def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, w
                                                 _lib.ptr_array([t.data_ptr() for t in feats_cl]),
                                                 _lib.ptr_array([t.data_ptr() for t in weights]),
                                                 _lib.ptr_array([t.data_ptr() for t in biases]),
-                                                out.data_ptr(), relu_mask.data_ptr() if relu_mask is not None else None,
+                                                out_ptr if out_ptr is not None else out.data_ptr(),
+                                                relu_mask.data_ptr() if relu_mask is not None else None,
                                                 ws.data_ptr(), ws.numel(), f, _stream()))
     return out
 
