@@ -61,6 +61,9 @@ def parse():
                     help='feature-map storage: f32 (parity path, default) or bf16 (half the gather bytes, stated tolerance)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the MultiviewX / Wildtrack B = 1 lines (BASELINE configs 2-3)')
+    ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the strong-scaling (camera-sharded, fused) block')
+    ap.add_argument('--no-config4', action='store_true', help='skip the batch-64 forward+backward block (BASELINE config 4)')
     return ap.parse_args()
 
 
@@ -70,8 +73,8 @@ def load_peaks():
         with open(path) as f:
             p = json.load(f)
         return dict(hbm_gbs=p['hbm_gbs'], tflops=p.get('bf16_tflops_sustained', p['bf16_tflops']),
-                    tflops_burst=p['bf16_tflops'], source='measured (MEASURED_PEAKS.json, sustained bf16 figure: kernel '
-                    'timed inside a long step)')
+                    tflops_burst=p['bf16_tflops'], source='measured (MEASURED_PEAKS.json: copy bandwidth; bf16 sustained for '
+                    'the step timed in a long loop, bf16 burst for kernels timed in isolation)')
     return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source='fallback (B200_PROFILING.md)')
 
 
@@ -329,6 +332,35 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def time_steps(fn, n, barrier, dev, world):
+    """n calls of fn between two barriers, CUDA events on the current stream, max over ranks -> total ms."""
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def pin_to_gpu_numa_node(local_rank):
+    """Bind this process to the CPU cores next to its GPU before pinned host buffers are allocated (first touch places the
+    pages on that NUMA node): the end-to-end path is bound by host memory / PCIe bandwidth when 8 ranks stream at once."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(vis.split(',')[local_rank]) if vis and vis.split(',')[local_rank].isdigit() else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -353,28 +385,39 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     import vfa_b200
+    from vfa_b200 import distributed as vd
     from vfa_b200 import geometry
     from vfa_b200 import synthetic
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def setup(workload, B, v_range=None, features='f32', seed=1234):
+        """Device-resident synthetic problem of one rank: geometry, table inputs, collapse parameters, channels-last
+        features [B,V,fH,fW,C] (logical [B,V,C,fH,fW]; the layout the lateral convs emit in torch.channels_last)."""
+        g = geometry.BENCH_WORKLOADS[workload]
+        zs = list(range(0, g.grid_height, g.cube_size[2]))
+        grid = geometry.grid_for(g).to(dev)
+        calibs = synthetic.ring_calibs(g).to(dev)
+        cg = vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid.shape[:2], g.name, g.image_size)
+        params = synthetic.collapse_params(g, seed=0)
+        ws, bs = [w.to(dev) for w, _ in params], [b.to(dev) for _, b in params]
+        gen = torch.Generator(device=dev).manual_seed(seed + rank)      # every GPU owns different frames
+        v0, v1 = v_range if v_range is not None else (0, g.n_views)
+        feats = [torch.randn(B, v1 - v0, h, w, g.channels, generator=gen, device=dev).relu_() for (h, w) in g.feature_sizes()]
+        if features == 'bf16':
+            feats = [f.to(torch.bfloat16) for f in feats]
+        return dict(g=g, zs=zs, grid=grid, calibs=calibs[v0:v1].contiguous(), cgeom=cg, ws=ws, bs=bs, feats=feats, gen=gen)
+
     geom = geometry.BENCH_WORKLOADS[args.workload]
     B, V, C = args.batch, geom.n_views, geom.channels
-    zs = list(range(0, geom.grid_height, geom.cube_size[2]))
-    grid = geometry.grid_for(geom).to(dev)
-    calibs = synthetic.ring_calibs(geom).to(dev)
-    cgeom = vfa_b200.make_geometry(len(zs), geom.cube_size, zs, grid.shape[:2], geom.name, geom.image_size)
-    params = synthetic.collapse_params(geom, seed=0)
-    weights, biases = [w.to(dev) for w, _ in params], [b.to(dev) for _, b in params]
-
-    # synthetic features, generated on the device (seed differs per rank: every GPU owns different frames);
-    # logical [B,V,C,fH,fW], stored channels-last = the layout the lateral convs emit in torch.channels_last
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    v0, v1 = (0, V)
-    if args.mode == 'views':
-        from vfa_b200 import distributed as _vd
-        v0, v1 = _vd.view_bounds(V, world, rank)
-    feats_cl = [torch.randn(B, v1 - v0, h, w, C, generator=gen, device=dev).relu_() for (h, w) in geom.feature_sizes()]
-    if args.features == 'bf16':
-        feats_cl = [f.to(torch.bfloat16) for f in feats_cl]
-        args.no_e2e = True
+    P = setup(args.workload, B, vd.view_bounds(V, world, rank) if args.mode == 'views' else None, args.features)
+    zs, grid, calibs, cgeom, weights, biases, feats_cl, gen = (P[k] for k in ('zs', 'grid', 'calibs', 'cgeom', 'ws', 'bs',
+                                                                              'feats', 'gen'))
+    v0, v1 = vd.view_bounds(V, world, rank) if args.mode == 'views' else (0, V)
     shape = ws = None
     if args.mode != 'views':
         shape = vfa_b200.make_shape(feats_cl, cgeom.n_layers)
@@ -382,8 +425,6 @@ def main():
     out = torch.empty(B, C, grid.shape[0], grid.shape[1], device=dev)
     nums = workload_numbers(geom, B, 2 if args.features == 'bf16' else 4)
 
-    kernel_ms = []
-    from vfa_b200 import distributed as vd
     zs_geom = lambda lw: vfa_b200.make_geometry(len(zs), geom.cube_size, zs, lw, geom.name, geom.image_size)  # noqa: E731
     if args.backward:
         for t in feats_cl + weights + biases:
@@ -408,7 +449,7 @@ def main():
         if timed_events is not None:
             timed_events[0].record()
         if args.mode == 'views':
-            res = vd.aggregate_views(feats_cl, calibs[v0:v1], grid, weights, biases, views_compute, out_channels=C,
+            res = vd.aggregate_views(feats_cl, calibs, grid, weights, biases, views_compute, out_channels=C,
                                      frames_per_chunk=args.view_chunk)
         elif args.mode == 'slab':
             vd.broadcast_features([f.detach() for f in feats_cl], src=0)
@@ -433,21 +474,18 @@ def main():
         if timed_events is not None:
             timed_events[0].record()
         vfa_b200.aggregate_forward_raw(feats_cl, table, weights, biases, args.flags, out=out, workspace=ws,
-                                       prepared=True)                                # 1 launch (+1 memset if view-split)
+                                       prepared=True)
         if timed_events is not None:
             timed_events[1].record()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):
         step()
     path = vfa_b200.last_kernel_path()
-    # table_build + 3 x prep_weight + tap records + {fused grid-side kernel | coverage bitmap + row lists + unit table +
-    # texel lists + per frame chunk: compacted ygemm + pool_list + its completion pass (pool_quad_kernel<OVF>)}
+    tile_pool = path.startswith('fside') and B >= 2 and os.environ.get('VFA_POOL_TILE', '1') != '0'
+    pool_name = 'pool_tile_kernel' if tile_pool else 'pool_list_kernel'
+    # launches of this repo's kernels per step: table_build + 3 x prep_weight + tap records + {fused grid-side kernel |
+    # coverage bitmap + row lists + unit table + pooling lists (tile_build_kernel or qlist_build_kernel) + per frame chunk:
+    # compacted ygemm + pooling kernel + its completion pass (pool_quad_kernel<OVF>)}; memsets are not counted
     launches_per_step = 5 + (4 + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
     if args.mode == 'views':                          # every frame chunk is a complete call (table and weights included)
         launches_per_step *= -(-B // (args.view_chunk or B))
@@ -472,14 +510,15 @@ def main():
     frames_per_step = B if args.mode in ('slab', 'views') else world * B
     value = frames_per_step * args.steps / (total_ms * 1e-3)
     kern = sum(kernel_ms) / len(kernel_ms)
+    plain = args.mode == 'dp' and not args.backward
 
     # ---- per-kernel durations of the feature-side pair (CUDA events; debug bits switch one kernel off at a time:
     #      64 = GEMM only, 128 = pooling only, 256 = reuse the tap records -> exactly one launch between the events) ----
     per_kernel = None
-    if path.startswith('fside') and args.mode == 'dp' and not args.backward:
+    if path.startswith('fside') and plain:
         table = vfa_b200.build_table(cgeom, calibs, grid)
         per_kernel = {}
-        for kname, bits in (('ygemm_kernel', 64 | 256), ('pool_list_kernel', 128 | 256), ('ygemm_kernel_all_tiles', 64)):
+        for kname, bits in (('ygemm_kernel', 64 | 256), (pool_name, 128 | 256), ('ygemm_kernel_all_tiles', 64)):
             os.environ['VFA_UMMA_VARIANT'] = str(bits)
             if kname == 'ygemm_kernel_all_tiles':        # every (tile, layer) multiplied: the GEMM's own efficiency
                 os.environ['VFA_FSIDE_NO_SKIP'] = '1'
@@ -499,15 +538,20 @@ def main():
         vfa_b200.aggregate_forward_raw(feats_cl, table, weights, biases, args.flags, out=out, workspace=ws, prepared=True)
         torch.cuda.synchronize()
 
-    # ---- end to end through the public API: pinned host NCHW features -> device -> aggregate -> host ----
-    e2e = None
-    if not args.no_e2e and args.mode == 'dp' and not args.backward:
-        host_feats = [f.permute(0, 1, 4, 2, 3).contiguous().cpu().pin_memory() for f in feats_cl]   # [B,V,C,fH,fW]
-        # the public streaming entry: H2D, compute and D2H on three streams, two device slots (vfa_b200/streaming.py)
+    # ---- end to end through the public API: pinned host features -> device -> aggregate -> host, every step ----
+    def run_e2e(layout, dtype):
+        """layout 'nchw' (the reference's [B,V,C,fH,fW] feature layout; transposed on the device) or 'nhwc'
+        ([B,V,fH,fW,C], what a channels-last backbone emits); dtype float32 or bfloat16 (feature storage)."""
+        src = [f.float() for f in feats_cl]
+        if layout == 'nchw':
+            host = [f.permute(0, 1, 4, 2, 3).contiguous().cpu().pin_memory() for f in src]
+        else:
+            host = [f.to(dtype).cpu().pin_memory() for f in src]
         table0 = vfa_b200.build_table(cgeom, calibs, grid)
-        agg = vfa_b200.StreamingAggregator(table0, weights, biases, [tuple(h.shape) for h in host_feats], args.flags, depth=2)
+        agg = vfa_b200.StreamingAggregator(table0, weights, biases, [tuple(h.shape) for h in host], args.flags, depth=2,
+                                           dtype=dtype, channels_last=layout == 'nhwc')
         for _ in range(3):
-            agg.submit(host_feats, calibs, grid)
+            agg.submit(host, calibs, grid)
         agg.drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -515,7 +559,7 @@ def main():
         e0.record(agg.s_h2d)
         last = None
         for _ in range(n_e2e):
-            last = agg.submit(host_feats, calibs, grid)
+            last = agg.submit(host, calibs, grid)
         host_out = agg.result(last)
         e1.record(agg.s_d2h)
         agg.drain()
@@ -523,12 +567,127 @@ def main():
         te = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * B * n_e2e / (float(te.item()) * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': sum(h.numel() * 4 for h in host_feats),
-               'd2h_bytes_per_step': host_out.numel() * 4, 'steps': n_e2e,
-               'note': 'vfa_b200.StreamingAggregator: every step copies pinned-host [B,V,C,fH,fW] fp32 features H2D, transposes '
-                       'NCHW->channels-last, rebuilds the table, runs the aggregation kernels (weights re-laid once: inference) and '
-                       'copies the full [B,C,L,W] result D2H; copies and compute overlap on 3 streams / 2 device slots'}
+        return {'value': world * B * n_e2e / (float(te.item()) * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': sum(h.numel() * h.element_size() for h in host),
+                'd2h_bytes_per_step': host_out.numel() * 4, 'steps': n_e2e,
+                'host_layout': '[B,V,C,fH,fW]' if layout == 'nchw' else '[B,V,fH,fW,C]',
+                'feature_storage': 'bf16' if dtype == torch.bfloat16 else 'f32'}
+
+    e2e = None
+    if not args.no_e2e and plain:
+        cpus = pin_to_gpu_numa_node(local_rank)
+        if args.features == 'bf16':
+            e2e = run_e2e('nhwc', torch.bfloat16)
+        else:
+            e2e = run_e2e('nchw', torch.float32)
+            e2e['variants'] = {'channels_last_f32': run_e2e('nhwc', torch.float32),
+                               'channels_last_bf16': run_e2e('nhwc', torch.bfloat16)}
+            for v_ in e2e['variants'].values():
+                v_.pop('unit', None)
+        e2e['cpu_affinity'] = None if cpus is None else f'{len(cpus)} cores next to GPU {local_rank}'
+        e2e['note'] = ('vfa_b200.StreamingAggregator: every step copies the pinned-host features H2D (fp32 [B,V,C,fH,fW] = the '
+                       'reference layout, transposed to channels-last on the device), rebuilds the table, runs the aggregation '
+                       'kernels (weights re-laid once: inference) and copies the full [B,C,L,W] result D2H; copies and compute '
+                       'overlap on 3 streams / 2 device slots.  variants: host buffers already channels-last (no transpose), '
+                       'fp32 and bf16 feature storage (bf16 halves the H2D bytes; tolerance 4e-3 of the output scale, '
+                       'tests/test_gpu_parity.py::test_bf16_feature_storage)')
+
+    # ---- BASELINE configs 2-3: MultiviewX / Wildtrack, one frame, one GPU (same run; N = 1 only) ----
+    configs = None
+    if plain and world == 1 and args.workload == 'MultiviewC' and not args.no_configs:
+        configs = []
+        for wl in ('MultiviewX', 'Wildtrack'):
+            Q = setup(wl, 1, seed=4321)
+            q_shape = vfa_b200.make_shape(Q['feats'], Q['cgeom'].n_layers)
+            q_ws = vfa_b200.workspace_for(Q['cgeom'], q_shape, args.flags, dev)
+            q_out = torch.empty(1, C, Q['grid'].shape[0], Q['grid'].shape[1], device=dev)
+
+            def q_step():
+                tb = vfa_b200.build_table(Q['cgeom'], Q['calibs'], Q['grid'])
+                vfa_b200.prepare_weights(Q['cgeom'], q_shape, Q['ws'], args.flags, workspace=q_ws)
+                vfa_b200.aggregate_forward_raw(Q['feats'], tb, Q['ws'], Q['bs'], args.flags, out=q_out, workspace=q_ws,
+                                               prepared=True)
+            for _ in range(3):
+                q_step()
+            ms = time_steps(q_step, args.steps, barrier, dev, world) / args.steps
+            qn = workload_numbers(Q['g'], 1)
+            configs.append({'workload': f'{wl}-shaped aggregation forward (BASELINE config {2 if wl == "MultiviewX" else 3})',
+                            'batch': 1, 'n_gpus': 1, 'views': Q['g'].n_views, 'grid': list(Q['grid'].shape[:2]) + [len(Q['zs'])],
+                            'value': 1e3 / ms, 'unit': UNIT, 'ms_per_step': ms, 'kernel_path': vfa_b200.last_kernel_path(),
+                            'table': 'rebuilt every step',
+                            'algorithmic_bytes_per_frame': qn['bytes'],
+                            'hbm_frac_of_step': qn['bytes'] / (ms * 1e-3) / 1e9 / load_peaks()['hbm_gbs']})
+            del Q, q_ws, q_out
+        torch.cuda.empty_cache()
+
+    # ---- strong scaling of ONE frame batch over the GPUs: camera sharding, the cross-GPU sum fused into the pooling
+    #      kernel (multimem.red over the NVLink multicast address); B frames total, every rank owns V/N cameras ----
+    strong = None
+    if plain and world > 1 and not args.no_strong:
+        sv0, sv1 = vd.view_bounds(V, world, rank)
+        S_ = setup(args.workload, B, (sv0, sv1), seed=777)        # this rank's cameras of the same B frames
+        try:
+            fused = vd.FusedViewAggregator(cgeom, B, C)
+            kind = 'fused multimem.red in pool_tile_kernel (NVSwitch multicast), 1 barrier per step, no NCCL call'
+        except Exception as exc:                                  # no multicast support: NCCL all-reduce of the partial maps
+            fused, kind = None, f'NCCL all-reduce of partial maps (fused path unavailable: {exc})'
+
+        def strong_step():
+            if sv1 > sv0:
+                tb = vfa_b200.build_table(cgeom, S_['calibs'], grid)
+            if fused is not None:
+                return fused(S_['feats'], tb if sv1 > sv0 else None, weights, biases)
+            part = (vfa_b200.aggregate_forward_raw(S_['feats'], tb, weights, biases, args.flags) if sv1 > sv0
+                    else torch.zeros(B, C, grid.shape[0], grid.shape[1], device=dev))
+            dist.all_reduce(part)
+            return part
+        for _ in range(3):
+            strong_step()
+        ms = time_steps(strong_step, args.steps, barrier, dev, world) / args.steps
+        one_gpu_ms = total_ms / args.steps                        # the dp step above: B frames, all V cameras, one GPU
+        map_bytes = B * C * grid.shape[0] * grid.shape[1] * 4
+        strong = {'mode': 'views (camera sharding)', 'collective': kind, 'frames_per_step': B, 'n_gpus': world,
+                  'cameras_per_rank': [vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0] for r in range(world)],
+                  'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'one_gpu_ms_per_step': one_gpu_ms,
+                  'speedup': one_gpu_ms / ms, 'efficiency': one_gpu_ms / ms / world,
+                  'max_speedup_from_camera_split': V / max(vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0]
+                                                           for r in range(world)),
+                  'reduced_bytes_per_rank_per_step': map_bytes,
+                  'note': 'each rank pushes its partial [B,L,W,C] map once through its NVLink egress; the switch adds it into '
+                          'every replica while the kernel still pools the next tiles (not separately timeable); step time '
+                          'includes the table + weight prep of the rank\'s cameras and the barrier'}
+        del S_, fused
+
+    # ---- BASELINE config 4: batch 64 forward + backward, sharded over the GPUs (64 / N frames per rank; dWeight / dBias
+    #      all-reduced over NCCL -- the only exchange; camera / slab sharding replicate or serialise work at this size) ----
+    config4 = None
+    if plain and not args.no_config4 and args.workload == 'MultiviewC':
+        B4 = 64
+        per = B4 // world
+        Q = setup(args.workload, per, seed=999)
+        for t_ in Q['feats'] + Q['ws'] + Q['bs']:
+            t_.requires_grad_(True)
+        g4 = torch.randn(per, C, grid.shape[0], grid.shape[1], device=dev)
+
+        def c4_step():
+            tb = vfa_b200.build_table(cgeom, Q['calibs'], grid)
+            res = vfa_b200.aggregate(Q['feats'], tb, Q['ws'], Q['bs'], flags=args.flags, channels_last=True)
+            for t_ in Q['feats'] + Q['ws'] + Q['bs']:
+                t_.grad = None
+            res.backward(g4)
+            if world > 1:
+                vd.allreduce_collapse_grads(Q['ws'] + Q['bs'])
+        for _ in range(2):
+            c4_step()
+        n4 = max(2, min(args.steps, 4))
+        ms = time_steps(c4_step, n4, barrier, dev, world) / n4
+        config4 = {'workload': 'MultiviewC batch-64 aggregation forward+backward (BASELINE config 4)', 'n_gpus': world,
+                   'frames_per_rank': per, 'value': per * world / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': n4,
+                   'sharding': 'frames (batch) over GPUs', 'collective': 'NCCL all-reduce of dWeight / dBias '
+                   f'({sum(w.numel() + b.numel() for w, b in zip(Q["ws"], Q["bs"])) * 4} bytes per step)',
+                   'scaling': 'strong (64 frames in total)'}
+        del Q, g4
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -546,77 +705,89 @@ def main():
         work_scale = (3.0 if args.backward else 1.0) / (world if args.mode in ('slab', 'views') else 1)
         tflops = nums['flops'] * work_scale / (kern * 1e-3) / 1e12
         gbs = nums['bytes'] / (kern * 1e-3) / 1e9
-        traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        tj = {}
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            per_frame = tj.get(args.workload, {}).get(path)
-            if per_frame is not None:
-                traffic = per_frame * B
+
         def traffic_of(kernel):
-            per_frame = None
-            if os.path.exists(tpath):
-                with open(tpath) as f:
-                    per_frame = json.load(f).get(args.workload, {}).get(kernel)
+            per_frame = tj.get(args.workload, {}).get(kernel)
             return None if per_frame is None else per_frame * B / nums['fside_chunks']
 
+        step_ms = total_ms / args.steps
+        # roofline fraction of the step = max(T_bytes, T_flops) / T_measured, both terms printed.
+        #   T_bytes: compulsory HBM traffic (features once + BEV map once + weights / boxes / grid once) / measured copy bandwidth
+        #   T_flops: the SHIPPED formulation's contraction (feature side: 2 * B*V*sum(fH*fW) * C * C*nl) / measured bf16 tensor
+        #            peak (sustained: the step runs inside a long loop); the same / (peak / 6) for what fp32 parity costs on the
+        #            tensor cores (3 TF32 passes at half the bf16 rate)
+        flops_step = nums['fside_flops'] if path.startswith('fside') else nums['flops']
+        t_bytes = nums['bytes'] / (peaks['hbm_gbs'] * 1e9) * 1e3
+        t_flops = flops_step / (peaks['tflops'] * 1e12) * 1e3
+        t_flops_x3 = flops_step / (peaks['tflops'] / 6.0 * 1e12) * 1e3
+        step_block = {
+            't_bytes_ms': t_bytes, 't_flops_ms': t_flops, 't_flops_tf32x3_ms': t_flops_x3, 't_measured_ms': step_ms,
+            'frac': max(t_bytes, t_flops) / step_ms, 'frac_tf32x3': max(t_bytes, t_flops_x3) / step_ms,
+            'algorithmic_bytes': nums['bytes'], 'algorithmic_flops': flops_step,
+            'flops_formulation': 'feature-side (image-plane) contraction' if path.startswith('fside') else
+                                 'grid-side contraction (as the reference)',
+            'hbm_achieved_gbs': nums['bytes'] / (step_ms * 1e-3) / 1e9,
+            'hbm_frac': nums['bytes'] / (step_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+            'hbm_peak_gbs': peaks['hbm_gbs'], 'tensor_peak_tflops': peaks['tflops'],
+            'peak_source': peaks['source'],
+            'note': 'step = table + weight re-layout + tap records + coverage + pooling lists + GEMM + pooling, B frames; '
+                    'algorithmic bytes / flops per SURVEY.md section 8(d); frac = max(t_bytes_ms, t_flops_ms) / t_measured_ms'}
         if per_kernel is not None:
-            # dominant kernel: the pooling of Y from the quads' texel lists.  Its compulsory HBM traffic per launch: Y once,
-            # the list entries once (taken as the tap records' bytes: 20 B per listed texel is 74 MB on this rig, the records
-            # 82 MB), the output once.  (What actually binds it is the L1 data pipe: two 4-line loads per texel row.)
             frames = B / nums['fside_chunks']
-            pool_bytes = (nums['y_bytes'] + nums['out_bytes']) / nums['fside_chunks'] + nums['rec_bytes']
-            t_pool, t_gemm = per_kernel['pool_list_kernel'], per_kernel['ygemm_kernel']
-            pool_gbs = pool_bytes / (t_pool * 1e-3) / 1e9
-            # the GEMM multiplies only the texel rows some box pools (compacted row lists); its tensor-core efficiency is quoted
-            # on the run that multiplies every row (VFA_FSIDE_NO_SKIP=1, ygemm_kernel; that run also carries the tap-record /
-            # coverage launches)
+            alg_bytes_launch = nums['bytes'] / nums['fside_chunks']          # 164.8 MB per MultiviewC frame x frames per launch
+            pool_form_bytes = (nums['y_bytes'] + nums['out_bytes']) / nums['fside_chunks'] + nums['rec_bytes']
+            t_pool, t_gemm = per_kernel[pool_name], per_kernel['ygemm_kernel']
             t_gemm_all = per_kernel['ygemm_kernel_all_tiles']
+            # kernels timed in isolation (one launch between two events, nothing else running): burst bf16 figure
+            burst = peaks['tflops_burst']
             gemm_tflops = nums['fside_flops'] / nums['fside_chunks'] / (t_gemm_all * 1e-3) / 1e12
-            step_bytes = nums['bytes'] + 2 * nums['y_bytes'] + nums['rec_bytes']
-            roofline = {
-                'bound': 'hbm', 'achieved': pool_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': pool_gbs / peaks['hbm_gbs'], 'traffic': traffic_of('pool_list_kernel'),
-                'kernel': 'pool_list_kernel', 'kernel_ms': t_pool, 'frames_per_launch': frames,
-                'kernel_share_of_step': t_pool * nums['fside_chunks'] * args.steps / total_ms,
-                'algorithmic_bytes_per_launch': pool_bytes,
-                'peak_source': peaks['source'],
-                'note': 'pooling of the per-layer products Y (fp32 [plane, layer, texel, C]) from precomputed texel lists: '
-                        'algorithmic bytes = Y once + list entries once + output once; the kernel is bound by the L1 data pipe '
-                        '(70 % busy: every texel row is two 4-line loads, L1 hit rate 34 %, 11 GB per launch from L2; '
-                        'profiles/r1_pool_list_ncu_full.json), not by HBM',
-                'second_kernel': {
-                    'kernel': 'ygemm_compact_kernel', 'bound': 'tensor', 'achieved': gemm_tflops, 'peak': peaks['tflops'],
-                    'unit': 'TFLOP/s', 'frac': gemm_tflops / peaks['tflops'], 'kernel_ms': t_gemm,
-                    'kernel_ms_all_rows': t_gemm_all, 'rows_skipped_frac_est': max(0.0, 1.0 - t_gemm / t_gemm_all),
-                    'kernel_share_of_step': t_gemm * nums['fside_chunks'] * args.steps / total_ms,
-                    'traffic': traffic_of('ygemm_compact_kernel'),
-                    'algorithmic_flops_per_launch': nums['fside_flops'] / nums['fside_chunks'],
-                    'tf32x3_ceiling_tflops': peaks['tflops'] / 6.0,
-                    'frac_of_tf32x3_ceiling': gemm_tflops / (peaks['tflops'] / 6.0),
-                    'note': 'image-plane contraction 2*B*V*fH*fW*C*(C*nl), quoted on the all-rows run; fp32 parity needs 3 TF32 '
-                            'passes at half the bf16 rate: the ceiling of a 3xTF32 GEMM is peak/6. The shipped kernel '
-                            '(kernel_ms) multiplies only the covered texel rows of every layer'},
-                'step': {
-                    'fused_ms': kern, 'algorithmic_bytes': step_bytes,
-                    'hbm_frac': step_bytes / (kern * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                    'reference_formulation_tflops': tflops,
-                    'note': 'bytes = features + output + constants (SURVEY 8(d)) + Y written and read once + tap records; '
-                            'reference_formulation_tflops = grid-side flop count of the reference (2*L*W*K*C per view and '
-                            'scale) / time, for comparison with the fused grid-side kernel (--flags 32)'},
-            }
+            pool_tr, gemm_tr = traffic_of(pool_name), traffic_of('ygemm_compact_kernel')
+            pool_block = {
+                'kernel': pool_name, 'bound': 'hbm', 'kernel_ms': t_pool,
+                'achieved': alg_bytes_launch / (t_pool * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': alg_bytes_launch / (t_pool * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                'algorithmic_bytes_per_launch': alg_bytes_launch, 'formulation_bytes': pool_form_bytes,
+                'formulation_gbs': pool_form_bytes / (t_pool * 1e-3) / 1e9,
+                'traffic': pool_tr, 'traffic_over_algorithmic': None if pool_tr is None else pool_tr / alg_bytes_launch,
+                'kernel_share_of_step': t_pool * nums['fside_chunks'] / step_ms, 'frames_per_launch': frames,
+                'note': 'pooling of the per-layer products Y; algorithmic bytes = SURVEY 8(d) per-frame figure x frames per '
+                        'launch (what the whole path must move); formulation_bytes = what THIS kernel must move (Y once + '
+                        'pooling lists once + output once).  Bound by the shared-memory / LSU data pipe and packed-FMA issue, '
+                        'not by HBM (profiles/README.md)'}
+            gemm_block = {
+                'kernel': 'ygemm_compact_kernel', 'bound': 'tensor', 'kernel_ms': t_gemm, 'kernel_ms_all_rows': t_gemm_all,
+                'achieved': gemm_tflops, 'peak': burst, 'unit': 'TFLOP/s', 'frac': gemm_tflops / burst,
+                'tf32x3_ceiling_tflops': burst / 6.0, 'frac_of_tf32x3_ceiling': gemm_tflops / (burst / 6.0),
+                'rows_skipped_frac_est': max(0.0, 1.0 - t_gemm / t_gemm_all),
+                'algorithmic_flops_per_launch': nums['fside_flops'] / nums['fside_chunks'],
+                'traffic': gemm_tr, 'kernel_share_of_step': t_gemm * nums['fside_chunks'] / step_ms,
+                'peak_source': 'measured bf16 burst (MEASURED_PEAKS.json): kernel timed in isolation',
+                'note': 'image-plane contraction 2*B*V*fH*fW*C*(C*nl), quoted on the all-rows run (kernel_ms_all_rows); fp32 '
+                        'parity needs 3 TF32 passes at half the bf16 rate: ceiling = peak/6.  The shipped kernel (kernel_ms) '
+                        'multiplies only the covered texel rows'}
+            dom = pool_block if t_pool >= t_gemm else gemm_block
+            roofline = dict(dom)
+            roofline['peak_source'] = dom.get('peak_source', peaks['source'])
+            roofline['step'] = step_block
+            roofline['kernels'] = [pool_block, gemm_block]
         else:
             roofline = {
                 'bound': 'tensor', 'achieved': tflops, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                'frac': tflops / peaks['tflops'], 'traffic': traffic,
-                'kernel': 'aggregate_fwd_umma_kernel' if path.startswith('umma') else 'aggregate_fwd_simt_kernel',
+                'frac': tflops / peaks['tflops'], 'traffic': traffic_of(path),
+                'kernel': 'aggregate_fwd_umma_kernel' if path.startswith('umma') else
+                          ('aggregate_fwd_simt_kernel' if path.startswith('simt') else 'whole step (several kernels)'),
                 'kernel_ms': kern, 'kernel_share_of_step': kern * args.steps / total_ms,
                 'algorithmic_flops_per_launch': nums['flops'], 'algorithmic_bytes_per_launch': nums['bytes'],
                 'hbm_achieved_gbs': gbs, 'hbm_peak_gbs': peaks['hbm_gbs'], 'hbm_frac': gbs / peaks['hbm_gbs'],
                 'peak_source': peaks['source'],
                 'tf32x3_ceiling_tflops': peaks['tflops'] / 6.0,
                 'frac_of_tf32x3_ceiling': tflops / (peaks['tflops'] / 6.0),
+                'step': step_block,
                 'note': 'collapse contraction counted grid-side (2*L*W*K*C per view and scale, as the reference computes '
                         'it); fp32 parity needs 3 TF32 tensor-core passes, so executed tensor flops are 3x the algorithmic '
                         'count and the TF32 rate is half the bf16 figure used as `peak`: the ceiling of this formulation '
@@ -632,13 +803,17 @@ def main():
                        'batch_per_gpu': B, 'views': V, 'channels': C, 'grid': list(grid.shape[:2]) + [len(zs)],
                        'feature_maps': [list(s) for s in geom.feature_sizes()], 'layout': 'channels_last',
                        'feature_storage': args.features,
-                       'parallelism': f'{args.mode}{world}', 'kernel_path': path, 'table': 'rebuilt every step',
+                       'parallelism': f'{args.mode}{world}', 'kernel_path': path, 'pooling': pool_name if path.startswith('fside') else None,
+                       'table': 'rebuilt every step',
                        'l2': f'inputs {nums["feat_bytes"] / 1e6:.0f} MB/step/GPU exceed the 126 MB L2'},
             'clocks': clocks,
             'e2e': e2e,
             'gpu_launches': launches_per_step * args.steps,
             'roofline': roofline,
             'cpu_baseline': cpu_baseline,
+            'configs': configs,
+            'strong': strong,
+            'config4': config4,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -42,10 +42,24 @@ def test_our_arm_line():
     e = d['e2e']
     assert e['value'] > 0 and e['h2d_bytes_per_step'] == 4 * 7 * 256 * (90 * 160 + 45 * 80 + 23 * 40) * 4
     assert e['d2h_bytes_per_step'] == 4 * 256 * 156 * 156 * 4 and e['value'] < d['value']
+    assert set(e['variants']) == {'channels_last_f32', 'channels_last_bf16'}
+    assert e['variants']['channels_last_bf16']['h2d_bytes_per_step'] * 2 == e['h2d_bytes_per_step']
     r = d['roofline']
     assert r['bound'] in ('hbm', 'tensor') and r['unit'] in ('GB/s', 'TFLOP/s')
     assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9 and 0 < r['frac'] < 1
-    assert r["kernel"] == "pool_list_kernel" and r['second_kernel']['kernel'] == 'ygemm_compact_kernel'
+    assert [k['kernel'] for k in r['kernels']] == ['pool_tile_kernel', 'ygemm_compact_kernel']
+    assert r['kernel'] in ('pool_tile_kernel', 'ygemm_compact_kernel')
+    # both terms printed, frac reproducible from the line
+    st = r['step']
+    assert abs(st['frac'] - max(st['t_bytes_ms'], st['t_flops_ms']) / st['t_measured_ms']) < 1e-9
+    assert abs(st['t_bytes_ms'] - st['algorithmic_bytes'] / (st['hbm_peak_gbs'] * 1e9) * 1e3) < 1e-9
+    assert abs(st['t_measured_ms'] - d['ms_per_step']) < 1e-9
+    pk = r['kernels'][0]
+    assert pk['algorithmic_bytes_per_launch'] == st['algorithmic_bytes'] and pk['formulation_bytes'] > pk['algorithmic_bytes_per_launch']
+    # BASELINE configs 2-4 ride on the same line
+    assert [c['workload'].split('-')[0] for c in d['configs']] == ['MultiviewX', 'Wildtrack']
+    assert all(c['value'] > 0 and c['batch'] == 1 for c in d['configs'])
+    assert d['config4']['frames_per_rank'] == 64 and d['config4']['value'] > 0 and d['strong'] is None
     assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['value'] > 0 and cb['cores'] >= 1

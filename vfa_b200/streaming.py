@@ -13,16 +13,23 @@ from . import vfa_op
 
 
 class StreamingAggregator:
-    def __init__(self, table: vfa_op.ProjectionTable, weights, biases, feature_shapes, flags: int = 0, depth: int = 2):
-        """feature_shapes: list of S shapes (B, V, C, fH, fW); weights/biases: the three collapse layers (CUDA)."""
+    def __init__(self, table: vfa_op.ProjectionTable, weights, biases, feature_shapes, flags: int = 0, depth: int = 2,
+                 dtype=torch.float32, channels_last: bool = False):
+        """feature_shapes: list of S shapes (B, V, C, fH, fW) -- or (B, V, fH, fW, C) with channels_last=True, the layout a
+        backbone running in torch.channels_last emits: no transpose kernel on the way in; weights/biases: the three
+        collapse layers (CUDA).  dtype=torch.bfloat16 (channels_last only): bf16 feature storage, half the PCIe bytes
+        (VFA_FLAG_BF16_FEATURES; tolerance: tests/test_gpu_parity.py::test_bf16_feature_storage)."""
+        if dtype == torch.bfloat16 and not channels_last:
+            raise ValueError('bfloat16 features must be channels-last')
         self.table, self.flags, self.depth = table, int(flags), int(depth)
+        self.dtype, self.channels_last = dtype, bool(channels_last)
         self.weights = [w.detach().contiguous() for w in weights]
         self.biases = [b.detach().contiguous() for b in biases]
         dev = self.weights[0].device
         self.device = dev
         geom = table.geom
-        B, _, C = feature_shapes[0][0], feature_shapes[0][1], feature_shapes[0][2]
-        self.in_slots = [[torch.empty(shape, dtype=torch.float32, device=dev) for shape in feature_shapes]
+        B, C = feature_shapes[0][0], feature_shapes[0][4 if channels_last else 2]
+        self.in_slots = [[torch.empty(shape, dtype=dtype, device=dev) for shape in feature_shapes]
                          for _ in range(depth)]
         self.out_slots = [torch.empty(B, C, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
                           for _ in range(depth)]
@@ -35,7 +42,7 @@ class StreamingAggregator:
         self.ev_host = [torch.cuda.Event() for _ in range(depth)]      # slot's result is in pinned host memory
         self._n = 0
         # frozen weights: re-lay them once
-        cl0 = [vfa_op.to_channels_last(t) for t in self.in_slots[0]]
+        cl0 = self.in_slots[0] if channels_last else [vfa_op.to_channels_last(t) for t in self.in_slots[0]]
         self.shape = vfa_op.make_shape(cl0, geom.n_layers)
         self.workspace = vfa_op.workspace_for(geom, self.shape, self.flags, dev)
         vfa_op.prepare_weights(geom, self.shape, self.weights, self.flags, workspace=self.workspace)
@@ -46,6 +53,7 @@ class StreamingAggregator:
         With calibs / grid given the projection table is rebuilt for this batch (moving cameras)."""
         i = self._n
         k = i % self.depth
+        caller = torch.cuda.current_stream(self.device)
         if i >= self.depth:
             self.s_h2d.wait_event(self.ev_free[k])          # the compute that read this slot has finished
             self.s_compute.wait_event(self.ev_host[k])      # and its previous result has left the device
@@ -55,8 +63,15 @@ class StreamingAggregator:
             self.ev_in[k].record(self.s_h2d)
         with torch.cuda.stream(self.s_compute):
             self.s_compute.wait_event(self.ev_in[k])
-            cl = [vfa_op.to_channels_last(t) for t in self.in_slots[k]]       # NCHW -> channels-last (own kernel)
+            # NCHW -> channels-last (own kernel) unless the host buffers already are
+            cl = self.in_slots[k] if self.channels_last else [vfa_op.to_channels_last(t) for t in self.in_slots[k]]
             if calibs is not None:
+                # moving cameras: the old table may still be read by kernels of this stream, and the new inputs were
+                # produced on the caller's stream (cross-stream lifetime / ordering)
+                self.s_compute.wait_stream(caller)
+                self.table.boxes.record_stream(self.s_compute)
+                calibs.record_stream(self.s_compute)
+                grid.record_stream(self.s_compute)
                 self.table = vfa_op.build_table(self.table.geom, calibs, grid)
             vfa_op.aggregate_forward_raw(cl, self.table, self.weights, self.biases, self.flags, out=self.out_slots[k],
                                          workspace=self.workspace, prepared=True)
