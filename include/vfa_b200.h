@@ -6,9 +6,11 @@
  * that path binds (INTEGRATION.md shows the ctypes stub); each one cites the reference lines it replaces.
  *
  * Conventions
- *   - every pointer named d_* is a DEVICE pointer owned by the caller; the library never allocates, frees,
- *     synchronises the device or keeps global state other than the thread-local last-error string (and, for
- *     vfa_aggregate_bwd only, one lazily created cuBLAS handle used for its two plain SGEMMs);
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; the library never allocates, frees or
+ *     synchronises the device.  Process-wide state, all of it: the thread-local last-error / last-path strings; the
+ *     debug switches read once from the environment (vfa_reload_env); per-device caches filled under a mutex (resident
+ *     cluster counts of the persistent kernels, SM count, and -- for the generic C < 256 backward only -- one lazily
+ *     created cuBLAS handle per device).  Any number of devices may be driven from one process;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued on it;
  *   - every function returns VFA_OK (0) or a negative vfa_status_t; vfa_last_error() describes the failure;
  *   - tensors are dense, row-major in the index order written in the comment.
@@ -97,8 +99,16 @@ typedef struct {
                                         (cuMulticast / torch symmetric memory): multimem.red.add -- the NVSwitch adds the
                                         tile into every GPU's replica (in-switch all-reduce fused into the kernel)         */
 
+#define VFA_FLAG_WS_FORWARD 1024u     /* vfa_aggregate_workspace_bytes only: size for vfa_aggregate_fwd alone (the kernel
+                                        family the other flags select: e.g. 90 MB with VFA_FLAG_GRID_SIDE)               */
+#define VFA_FLAG_WS_BACKWARD 2048u    /* vfa_aggregate_workspace_bytes only: size for vfa_aggregate_bwd alone            */
+
 int vfa_version(void);
 const char* vfa_last_error(void);
+
+/* The library reads its debug / A-B switches (VFA_POOL_TILE, VFA_FSIDE_Y_BUDGET_MB, ...: csrc/vfa_common.cuh,
+ * RuntimeConfig) from the environment once, at the first call.  This re-reads them (tests and timing scripts). */
+void vfa_reload_env(void);
 
 /* Human-readable name of the kernel family the last vfa_aggregate_fwd on this thread dispatched to. */
 const char* vfa_last_path(void);
@@ -121,7 +131,9 @@ int vfa_table_scale(const float* d_boxes, int64_t n_boxes, int32_t feat_h, int32
 int vfa_nchw_to_nhwc(const float* d_src, float* d_dst, int64_t n, int32_t channels, int64_t hw, void* stream);
 int vfa_nhwc_to_nchw(const float* d_src, float* d_dst, int64_t n, int32_t channels, int64_t hw, void* stream);
 
-/* Bytes of scratch vfa_aggregate_fwd / _bwd need for this problem: prepared weights, tap records, coverage bitmap and
+/* Bytes of scratch for this problem and these flags.  Without a VFA_FLAG_WS_* flag: enough for vfa_aggregate_fwd with
+ * `flags` AND vfa_aggregate_bwd (one buffer serving both directions); VFA_FLAG_WS_FORWARD / _BACKWARD size one direction.
+ * Contents: prepared weights, tap records, coverage bitmap and
  * row lists, the quads' texel lists, Y of one frame chunk (forward); CSR, masked gradients, Gs (backward).  Pure host
  * arithmetic on (geom, shape, flags). */
 size_t vfa_aggregate_workspace_bytes(const vfa_geometry_t* geom, const vfa_shape_t* shape, uint32_t flags);

@@ -18,6 +18,7 @@ res = {}
 for tag, env in (('tc', None), ('cublas', '1')):
     if env: os.environ['VFA_BWD_CUBLAS_DW'] = env
     else: os.environ.pop('VFA_BWD_CUBLAS_DW', None)
+    vfa_b200.reload_env()
     fc = [t.cuda().requires_grad_(True) for t in feats0]
     ws = [w.cuda().requires_grad_(True) for w, _ in params]
     bs = [b.cuda().requires_grad_(True) for _, b in params]

@@ -21,7 +21,7 @@ def _header():
 
 
 def test_library_exports_every_declared_symbol():
-    declared = set(re.findall(r'^(?:int|size_t|const char\*)\s+(vfa_\w+)\s*\(', _header(), flags=re.M))
+    declared = set(re.findall(r'^(?:int|void|size_t|const char\*)\s+(vfa_\w+)\s*\(', _header(), flags=re.M))
     assert declared, 'no prototypes found in include/vfa_b200.h'
     L = _lib.lib()
     missing = [n for n in sorted(declared) if not hasattr(L, n)]
@@ -39,7 +39,10 @@ def test_struct_layouts_match_header():
     assert int(re.search(r'#define VFA_MAX_SCALES (\d+)', h).group(1)) == _lib.VFA_MAX_SCALES
     for name, val in (('FORCE_SIMT', _lib.FLAG_FORCE_SIMT), ('FORCE_UMMA', _lib.FLAG_FORCE_UMMA),
                       ('BF16_MMA', _lib.FLAG_BF16_MMA), ('WEIGHTS_PREPARED', _lib.FLAG_WEIGHTS_PREPARED),
-                      ('BF16_FEATURES', _lib.FLAG_BF16_FEATURES), ('GRID_SIDE', _lib.FLAG_GRID_SIDE)):
+                      ('BF16_FEATURES', _lib.FLAG_BF16_FEATURES), ('GRID_SIDE', _lib.FLAG_GRID_SIDE),
+                      ('TABLE_PREPARED', _lib.FLAG_TABLE_PREPARED), ('OUT_NHWC', _lib.FLAG_OUT_NHWC),
+                      ('OUT_ACCUMULATE', _lib.FLAG_OUT_ACCUMULATE), ('OUT_MULTICAST', _lib.FLAG_OUT_MULTICAST),
+                      ('WS_FORWARD', _lib.FLAG_WS_FORWARD), ('WS_BACKWARD', _lib.FLAG_WS_BACKWARD)):
         assert int(re.search(rf'#define VFA_FLAG_{name}\s+(\d+)u', h).group(1)) == val
 
 
@@ -104,7 +107,7 @@ def test_synthetic_inputs_are_deterministic():
     assert p[0][0].shape == (4, 20) and p[0][1].shape == (4,)
 
 
-def test_workspace_sizing_is_host_only(monkeypatch):
+def test_workspace_sizing_is_host_only(libenv):
     """vfa_aggregate_workspace_bytes is pure host arithmetic: the default C = 256 forward carries the image-plane
     intermediate Y of one frame chunk (bounded by the 6 GiB budget), VFA_FLAG_GRID_SIDE does not; the backward adds its
     CSR / gm / Gs buffers; other channel counts use the generic kernels' small workspace."""
@@ -124,7 +127,7 @@ def test_workspace_sizing_is_host_only(monkeypatch):
         sh = shape(batch, channels)
         return L.vfa_aggregate_workspace_bytes(ctypes.byref(geom), ctypes.byref(sh), flags)
 
-    monkeypatch.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
+    libenv.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
     y_frame = g.n_views * len(zs) * sum(h * w for h, w in g.feature_sizes()) * 256 * 4          # 678 MB
     one = ws(1)
     assert one > y_frame                                       # Y of one frame + CSR / gm / Gs of the backward
@@ -132,7 +135,13 @@ def test_workspace_sizing_is_host_only(monkeypatch):
     assert 0 <= ws(64) - ws(32) < 1 << 20                      # ... up to the 6 GiB budget (chunks are looped; only the
                                                                # per-tile need bytes of the backward still grow with B)
     assert ws(4, channels=16) < 200 << 20                      # generic kernels: weights + small scratch
-    monkeypatch.setenv('VFA_FSIDE_Y_BUDGET_MB', '700')         # one frame per chunk
+    # sizing honours flags and direction: the grid-side forward needs no intermediate, a forward-only caller is not
+    # told to allocate the backward's CSR / Gs, and vice versa
+    fwd, bwd = ws(1, _lib.FLAG_WS_FORWARD), ws(1, _lib.FLAG_WS_BACKWARD)
+    assert max(fwd, bwd) == one and y_frame < fwd < one
+    assert ws(1, _lib.FLAG_WS_FORWARD | _lib.FLAG_GRID_SIDE) < 128 << 20 < ws(4, _lib.FLAG_WS_FORWARD)
+    assert ws(4, _lib.FLAG_WS_FORWARD | _lib.FLAG_FORCE_SIMT) < 200 << 20
+    libenv.setenv('VFA_FSIDE_Y_BUDGET_MB', '700')         # one frame per chunk
     assert 0 <= ws(4) - ws(1) < 1 << 20
 
 

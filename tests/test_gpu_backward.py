@@ -88,7 +88,7 @@ def test_fused_backward_matches_port(name, channels):
 
 @pytest.mark.parametrize('path,bwd', [('fside_tf32x3', 'gather'), ('umma_tf32x3', 'gather'), ('fside_tf32x3', 'overflow'),
                                       ('fside_tf32x3', 'scatter')])
-def test_full_width_backward_matches_port(path, bwd, monkeypatch):
+def test_full_width_backward_matches_port(path, bwd, libenv):
     """C = 256: tcgen05 forward (either formulation; writes the ReLU mask) + CUDA backward on a strided sub-grid vs
     the float64 port.
 
@@ -114,9 +114,9 @@ def test_full_width_backward_matches_port(path, bwd, monkeypatch):
     # backward variants: CSR gather + tcgen05 dFeature product (default); the same with a CSR too small for most rows
     # (they are completed by the atomic overflow kernel); the older scatter + cuBLAS path
     if bwd == 'overflow':
-        monkeypatch.setenv('VFA_BWD_CSR_PER_BOX', '1')
+        libenv.setenv('VFA_BWD_CSR_PER_BOX', '1')
     if bwd == 'scatter':
-        monkeypatch.setenv('VFA_BWD_SCATTER', '1')
+        libenv.setenv('VFA_BWD_SCATTER', '1')
     flags = vfa_b200.FLAG_GRID_SIDE if path == 'umma_tf32x3' else 0
     out = vfa_b200.aggregate(fc, table, ws, bs, flags=flags)
     assert vfa_b200.last_kernel_path() == path
@@ -165,7 +165,7 @@ def test_grad_flags_are_respected():
     assert ws[1].grad is not None and ws[0].grad is None and ws[2].grad is None
 
 
-def test_full_size_backward_variants_agree(monkeypatch):
+def test_full_size_backward_variants_agree(libenv):
     """BASELINE-size problem (MultiviewC, 7 views, 3 scales, C = 256, 2 frames): the gather-form backward (CSR + tcgen05
     dFeature / dWeight) against the scatter + SGEMM backward, gradients of a random cotangent."""
     g = geometry.MULTIVIEWC
@@ -180,13 +180,13 @@ def test_full_size_backward_variants_agree(monkeypatch):
     grads = {}
     for tag in ('gather', 'scatter'):
         if tag == 'scatter':
-            monkeypatch.setenv('VFA_BWD_SCATTER', '1')
+            libenv.setenv('VFA_BWD_SCATTER', '1')
         fc = [t.cuda().requires_grad_(True) for t in feats]
         ws = [w.cuda().requires_grad_(True) for w, _ in params]
         bs = [b.cuda().requires_grad_(True) for _, b in params]
         vfa_b200.aggregate(fc, table, ws, bs).backward(gout)
         grads[tag] = [t.grad for t in fc + ws + bs]
-    monkeypatch.delenv('VFA_BWD_SCATTER', raising=False)
+    libenv.delenv('VFA_BWD_SCATTER', raising=False)
     names = [f'dFeature{s}' for s in range(3)] + [f'dWeight{s}' for s in range(3)] + [f'dBias{s}' for s in range(3)]
     for name, a, b in zip(names, grads['gather'], grads['scatter']):
         _close(a.cpu().numpy(), b.cpu().numpy().astype(np.float64), f'full size {name}')

@@ -130,7 +130,7 @@ def test_whole_frame_backward_vs_float64_port(name):
             assert err < 2e-5, f'{name} scale {s} {what}: {err:.3e}'
 
 
-def test_tile_pooling_overflow_nhwc_and_determinism(monkeypatch):
+def test_tile_pooling_overflow_nhwc_and_determinism(libenv):
     """Staged-tile pooling (pool_tile_kernel, the default): bit-reproducible run to run; with its pools forced to overflow
     (VFA_POOL_TILE_CAP = 1 %: nearly every tile is left to the walking kernel) and with the quads' list kernel
     (VFA_POOL_TILE = 0) the sums only change their order (fp32 rounding); the [B, L, W, C] output (VFA_FLAG_OUT_NHWC) holds
@@ -144,7 +144,7 @@ def test_tile_pooling_overflow_nhwc_and_determinism(monkeypatch):
     feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=V, seed=8)]
     table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
     for k in ('VFA_POOL_TILE_CAP', 'VFA_POOL_TILE'):
-        monkeypatch.delenv(k, raising=False)
+        libenv.delenv(k, raising=False)
     ref = vfa_b200.aggregate(feats, table, ws, bs)
     assert torch.equal(vfa_b200.aggregate(feats, table, ws, bs), ref)
     simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
@@ -164,7 +164,7 @@ def test_tile_pooling_overflow_nhwc_and_determinism(monkeypatch):
     out_t, grad_t = train_run()
     assert torch.equal(out_t, ref)
     for key, val in (('VFA_POOL_TILE_CAP', '1'), ('VFA_POOL_TILE', '0')):
-        monkeypatch.setenv(key, val)
+        libenv.setenv(key, val)
         other = vfa_b200.aggregate(feats, table, ws, bs)
         err = (other - ref).abs()
         assert bool((err <= 1e-6 + 2e-6 * ref.abs()).all()), f'{key}={val}: worst {float(err.max()):.2e}'
@@ -176,4 +176,4 @@ def test_tile_pooling_overflow_nhwc_and_determinism(monkeypatch):
         # gradient elements move, everything else agrees to rounding
         moved = ((grad_c - grad_t).abs() > 2e-5 * float(grad_t.abs().max())).float().mean()
         assert float(moved) < 1e-4, f'{key}={val}: {float(moved):.2e} of dFeature elements differ'
-        monkeypatch.delenv(key, raising=False)
+        libenv.delenv(key, raising=False)

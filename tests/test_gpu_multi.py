@@ -161,3 +161,35 @@ def test_fused_multicast_camera_sharding_two_gpus_matches_single_gpu():
     results = mgr.dict()
     mp.spawn(_fused_views_worker, args=(2, _free_port(), results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_one_process_drives_two_devices():
+    """Kernel attributes, resident-cluster counts and the cuBLAS handle are cached per device: forward + backward on
+    cuda:1 after cuda:0 in ONE process (nn.DataParallel-style use) give the same results (C = 256 tcgen05 path with its >
+    48 KB dynamic shared memory, and the generic C = 16 path whose backward calls cuBLAS)."""
+    import vfa_b200
+    from vfa_b200 import geometry, synthetic
+    g = geometry.MULTIVIEWC
+    zs = list(range(0, g.grid_height, g.cube_size[2]))
+    grid = geometry.grid_for(g)[::2, ::2].contiguous()
+    cgeom = vfa_b200.make_geometry(len(zs), g.cube_size, zs, grid.shape[:2], g.name, g.image_size)
+    calibs = synthetic.ring_calibs(g, n_views=2)
+    for channels in (256, 16):
+        feats = synthetic.features(g, batch=2, n_views=2, channels=channels, seed=3)
+        params = synthetic.collapse_params(g, channels=channels, seed=3)
+        gout = torch.randn(2, channels, *grid.shape[:2], generator=torch.Generator().manual_seed(4))
+        res = []
+        for d in (0, 1):
+            dev = torch.device('cuda', d)
+            table = vfa_b200.build_table(cgeom, calibs.to(dev), grid.to(dev))
+            f = [t.to(dev).requires_grad_(True) for t in feats]
+            w = [x.to(dev).requires_grad_(True) for x, _ in params]
+            b = [x.to(dev).requires_grad_(True) for _, x in params]
+            out = vfa_b200.aggregate(f, table, w, b)
+            out.backward(gout.to(dev))
+            torch.cuda.synchronize(dev)
+            res.append([out.detach().cpu()] + [t.grad.cpu() for t in f + w + b])
+        assert torch.equal(res[0][0], res[1][0])                                  # the forward is deterministic
+        for a, b_ in zip(res[0][1:], res[1][1:]):                                 # the backward sums with atomics
+            assert float((a - b_).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12

@@ -308,7 +308,7 @@ def test_bf16_feature_storage():
         vfa_b200.aggregate(f16, table, [w.requires_grad_(True) for w in ws], bs, channels_last=True)
 
 
-def test_feature_side_chunking_and_ragged_grids(monkeypatch):
+def test_feature_side_chunking_and_ragged_grids(libenv):
     """Feature-side forward (default, C = 256): frame chunks (Y budget forced down to one frame per chunk), grids whose
     sides are not multiples of the 2 x 2 quads / 4 x 8 CTA tiles, a texel-row count that is not a multiple of the
     256-row GEMM tile -- all bit-identical to the unchunked run and inside the tolerance of the fp32 FFMA kernel."""
@@ -323,20 +323,20 @@ def test_feature_side_chunking_and_ragged_grids(monkeypatch):
                (slice(100, 101), slice(0, 156))):             # a single row
         grid = full[sl].contiguous()
         table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
-        monkeypatch.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
+        libenv.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
         ref = vfa_b200.aggregate(feats, table, ws, bs)
         assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
         simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
         ok, err = _within(ref.cpu().numpy().astype(np.float64), simt.cpu().numpy().astype(np.float64))
         assert ok.all(), f'grid {tuple(grid.shape[:2])}: worst {err.max():.2e}'
         # Y of one MultiviewC frame with 3 views is 291 MB: 300 MB -> one frame per chunk, 3 chunks
-        monkeypatch.setenv('VFA_FSIDE_Y_BUDGET_MB', '300')
+        libenv.setenv('VFA_FSIDE_Y_BUDGET_MB', '300')
         chunked = vfa_b200.aggregate(feats, table, ws, bs)
         assert torch.equal(chunked, ref)
-    monkeypatch.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
+    libenv.delenv('VFA_FSIDE_Y_BUDGET_MB', raising=False)
 
 
-def test_list_pooling_equals_walking_pooling_bit_for_bit(monkeypatch):
+def test_list_pooling_equals_walking_pooling_bit_for_bit(libenv):
     """The default pooling reads precomputed texel lists (pool_list_kernel); quads whose list does not fit its slot are
     pooled by the walking kernel (pool_quad_kernel, completion pass).  Both apply the same weights in the same order, so
     any split of the quads between them gives the same bits: default slots (every quad listed), slots of 1 and 3 entries
@@ -350,7 +350,7 @@ def test_list_pooling_equals_walking_pooling_bit_for_bit(monkeypatch):
     ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
     feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=V, seed=8)]
     table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
-    monkeypatch.delenv('VFA_POOL_LIST_CAP', raising=False)
+    libenv.delenv('VFA_POOL_LIST_CAP', raising=False)
     ref = vfa_b200.aggregate(feats, table, ws, bs)
     assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
     simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
@@ -367,13 +367,13 @@ def test_list_pooling_equals_walking_pooling_bit_for_bit(monkeypatch):
     out_t, grad_t = train_run()
     assert torch.equal(out_t, ref)
     for cap in ('1', '3'):
-        monkeypatch.setenv('VFA_POOL_LIST_CAP', cap)
+        libenv.setenv('VFA_POOL_LIST_CAP', cap)
         assert torch.equal(vfa_b200.aggregate(feats, table, ws, bs), ref), f'slot of {cap} entries per iteration'
         out_c, grad_c = train_run()
         assert torch.equal(out_c, ref)
         # same ReLU mask -> same masked gradient (the backward's atomics reorder sums: compare to rounding)
         assert float((grad_c - grad_t).abs().max()) <= 1e-5 * float(grad_t.abs().max())
-    monkeypatch.delenv('VFA_POOL_LIST_CAP', raising=False)
+    libenv.delenv('VFA_POOL_LIST_CAP', raising=False)
 
 
 def test_relu_mask_agrees_between_formulations():

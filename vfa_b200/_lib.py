@@ -21,12 +21,14 @@ FLAG_TABLE_PREPARED = 64
 FLAG_OUT_NHWC = 128
 FLAG_OUT_ACCUMULATE = 256
 FLAG_OUT_MULTICAST = 512
+FLAG_WS_FORWARD = 1024
+FLAG_WS_BACKWARD = 2048
 
 # VFA_B200_LIB: another build of the same library (A/B timing of compile-time kernel variants, scripts/build_variant.sh)
 LIB_PATH = os.environ.get('VFA_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                                                            'libvfa_b200.so')
 
-EXPORTS = ['vfa_version', 'vfa_last_error', 'vfa_last_path', 'vfa_table_build', 'vfa_table_scale',
+EXPORTS = ['vfa_version', 'vfa_last_error', 'vfa_last_path', 'vfa_reload_env', 'vfa_table_build', 'vfa_table_scale',
            'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_workspace_bytes', 'vfa_prepare_weights', 'vfa_aggregate_fwd',
            'vfa_aggregate_bwd']
 
@@ -63,6 +65,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, fp, i32, i64, u32, sz = C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_size_t
     L.vfa_version.restype = C.c_int
+    L.vfa_reload_env.restype = None
     L.vfa_last_error.restype = C.c_char_p
     L.vfa_last_path.restype = C.c_char_p
     L.vfa_table_build.argtypes = [C.POINTER(Geometry), i32, fp, fp, fp, vp]
@@ -88,6 +91,11 @@ def lib():
 def check(rc):
     if rc != 0:
         raise VFAError(rc, lib().vfa_last_error().decode())
+
+
+def reload_env():
+    """Make the library re-read its debug / A-B switches (VFA_* environment variables; it reads them once per process)."""
+    lib().vfa_reload_env()
 
 
 def last_path() -> str:

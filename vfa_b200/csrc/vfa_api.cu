@@ -1,7 +1,10 @@
 // extern "C" entry points of libvfa_b200.so (include/vfa_b200.h): argument validation, dispatch, no state.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "vfa_common.cuh"
 
@@ -19,6 +22,55 @@ void set_error(const char* fmt, ...) {
 void set_path(const char* name) {
   strncpy(g_path, name, sizeof(g_path) - 1);
   g_path[sizeof(g_path) - 1] = 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+static RuntimeConfig g_config;
+static std::once_flag g_config_once;
+static std::mutex g_state_mutex;
+static void load_config() {
+  RuntimeConfig c;
+  c.pool_tile = env_int("VFA_POOL_TILE", 1);
+  c.pool_tile_cap = env_int("VFA_POOL_TILE_CAP", 100);
+  c.tile_variant = env_int("VFA_TILE_VARIANT", 0);
+  c.pool_list = env_int("VFA_POOL_LIST", 1);
+  c.pool_quad = env_int("VFA_POOL_QUAD", 1);
+  c.pool_list_cap = env_int("VFA_POOL_LIST_CAP", 0);
+  c.fside_compact = env_int("VFA_FSIDE_COMPACT", 1);
+  c.fside_no_skip = env_int("VFA_FSIDE_NO_SKIP", 0);
+  const char* mb = getenv("VFA_FSIDE_Y_BUDGET_MB");
+  c.y_budget_mb = mb != nullptr ? atoll(mb) : 0;
+  c.umma_variant = env_int("VFA_UMMA_VARIANT", 0);
+  c.fwd_gridside = env_int("VFA_FWD_GRIDSIDE", 0);
+  c.bwd_scatter = getenv("VFA_BWD_SCATTER") != nullptr;
+  c.bwd_untiled = getenv("VFA_BWD_UNTILED") != nullptr;
+  c.bwd_generic = getenv("VFA_BWD_GENERIC") != nullptr;
+  c.bwd_cublas_dw = getenv("VFA_BWD_CUBLAS_DW") != nullptr;
+  c.bwd_csr_per_box = env_int("VFA_BWD_CSR_PER_BOX", 0);
+  std::lock_guard<std::mutex> lock(g_state_mutex);
+  g_config = c;
+}
+const RuntimeConfig& runtime_config() {
+  std::call_once(g_config_once, load_config);
+  return g_config;
+}
+
+constexpr int MAX_DEVICES = 64;
+static int g_device_cache[MAX_DEVICES][DC_SLOTS];
+int device_cache_get(int slot) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 0;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
+  return g_device_cache[dev][slot];
+}
+void device_cache_set(int slot, int value) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return;
+  std::lock_guard<std::mutex> lock(g_state_mutex);
+  g_device_cache[dev][slot] = value;
 }
 
 int check_device() {
@@ -128,6 +180,10 @@ using namespace vfa;
 extern "C" {
 
 int vfa_version(void) { return VFA_ABI_VERSION; }
+void vfa_reload_env(void) {
+  (void)runtime_config();
+  load_config();
+}
 const char* vfa_last_error(void) { return g_error; }
 const char* vfa_last_path(void) { return g_path; }
 
@@ -165,11 +221,14 @@ int vfa_nhwc_to_nchw(const float* d_src, float* d_dst, int64_t n, int32_t channe
 
 size_t vfa_aggregate_workspace_bytes(const vfa_geometry_t* geom, const vfa_shape_t* shape, uint32_t flags) {
   if (!geom || !shape) return 0;
-  size_t a = simt_workspace_bytes(geom, shape);
-  size_t b = umma_workspace_bytes(geom, shape, flags);
-  size_t c = bwd_workspace_bytes(geom, shape);
-  size_t m = a > b ? a : b;
-  m = m > c ? m : c;
+  // forward: the one kernel family `flags` selects (the same dispatch as vfa_aggregate_fwd)
+  const bool use_umma = !(flags & VFA_FLAG_FORCE_SIMT) && umma_supported(geom, shape, flags);
+  const size_t fwd = use_umma ? umma_workspace_bytes(geom, shape, flags) : simt_workspace_bytes(geom, shape);
+  const size_t bwd = bwd_workspace_bytes(geom, shape);
+  size_t m;
+  if (flags & VFA_FLAG_WS_FORWARD) m = fwd;
+  else if (flags & VFA_FLAG_WS_BACKWARD) m = bwd;
+  else m = fwd > bwd ? fwd : bwd;                    // one buffer for both directions
   return (m + 255) & ~(size_t)255;
 }
 

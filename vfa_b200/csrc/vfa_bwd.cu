@@ -17,6 +17,8 @@
 // the cell tiles; it re-pools its 32 channels for every tile and accumulates a rank-64 update in registers.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "vfa_common.cuh"
 
 namespace vfa {
@@ -276,10 +278,15 @@ struct Cublas {
   cublasSgemm_t sgemm = nullptr;
   bool tried = false;
 };
-static Cublas g_cublas;     // one lazily created handle (process-wide; the backward is not re-entrant across threads)
+static Cublas g_cublas[64];     // one lazily created handle per device, created under a mutex
+static std::mutex g_cublas_mutex;
 
 static int get_cublas(Cublas** out) {
-  Cublas& c = g_cublas;
+  int dev = 0;
+  VFA_CUDA(cudaGetDevice(&dev));
+  VFA_REQUIRE(dev >= 0 && dev < 64, VFA_ERR_UNSUPPORTED, "device index %d beyond the 64 this library caches handles for", dev);
+  std::lock_guard<std::mutex> lock(g_cublas_mutex);
+  Cublas& c = g_cublas[dev];
   if (!c.tried) {
     c.tried = true;
     void* lib = dlopen("libcublas.so.12", RTLD_NOW | RTLD_GLOBAL);
@@ -517,7 +524,7 @@ int launch_unprep_dweight(const float* dwr, float* dw, int C, int nl, cudaStream
 size_t bwd_fside_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh);
 int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_grad_out, float* const* d_grad_feats,
                      float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, cudaStream_t st);
-static bool gather_backward(int channels) { return channels == 256 && getenv("VFA_BWD_SCATTER") == nullptr; }
+static bool gather_backward(int channels) { return channels == 256 && !runtime_config().bwd_scatter; }
 
 static size_t fs_gs_elems(const AggParams& p) {
   size_t px = 0;
@@ -573,17 +580,13 @@ static int launch_bwd_feature_side(AggParams p, const float* const* d_weight, co
       VFA_CUDA(cudaMemsetAsync(gs, 0, gs_elems * sizeof(float), st));
       q.b = b;
       q.v = v;
-      if (getenv("VFA_BWD_UNTILED") != nullptr) {
+      if (runtime_config().bwd_untiled) {
         fs::scatter_g_kernel<<<sblocks, 256, 0, st>>>(q);
         VFA_LAUNCH_CHECK("scatter_g_kernel");
       } else {
         const int tiles_x = (p.W + fs::SC_TW - 1) / fs::SC_TW, tiles_y = (p.L + fs::SC_TH - 1) / fs::SC_TH;
         const size_t smem = (size_t)fs::SC_RMAX * fs::SC_CH * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-          VFA_CUDA(cudaFuncSetAttribute(fs::scatter_g_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr_set = true;
-        }
+        VFA_CUDA(cudaFuncSetAttribute(fs::scatter_g_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(tiles_x * tiles_y, p.S * p.nl, (p.C + fs::SC_CH - 1) / fs::SC_CH);
         fs::scatter_g_tiled_kernel<<<grid, 256, smem, st>>>(q, tiles_x);
         VFA_LAUNCH_CHECK("scatter_g_tiled_kernel");
@@ -641,7 +644,7 @@ int launch_bwd(AggParams p, const float* const* d_weight, const float* d_grad_ou
   VFA_REQUIRE(p.C <= MAXC, VFA_ERR_UNSUPPORTED, "backward supports up to %d channels (got %d)", MAXC, p.C);
   if (gather_backward(p.C))
     return launch_bwd_fside(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, ws, ws_bytes, st);
-  if (feature_side_ok(p) && getenv("VFA_BWD_GENERIC") == nullptr)
+  if (feature_side_ok(p) && !runtime_config().bwd_generic)
     return launch_bwd_feature_side(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, ws, st);
   BwdParams q;
   q.p = p;
@@ -688,11 +691,7 @@ int launch_bwd(AggParams p, const float* const* d_weight, const float* d_grad_ou
     if (parts > total) parts = (int)total;
     q.cell_parts = parts;
     const size_t smem = (size_t)(TM * GSTRIDE + TM * KC) * sizeof(float) + TM * sizeof(BoxTaps);
-    static bool attr_set = false;
-    if (!attr_set) {
-      VFA_CUDA(cudaFuncSetAttribute(bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    VFA_CUDA(cudaFuncSetAttribute(bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(blocks_x, parts);
     bwd_weight_kernel<<<grid, THREADS, smem, st>>>(q);
     VFA_LAUNCH_CHECK("bwd_weight_kernel");

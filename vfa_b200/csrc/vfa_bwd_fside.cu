@@ -154,49 +154,53 @@ __global__ void __launch_bounds__(1024) scan_block_kernel(const int* __restrict_
   if (i < n) out[i] = incl - x;
   if (threadIdx.x == 1023) block_sums[blockIdx.x] = incl;
 }
+// Block offsets are summed in 64 bits and SATURATED at INT_MAX: a rig whose boxes hold more than 2^31 taps (close-up
+// cameras, many views) must not wrap the 32-bit offsets negative -- a saturated offset exceeds every capacity, so the rows
+// behind it are completed by the overflow kernel like any other row the list could not hold.
+__device__ __forceinline__ int sat_int(long long x) { return x > 0x7fffffffll ? 0x7fffffff : (int)x; }
 __global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ block_sums, int nblocks) {
-  __shared__ int warp_sums[32];
-  __shared__ int carry_s;
+  __shared__ long long warp_sums[32];
+  __shared__ long long carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b0 = 0; b0 < nblocks; b0 += 1024) {
     const int i = b0 + threadIdx.x;
-    const int x = i < nblocks ? block_sums[i] : 0;
-    int v = x;
+    const long long x = i < nblocks ? block_sums[i] : 0;
+    long long v = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      const long long t = __shfl_up_sync(0xffffffffu, v, d);
       if (lane >= d) v += t;
     }
     if (lane == 31) warp_sums[warp] = v;
     __syncthreads();
     if (warp == 0) {
-      int w = warp_sums[lane];
+      long long w = warp_sums[lane];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, d);
+        const long long t = __shfl_up_sync(0xffffffffu, w, d);
         if (lane >= d) w += t;
       }
       warp_sums[lane] = w;
     }
     __syncthreads();
-    const int carry = carry_s;
-    const int incl = v + (warp > 0 ? warp_sums[warp - 1] : 0);
-    if (i < nblocks) block_sums[i] = carry + incl - x;      // exclusive
+    const long long carry = carry_s;
+    const long long incl = v + (warp > 0 ? warp_sums[warp - 1] : 0);
+    if (i < nblocks) block_sums[i] = sat_int(carry + incl - x);      // exclusive
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = carry + incl;
     __syncthreads();
   }
 }
-// out[i] += block offset; out[n] = grand total
+// out[i] += block offset; out[n] = grand total (both saturating)
 __global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, const int* __restrict__ block_sums,
                                                         const int* __restrict__ in, int n) {
   const int i = blockIdx.x * 1024 + threadIdx.x;
   if (i < n) {
-    const int o = out[i] + block_sums[blockIdx.x];
+    const int o = sat_int((long long)out[i] + block_sums[blockIdx.x]);
     out[i] = o;
-    if (i == n - 1) out[n] = o + in[i];
+    if (i == n - 1) out[n] = sat_int((long long)o + in[i]);
   }
 }
 
@@ -678,11 +682,7 @@ __global__ void __launch_bounds__(THREADS, 1) dweight_kernel(const Args a) {
 static int launch_dweight(const float* const* gs, const float* const* f, float* const* dwr, const int* T, int nl, int S,
                           const uint8_t* need, cudaStream_t st) {
   using namespace dwg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VFA_CUDA(cudaFuncSetAttribute(dweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  VFA_CUDA(cudaFuncSetAttribute(dweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   Args a;
   a.nl = nl;
   a.S = S;
@@ -713,7 +713,7 @@ static int launch_dweight(const float* const* gs, const float* const* f, float* 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int resident_clusters = 0;
+  int resident_clusters = device_cache_get(DC_DWEIGHT_CLUSTERS);
   if (resident_clusters == 0) {
     cfg.gridDim = dim3(2 * 148);
     int n = 0;
@@ -722,6 +722,7 @@ static int launch_dweight(const float* const* gs, const float* const* f, float* 
       n = 64;
     }
     resident_clusters = n;
+    device_cache_set(DC_DWEIGHT_CLUSTERS, n);
   }
   int shares = resident_clusters / nl;
   if (shares < 1) shares = 1;
@@ -750,10 +751,7 @@ static Plan make_plan(int B, int V, int S, int nl, size_t LW, const int* fh, con
   for (int s = 0; s < S; ++s) pl.px += (size_t)fh[s] * fw[s];
   pl.rows = (int)(pl.px * V * nl);
   int per_box = CSR_PER_BOX;
-  if (const char* e = getenv("VFA_BWD_CSR_PER_BOX")) {     // tests: a tiny list forces the overflow path
-    const int v = atoi(e);
-    if (v > 0) per_box = v;
-  }
+  if (runtime_config().bwd_csr_per_box > 0) per_box = runtime_config().bwd_csr_per_box;     // tests: force the overflow path
   size_t cap = (size_t)per_box * V * S * nl * LW;
   if (cap > ((size_t)1 << 30)) cap = (size_t)1 << 30;      // entry offsets are 32-bit; rows beyond go to the overflow kernel
   pl.capacity = (int)cap;
@@ -785,10 +783,7 @@ static Plan make_plan(int B, int V, int S, int nl, size_t LW, const int* fh, con
 
 static int chunk_frames(const Plan& pl, int B) {
   size_t budget = (size_t)6 << 30;
-  if (const char* e = getenv("VFA_FSIDE_Y_BUDGET_MB")) {
-    const long long mb = atoll(e);
-    if (mb > 0) budget = (size_t)mb << 20;
-  }
+  if (runtime_config().y_budget_mb > 0) budget = (size_t)runtime_config().y_budget_mb << 20;
   size_t cb = budget / pl.per_frame;
   if (cb < 1) cb = 1;
   if (cb > (size_t)B) cb = (size_t)B;
@@ -874,12 +869,8 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
   csr_walk_kernel<true><<<148 * 8, 256, 0, st>>>(p, recs, rm, counts, offsets, entries, pl.capacity);
   VFA_LAUNCH_CHECK("csr_walk_kernel<fill>");
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    VFA_CUDA(cudaFuncSetAttribute(dy_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  (int)cudaSharedmemCarveoutMaxL1));
-    attr_set = true;
-  }
+  VFA_CUDA(cudaFuncSetAttribute(dy_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                (int)cudaSharedmemCarveoutMaxL1));
 
   for (int b0 = 0; b0 < p.B; b0 += cb) {
     const int nb = p.B - b0 < cb ? p.B - b0 : cb;
@@ -943,7 +934,7 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
     if (any_f) {
       if (int rc = launch_ygemm_accum(a_rows, outs, wts, rows, p.nl, p.S, need, st)) return rc;
     }
-    if (any_w && getenv("VFA_BWD_CUBLAS_DW") == nullptr) {
+    if (any_w && !runtime_config().bwd_cublas_dw) {
       const float* gsp[VFA_MAX_SCALES];
       const float* fp[VFA_MAX_SCALES];
       float* dwp[VFA_MAX_SCALES];

@@ -45,6 +45,34 @@ void set_path(const char* name);
 int check_device();   // VFA_OK iff the current device is sm_100
 
 // ---------------------------------------------------------------------------------------------------------
+// process-wide state (host): everything the library keeps besides the thread-local error string
+// ---------------------------------------------------------------------------------------------------------
+// Debug / A-B switches, read from the environment ONCE (first call) -- never on the launch path.  vfa_reload_env()
+// re-reads them (tests and timing scripts that flip a switch inside one process).
+struct RuntimeConfig {
+  int pool_tile;          // VFA_POOL_TILE      1 (default): staged-tile pooling for batch >= 2; 2: any batch; 0: off
+  int pool_tile_cap;      // VFA_POOL_TILE_CAP  pool sizes of the tiles' chunk lists in percent (100)
+  int tile_variant;       // VFA_TILE_VARIANT   pool_tile_kernel debug bits
+  int pool_list;          // VFA_POOL_LIST      0: walking kernel instead of the quads' texel lists
+  int pool_quad;          // VFA_POOL_QUAD      0: one-cell-per-warp comparison kernel
+  int pool_list_cap;      // VFA_POOL_LIST_CAP  list entries per (view, scale, layer) of a quad's slot (0 = default)
+  int fside_compact;      // VFA_FSIDE_COMPACT  0: whole 256-row GEMM tiles instead of compacted rows
+  int fside_no_skip;      // VFA_FSIDE_NO_SKIP  1: multiply every (tile, layer)
+  long long y_budget_mb;  // VFA_FSIDE_Y_BUDGET_MB  Y bytes held per frame chunk (0 = 6 GiB)
+  int umma_variant;       // VFA_UMMA_VARIANT   debug bits of the forward launchers
+  int fwd_gridside;       // VFA_FWD_GRIDSIDE   1: grid-side fused kernel by default
+  int bwd_scatter, bwd_untiled, bwd_generic, bwd_cublas_dw;   // VFA_BWD_*  (set = 1)
+  int bwd_csr_per_box;    // VFA_BWD_CSR_PER_BOX  CSR capacity per box (0 = default)
+};
+const RuntimeConfig& runtime_config();
+
+// Per-device caches (a process may drive several GPUs: nn.DataParallel, `with torch.cuda.device(d)`): keyed by the
+// current device, filled under a mutex.  `slot` names the cached quantity.
+enum DeviceCacheSlot { DC_YGEMM_CLUSTERS = 0, DC_YGEMM_COMPACT_CLUSTERS, DC_DWEIGHT_CLUSTERS, DC_SM_COUNT, DC_SLOTS };
+int device_cache_get(int slot);            // 0 = not cached yet
+void device_cache_set(int slot, int value);
+
+// ---------------------------------------------------------------------------------------------------------
 // per-box taps (device)
 // ---------------------------------------------------------------------------------------------------------
 #define VFA_EPSILON_F 1e-6f          // reference vfa_op.py:14

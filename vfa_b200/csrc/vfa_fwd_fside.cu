@@ -1063,8 +1063,7 @@ int launch_tile_need(const AggParams& p, void* cover_ws, int frames, const uint8
   const int total = q.tile_begin[p.S] * p.nl;
   *need_out = need;
   if (!run) return VFA_OK;
-  const char* e = getenv("VFA_FSIDE_NO_SKIP");
-  if (e != nullptr && atoi(e) != 0) {
+  if (runtime_config().fside_no_skip != 0) {
     VFA_CUDA(cudaMemsetAsync(need, 1, (size_t)total, st));
     return VFA_OK;
   }
@@ -1395,13 +1394,10 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_compact_kernel(const YCompac
 
 // One persistent launch over all cluster tiles of `g` (tile_begin must be filled for g.S scales).
 static int launch_ygemm(YGemmArgs& g, int mode, bool bf16, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  // function attributes are per device: set on every launch (a host-side table update, no device work)
+  VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  VFA_CUDA(cudaFuncSetAttribute(ygemm_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
@@ -1413,7 +1409,7 @@ static int launch_ygemm(YGemmArgs& g, int mode, bool bf16, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int resident_clusters = 0;      // CTA pairs the device can hold at once (1 CTA per SM)
+  int resident_clusters = device_cache_get(DC_YGEMM_CLUSTERS);      // CTA pairs the device can hold at once (1 CTA per SM)
   if (resident_clusters == 0) {
     cfg.gridDim = dim3(2 * 148);
     int n = 0;
@@ -1422,6 +1418,7 @@ static int launch_ygemm(YGemmArgs& g, int mode, bool bf16, cudaStream_t st) {
       n = 64;
     }
     resident_clusters = n;
+    device_cache_set(DC_YGEMM_CLUSTERS, n);
   }
   g.n_tiles = g.tile_begin[g.S];
   if (g.n_tiles <= 0) return VFA_OK;
@@ -1479,12 +1476,8 @@ static int launch_rowlists(const AggParams& p, void* cover_ws, int frames, cudaS
 
 static int launch_ygemm_compact(const AggParams& p, const YGemmArgs& g, void* cover_ws, int frames_layout, int nb, bool bf16,
                                 cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
-  }
+  VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const CoverMap cm = make_cover_map(p);
   const CoverLayout L = cover_layout(p, frames_layout);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(cover_ws);
@@ -1514,7 +1507,7 @@ static int launch_ygemm_compact(const AggParams& p, const YGemmArgs& g, void* co
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static int resident_clusters = 0;
+  int resident_clusters = device_cache_get(DC_YGEMM_COMPACT_CLUSTERS);
   if (resident_clusters == 0) {
     cfg.gridDim = dim3(2 * 148);
     int n = 0;
@@ -1523,6 +1516,7 @@ static int launch_ygemm_compact(const AggParams& p, const YGemmArgs& g, void* co
       n = 64;
     }
     resident_clusters = n;
+    device_cache_set(DC_YGEMM_COMPACT_CLUSTERS, n);
   }
   long long max_units = (long long)L.max_units * nb;     // the real count lives on the device; this bounds the grid
   cfg.gridDim = dim3(2 * (int)(max_units < resident_clusters ? max_units : resident_clusters));
@@ -1544,10 +1538,7 @@ size_t fside_y_bytes_per_frame(const AggParams& p) {
 // frames per chunk for a Y budget (the workspace holds Y of one chunk)
 int fside_chunk_frames(const AggParams& p) {
   size_t budget = (size_t)6 << 30;
-  if (const char* e = getenv("VFA_FSIDE_Y_BUDGET_MB")) {      // tests: force several chunks on small inputs
-    const long long mb = atoll(e);
-    if (mb > 0) budget = (size_t)mb << 20;
-  }
+  if (runtime_config().y_budget_mb > 0) budget = (size_t)runtime_config().y_budget_mb << 20;      // tests: several chunks
   const size_t per = fside_y_bytes_per_frame(p);
   size_t cb = budget / per;
   if (cb < 1) cb = 1;
@@ -1564,9 +1555,8 @@ struct ListLayout {
   uint32_t slot;
 };
 static bool pool_list_enabled() {
-  const char* e = getenv("VFA_POOL_LIST");
-  const char* q = getenv("VFA_POOL_QUAD");               // the one-cell-per-warp comparison kernel has no lists
-  return (e == nullptr || atoi(e) != 0) && !(q != nullptr && atoi(q) == 0);
+  // (the one-cell-per-warp comparison kernel has no lists)
+  return runtime_config().pool_list != 0 && runtime_config().pool_quad != 0;
 }
 static ListLayout list_layout(const AggParams& p) {
   ListLayout L = {};
@@ -1575,10 +1565,7 @@ static ListLayout list_layout(const AggParams& p) {
   L.quads_x = (p.W + 1) / 2;
   L.n_quads = L.quads_x * ((p.L + 1) / 2);
   unsigned long long per = LIST_PER_ITER;
-  if (const char* e = getenv("VFA_POOL_LIST_CAP")) {
-    const long long c = atoll(e);
-    if (c > 0) per = (unsigned long long)c;
-  }
+  if (runtime_config().pool_list_cap > 0) per = (unsigned long long)runtime_config().pool_list_cap;
   unsigned long long slot = per * (unsigned long long)(p.V * p.S * p.nl);
   const unsigned long long most = 0xfffffff0ull / (unsigned long long)(L.n_quads > 0 ? L.n_quads : 1);
   if (slot > most) slot = most;                          // entry indices are 32-bit
@@ -1626,8 +1613,7 @@ size_t fside_workspace_bytes(const AggParams& p) {
 int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
                      uint32_t flags, int variant, cudaStream_t st) {
   const bool bf16 = (flags & VFA_FLAG_BF16_FEATURES) != 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxL1));
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1639,7 +1625,6 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_list_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_list_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
-    attr_set = true;
   }
   const size_t per_frame = fside_y_bytes_per_frame(p);
   const size_t tile_bytes = tile_pool_workspace_bytes(p);
@@ -1657,9 +1642,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
   uint8_t* list_ws = reinterpret_cast<uint8_t*>(fs_ws) + cover_bytes;
   float* y_ws = reinterpret_cast<float*>(list_ws + lists_bytes);
   // row-compacted GEMM unless VFA_FSIDE_COMPACT=0 (whole 256-row tiles, skipped by the need bytes) or VFA_FSIDE_NO_SKIP=1
-  const char* ec = getenv("VFA_FSIDE_COMPACT");
-  const char* en = getenv("VFA_FSIDE_NO_SKIP");
-  const bool compact = !(ec != nullptr && atoi(ec) == 0) && !(en != nullptr && atoi(en) != 0);
+  const bool compact = runtime_config().fside_compact != 0 && runtime_config().fside_no_skip == 0;
   if (!(variant & 256)) {       // (debug bit 256: reuse tap records, coverage bitmap, lists and need bytes of the previous call)
     if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
     if (compact)
@@ -1709,8 +1692,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       }
     }
     if (!(variant & 64)) {
-      const char* eq = getenv("VFA_POOL_QUAD");     // VFA_POOL_QUAD=0 selects the one-cell-per-warp kernel (debug / comparison)
-      const int quad = (eq == nullptr || atoi(eq) != 0) ? 1 : 0;
+      const int quad = runtime_config().pool_quad != 0;     // 0 selects the one-cell-per-warp kernel (debug / comparison)
       q.tile_ovf = nullptr;
       q.ptiles_x = 0;
       if (quad && tile_bytes != 0) {

@@ -815,8 +815,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
                      uint32_t flags, int variant, cudaStream_t st);
 
 static bool grid_side_requested(uint32_t flags) {
-  const char* e = getenv("VFA_FWD_GRIDSIDE");
-  return (flags & VFA_FLAG_GRID_SIDE) != 0 || (e != nullptr && atoi(e) != 0);
+  return (flags & VFA_FLAG_GRID_SIDE) != 0 || runtime_config().fwd_gridside != 0;
 }
 
 // workspace: [prepared weights][tap records][Y of one frame chunk (feature-side forward only)]
@@ -860,18 +859,15 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, size_t 
     if (int rc = prep_weights_umma(p, d_weight, ws, st)) return rc;
   }
   const bool bf16 = (flags & VFA_FLAG_BF16_FEATURES) != 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (grid_side_requested(flags)) {
     VFA_CUDA(cudaFuncSetAttribute(aggregate_fwd_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SMEM_BYTES));
     VFA_CUDA(cudaFuncSetAttribute(aggregate_fwd_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SMEM_BYTES));
-    attr_set = true;
   }
   UmmaArgs a;
   a.p = p;
-  const char* var = getenv("VFA_UMMA_VARIANT");
-  a.variant = var ? atoi(var) : 0;
+  a.variant = runtime_config().umma_variant;
   if (flags & VFA_FLAG_TABLE_PREPARED) a.variant |= 256;      // static cameras: records / coverage / lists are still valid
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   for (int s = 0; s < VFA_MAX_SCALES; ++s) a.wprep[s] = reinterpret_cast<const uint8_t*>(ws) + (s < p.S ? s : 0) * per_scale;

@@ -711,21 +711,14 @@ struct TileLayout {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
-static bool tile_enabled() {
-  return env_int("VFA_POOL_TILE", 1) != 0 && env_int("VFA_POOL_QUAD", 1) != 0;
-}
+static bool tile_enabled() { return runtime_config().pool_tile != 0 && runtime_config().pool_quad != 0; }
 
 static TileLayout tile_layout(const AggParams& p) {
   TileLayout L = {};
   L.VS = p.V * p.S;
   // The chunk lists cost 0.3 ms to build (the quads' texel lists 0.15 ms) and save 0.1 ms of pooling per frame: they pay
   // from two frames per call on (VFA_POOL_TILE=2 forces them for any batch).
-  if (!tile_enabled() || L.VS > 32 || (p.B < 2 && env_int("VFA_POOL_TILE", 1) < 2)) return L;
+  if (!tile_enabled() || L.VS > 32 || (p.B < 2 && runtime_config().pool_tile < 2)) return L;
   size_t max_bits = 0;
   for (int s = 0; s < p.S; ++s) max_bits = max_bits > (size_t)p.nl * p.sc[s].fh * p.sc[s].fw ? max_bits : (size_t)p.nl * p.sc[s].fh * p.sc[s].fw;
   L.max_words = (int)((max_bits + 31) / 32);
@@ -738,7 +731,7 @@ static TileLayout tile_layout(const AggParams& p) {
   L.tiles_x = (p.W + TC - 1) / TC;
   L.n_tiles = L.tiles_x * ((p.L + TC - 1) / TC);
   // pools: chunks and blob bytes per (tile, view, scale, layer); VFA_POOL_TILE_CAP scales both (tests force overflows)
-  const int cap = env_int("VFA_POOL_TILE_CAP", 100);
+  const int cap = runtime_config().pool_tile_cap;
   const unsigned long long iters = (unsigned long long)L.n_tiles * L.VS * p.nl;
   unsigned long long dc = iters * 3ull * cap / 100 + L.n_tiles * L.VS, bc16 = iters * (3072ull / 16) * cap / 100 + L.n_tiles * L.VS * 8ull;
   if (dc > 0x7fffffffull) dc = 0x7fffffffull;
@@ -810,10 +803,14 @@ int launch_pool_tile(fside::PoolArgs q, void* ws, int nb, bool y_bf16, cudaStrea
   a.nb = nb;
   a.next_item = reinterpret_cast<uint32_t*>(w8 + L.off_cursors) + 2;
   VFA_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(uint32_t), st));
-  a.variant = env_int("VFA_TILE_VARIANT", 0);
-  int dev = 0, sms = 148;
-  VFA_CUDA(cudaGetDevice(&dev));
-  VFA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  a.variant = runtime_config().tile_variant;
+  int sms = device_cache_get(DC_SM_COUNT);
+  if (sms == 0) {
+    int dev = 0;
+    VFA_CUDA(cudaGetDevice(&dev));
+    VFA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    device_cache_set(DC_SM_COUNT, sms);
+  }
   const long long items = (long long)L.n_tiles * nb;
   const int grid = (int)(items < sms ? items : sms);
   const bool mask = p.mask != nullptr;

@@ -144,8 +144,10 @@ def make_shape(feats_cl, n_layers: int) -> _lib.Shape:
     return shape
 
 
-def workspace_for(geom, shape, flags, device) -> torch.Tensor:
-    n = _lib.lib().vfa_aggregate_workspace_bytes(C.byref(geom), C.byref(shape), int(flags))
+def workspace_for(geom, shape, flags, device, direction: str = 'forward') -> torch.Tensor:
+    """Scratch for one direction ('forward' / 'backward') or both ('both') of the kernel family `flags` selects."""
+    size_flag = {'forward': _lib.FLAG_WS_FORWARD, 'backward': _lib.FLAG_WS_BACKWARD, 'both': 0}[direction]
+    n = _lib.lib().vfa_aggregate_workspace_bytes(C.byref(geom), C.byref(shape), int(flags) | size_flag)
     return torch.empty(max(n, 256), dtype=torch.uint8, device=device)
 
 
@@ -178,6 +180,9 @@ def aggregate_forward_raw(feats_cl, table, weights, biases, flags=0, out=None, w
             out = torch.empty(shape.batch, geom.grid_l, geom.grid_w, shape.channels, dtype=torch.float32, device=dev)
         else:
             out = torch.empty(shape.batch, shape.channels, geom.grid_l, geom.grid_w, dtype=torch.float32, device=dev)
+    if workspace is None and int(flags) & (_lib.FLAG_TABLE_PREPARED | _lib.FLAG_WEIGHTS_PREPARED):
+        raise ValueError('FLAG_TABLE_PREPARED / FLAG_WEIGHTS_PREPARED describe the contents of a caller-owned workspace: '
+                         'pass `workspace=` (a freshly allocated one holds garbage)')
     ws = workspace if workspace is not None else workspace_for(geom, shape, flags, dev)
     f = int(flags) | (_lib.FLAG_WEIGHTS_PREPARED if prepared else 0)
     if table_prepared:
@@ -241,7 +246,7 @@ class _AggregateFn(torch.autograd.Function):
         gw = [torch.empty_like(weights[s]) if want_wb[s] else None for s in range(S)]
         gb = [torch.empty(weights[s].shape[0], dtype=torch.float32, device=dev) if want_wb[s] else None
               for s in range(S)]
-        ws = workspace_for(ctx.geom, ctx.shape, ctx.flags, dev)
+        ws = workspace_for(ctx.geom, ctx.shape, ctx.flags, dev, direction='backward')
         with torch.cuda.device(dev):
             _lib.check(L.vfa_aggregate_bwd(C.byref(ctx.geom), C.byref(ctx.shape), boxes.data_ptr(),
                                            _lib.ptr_array([t.data_ptr() for t in feats]),
@@ -282,7 +287,9 @@ def aggregate(feats, table: ProjectionTable, weights, biases, flags: int = 0, ch
             raise RuntimeError('bfloat16 feature maps are forward-only; run under torch.no_grad() or pass float32')
         return aggregate_forward_raw([t.contiguous() for t in cl], table, [w.detach() for w in weights],
                                      [b.detach() for b in biases], flags)
-    return _AggregateFn.apply(table.geom, table.boxes, int(flags), S, *cl, *weights, *biases)
+    # the PREPARED bits describe a caller-owned workspace; the autograd path allocates its own
+    flags = int(flags) & ~(_lib.FLAG_TABLE_PREPARED | _lib.FLAG_WEIGHTS_PREPARED)
+    return _AggregateFn.apply(table.geom, table.boxes, flags, S, *cl, *weights, *biases)
 
 
 def last_kernel_path() -> str:
