@@ -159,7 +159,7 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
                       void* stream);
 
 /* Backward of vfa_aggregate_fwd (what autograd derives for reference vfa_op.py:110-124): given d_grad_out
- * [B,C,L,W] accumulates into d_grad_feats[s] [B,V,fH,fW,C] (must be zero-initialised by the caller),
+ * [B,C,L,W] ([B,L,W,C] with VFA_FLAG_OUT_NHWC, C = 256: read in place, no transpose) accumulates into d_grad_feats[s] [B,V,fH,fW,C] (must be zero-initialised by the caller),
  * d_grad_weight[s] [C, C*nl] and d_grad_bias[s] [C] (both fully overwritten).  Any gradient pointer array
  * entry may be NULL to skip it.  Needs the ReLU mask the forward wrote; recomputes the pooled voxels instead of
  * saving them (the reference keeps 0.6-1.8 GB of intermediates per call for autograd). */

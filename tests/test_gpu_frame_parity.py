@@ -177,3 +177,30 @@ def test_tile_pooling_overflow_nhwc_and_determinism(libenv):
         moved = ((grad_c - grad_t).abs() > 2e-5 * float(grad_t.abs().max())).float().mean()
         assert float(moved) < 1e-4, f'{key}={val}: {float(moved):.2e} of dFeature elements differ'
         libenv.delenv(key, raising=False)
+
+
+def test_channels_last_output_through_autograd():
+    """VFA_FLAG_OUT_NHWC through the autograd entry (what VFANet hands its heads): the result is a [B, C, L, W] tensor in
+    torch.channels_last with the bits of the [B, C, L, W]-contiguous result, and the backward reads a channels-last
+    cotangent in place -- same gradients (atomics reorder the sums: compared to rounding)."""
+    g = geometry.MULTIVIEWX
+    grid = geometry.grid_for(g)[::2, ::2].contiguous()
+    calibs = synthetic.ring_calibs(g, n_views=2)
+    feats = synthetic.features(g, batch=2, n_views=2, seed=61)
+    params = synthetic.collapse_params(g, seed=61)
+    table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    gout = torch.randn(2, 256, *grid.shape[:2], generator=torch.Generator().manual_seed(7)).cuda()
+    res = {}
+    for tag, flags in (('nchw', 0), ('nhwc', vfa_b200.FLAG_OUT_NHWC)):
+        f = [t.cuda().requires_grad_(True) for t in feats]
+        w = [x.cuda().requires_grad_(True) for x, _ in params]
+        b = [x.cuda().requires_grad_(True) for _, x in params]
+        out = vfa_b200.aggregate(f, table, w, b, flags=flags)
+        go = gout.contiguous(memory_format=torch.channels_last) if tag == 'nhwc' else gout
+        out.backward(go)
+        res[tag] = (out.detach(), [t.grad for t in f + w + b])
+    assert res['nhwc'][0].shape == res['nchw'][0].shape
+    assert res['nhwc'][0].is_contiguous(memory_format=torch.channels_last) and not res['nhwc'][0].is_contiguous()
+    assert torch.equal(res['nhwc'][0], res['nchw'][0])
+    for a, b_ in zip(res['nhwc'][1], res['nchw'][1]):
+        assert float((a - b_).abs().max()) <= 1e-5 * float(b_.abs().max())

@@ -102,7 +102,7 @@ bool umma_supported(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
 int launch_fwd_umma(AggParams, const float* const*, void*, size_t, uint32_t, cudaStream_t);
 size_t bwd_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*);
 int launch_bwd(AggParams, const float* const*, const float*, float* const*, float* const*, float* const*, void*, size_t,
-               cudaStream_t);
+               uint32_t, cudaStream_t);
 
 static int validate_geometry(const vfa_geometry_t* g) {
   VFA_REQUIRE(g != nullptr, VFA_ERR_INVALID_ARGUMENT, "geometry is NULL");
@@ -300,7 +300,6 @@ int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
                       const float* d_grad_out, float* const* d_grad_feats, float* const* d_grad_weight,
                       float* const* d_grad_bias, void* d_workspace, size_t workspace_bytes, uint32_t flags,
                       void* stream) {
-  (void)flags;
   if (int rc = validate_geometry(geom)) return rc;
   if (int rc = validate_shape(geom, shape)) return rc;
   VFA_REQUIRE(d_boxes && d_feats && d_weight && d_relu_mask && d_grad_out, VFA_ERR_INVALID_ARGUMENT,
@@ -317,7 +316,7 @@ int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
               "workspace must be a 256-byte aligned device pointer");
   VFA_REQUIRE(workspace_bytes >= bwd_workspace_bytes(geom, shape), VFA_ERR_WORKSPACE, "workspace %zu < required %zu",
               workspace_bytes, bwd_workspace_bytes(geom, shape));
-  return launch_bwd(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, d_workspace, workspace_bytes,
+  return launch_bwd(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, d_workspace, workspace_bytes, flags,
                     (cudaStream_t)stream);
 }
 

@@ -523,7 +523,7 @@ int launch_unprep_dweight(const float* dwr, float* dw, int C, int nl, cudaStream
 // C = 256: gather-form backward with the tcgen05 dFeature product (vfa_bwd_fside.cu)
 size_t bwd_fside_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh);
 int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_grad_out, float* const* d_grad_feats,
-                     float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, cudaStream_t st);
+                     float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, bool gout_nhwc, cudaStream_t st);
 static bool gather_backward(int channels) { return channels == 256 && !runtime_config().bwd_scatter; }
 
 static size_t fs_gs_elems(const AggParams& p) {
@@ -640,10 +640,14 @@ size_t bwd_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh) {
 }
 
 int launch_bwd(AggParams p, const float* const* d_weight, const float* d_grad_out, float* const* d_grad_feats,
-               float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, cudaStream_t st) {
+               float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, uint32_t flags,
+               cudaStream_t st) {
   VFA_REQUIRE(p.C <= MAXC, VFA_ERR_UNSUPPORTED, "backward supports up to %d channels (got %d)", MAXC, p.C);
+  const bool gout_nhwc = (flags & VFA_FLAG_OUT_NHWC) != 0;
   if (gather_backward(p.C))
-    return launch_bwd_fside(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, ws, ws_bytes, st);
+    return launch_bwd_fside(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, ws, ws_bytes, gout_nhwc, st);
+  VFA_REQUIRE(!gout_nhwc, VFA_ERR_UNSUPPORTED, "a channels-last cotangent (VFA_FLAG_OUT_NHWC) is read by the C = 256 gather "
+              "backward only");
   if (feature_side_ok(p) && !runtime_config().bwd_generic)
     return launch_bwd_feature_side(p, d_weight, d_grad_out, d_grad_feats, d_grad_weight, d_grad_bias, ws, st);
   BwdParams q;

@@ -799,7 +799,8 @@ size_t bwd_fside_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh)
 }
 
 int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_grad_out, float* const* d_grad_feats,
-                     float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, cudaStream_t st) {
+                     float* const* d_grad_weight, float* const* d_grad_bias, void* ws, size_t ws_bytes, bool gout_nhwc,
+                     cudaStream_t st) {
   using namespace bfs;
   int fh[VFA_MAX_SCALES] = {0, 0, 0}, fwv[VFA_MAX_SCALES] = {0, 0, 0};
   for (int s = 0; s < p.S; ++s) {
@@ -874,11 +875,12 @@ int launch_bwd_fside(AggParams p, const float* const* d_weight, const float* d_g
 
   for (int b0 = 0; b0 < p.B; b0 += cb) {
     const int nb = p.B - b0 < cb ? p.B - b0 : cb;
-    // dOut[b0 .. b0+nb) : [C, LW] -> [LW, C]
-    if (int rc = launch_transpose(d_grad_out + (size_t)b0 * CH * p.LW, gt, nb, CH, p.LW, st)) return rc;
+    // dOut[b0 .. b0+nb) : [C, LW] -> [LW, C]; a channels-last cotangent (VFA_FLAG_OUT_NHWC) is read in place
+    if (!gout_nhwc)
+      if (int rc = launch_transpose(d_grad_out + (size_t)b0 * CH * p.LW, gt, nb, CH, p.LW, st)) return rc;
     GradParams gq;
     gq.p = p;
-    gq.gt = gt;
+    gq.gt = gout_nhwc ? d_grad_out + (size_t)b0 * p.LW * CH : gt;
     gq.gm = gm;
     gq.b0 = b0;
     for (int s = 0; s < VFA_MAX_SCALES; ++s) gq.gbias[s] = s < p.S ? d_grad_bias[s] : nullptr;

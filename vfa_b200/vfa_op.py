@@ -228,6 +228,8 @@ class _AggregateFn(torch.autograd.Function):
         ctx.geom, ctx.shape, ctx.flags, ctx.S = geom, shape, flags, S
         if need_grad:
             ctx.save_for_backward(boxes, mask, *feats, *weights)
+        if flags & _lib.FLAG_OUT_NHWC:                # memory is [B,L,W,C]: a [B,C,L,W] tensor in torch.channels_last
+            return out.permute(0, 3, 1, 2)
         return out
 
     @staticmethod
@@ -235,7 +237,10 @@ class _AggregateFn(torch.autograd.Function):
         S = ctx.S
         saved = ctx.saved_tensors
         boxes, mask, feats, weights = saved[0], saved[1], saved[2:2 + S], saved[2 + S:2 + 2 * S]
-        grad_out = grad_out.contiguous()
+        if ctx.flags & _lib.FLAG_OUT_NHWC:            # zero-copy when the consumer ran in channels_last (cuDNN heads)
+            grad_out = grad_out.permute(0, 2, 3, 1).contiguous()
+        else:
+            grad_out = grad_out.contiguous()
         dev = grad_out.device
         L = _lib.lib()
         need_f = [ctx.needs_input_grad[4 + s] for s in range(S)]

@@ -12,7 +12,18 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from .vfa_op import aggregate, build_table
+
+
+def head_flags(flags: int, channels: int) -> int:
+    """Flags of the aggregation when its consumer is a convolutional head (reference vfanet.py:131-139): with the C = 256
+    feature-side forward the BEV map is emitted [B, L, W, C] and returned as a [B, C, L, W] tensor in torch.channels_last
+    -- cuDNN reads it without a permute, the pooling epilogue writes 1 KB rows instead of a stride-L*W scatter, and the
+    backward reads the heads' channels-last cotangent in place."""
+    if channels == 256 and not (int(flags) & (_lib.FLAG_GRID_SIDE | _lib.FLAG_FORCE_SIMT)):
+        return int(flags) | _lib.FLAG_OUT_NHWC
+    return int(flags)
 
 
 def lateral_features(model, feats8, feats16, feats32):
@@ -42,7 +53,7 @@ def aggregate_cameras(model, feats8, feats16, feats32, calibs, grid, crange=(-1.
     table = build_table(geom, calibs, grid)
     feats = [x.reshape(batch, V, *x.shape[1:]) for x in lats]
     return aggregate(feats, table, [m.collapse.weight for m in vfas], [m.collapse.bias for m in vfas],
-                     flags=vfas[0].flags)
+                     flags=head_flags(vfas[0].flags, lats[0].shape[1]))
 
 
 class MultiScaleVFA(torch.nn.Module):
