@@ -204,3 +204,40 @@ def test_channels_last_output_through_autograd():
     assert torch.equal(res['nhwc'][0], res['nchw'][0])
     for a, b_ in zip(res['nhwc'][1], res['nchw'][1]):
         assert float((a - b_).abs().max()) <= 1e-5 * float(b_.abs().max())
+
+
+@pytest.mark.parametrize('storage', ['f32', 'bf16'])
+def test_bf16_mma_variant(storage):
+    """VFA_FLAG_BF16_MMA (north_star: "bf16 features within a stated tolerance"): bf16 operands in ONE tcgen05 kind::f16
+    pass with fp32 accumulation, Y stored in bf16, pooling / bias / ReLU / sums in fp32.  Stated tolerance against the
+    float64 port of the reference on the SAME fp32 inputs: 4e-3 of the output scale (max |out|) on every element (measured 1.6e-3),
+    mean |error| below 5e-4 of it (measured 2e-4) -- operands and Y carry 8 bits of mantissa (relative rounding 2^-9 = 2e-3), the
+    contraction and the sum over layers average the rounding errors down.  Whole frame, all views and scales, batch 2."""
+    name = 'MultiviewC'
+    g = geometry.GEOMETRIES[name]
+    grid = geometry.grid_for(g)
+    calibs = synthetic.ring_calibs(g)
+    feats = synthetic.features(g, batch=2, seed=71)
+    params = synthetic.collapse_params(g, seed=71)
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    cl = [vfa_b200.to_channels_last(f.cuda()) for f in feats]
+    if storage == 'bf16':
+        cl = [t.to(torch.bfloat16) for t in cl]
+    with torch.no_grad():
+        out = vfa_b200.aggregate(cl, table, ws, bs, flags=vfa_b200.FLAG_BF16_MMA, channels_last=True)
+        assert vfa_b200.last_kernel_path() == ('fside_bf16mma_bf16feat' if storage == 'bf16' else 'fside_bf16mma')
+        again = vfa_b200.aggregate(cl, table, ws, bs, flags=vfa_b200.FLAG_BF16_MMA, channels_last=True)
+        assert torch.equal(out, again)                                   # deterministic
+        full = vfa_b200.aggregate([f.cuda() for f in feats], table, ws, bs)
+    r0, sr, c0, sc = SUBSET[name]
+    want = _port(name, [f[1:2] for f in feats], calibs, grid[r0::sr, c0::sc].contiguous(), params)[0].numpy()
+    got = out[1, :, r0::sr, c0::sc].cpu().numpy().astype(np.float64)
+    scale = np.abs(want).max()
+    err = np.abs(got - want)
+    print(f'bf16 MMA ({storage} features): max |err| / max|out| = {err.max() / scale:.2e}, mean = {err.mean() / scale:.2e}; '
+          f'vs the fp32 path: {float((out - full).abs().max()) / scale:.2e}')
+    assert err.max() <= 4e-3 * scale and err.mean() <= 5e-4 * scale
+    with pytest.raises(RuntimeError, match='forward-only'):
+        vfa_b200.aggregate([t.float().requires_grad_(True) for t in cl], table, ws, bs, flags=vfa_b200.FLAG_BF16_MMA,
+                           channels_last=True)

@@ -96,7 +96,7 @@ int launch_transpose(const float*, float*, long long, int, long long, cudaStream
 size_t simt_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*);
 int prep_weights_simt(const AggParams&, const float* const*, void*, cudaStream_t);
 int launch_fwd_simt(AggParams, const float* const*, void*, uint32_t, cudaStream_t);
-int prep_weights_umma(const AggParams&, const float* const*, void*, cudaStream_t);
+int prep_weights_umma(const AggParams&, const float* const*, void*, uint32_t, cudaStream_t);
 size_t umma_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
 bool umma_supported(const vfa_geometry_t*, const vfa_shape_t*, uint32_t);
 int launch_fwd_umma(AggParams, const float* const*, void*, size_t, uint32_t, cudaStream_t);
@@ -155,6 +155,7 @@ static int fill_params(const vfa_geometry_t* g, const vfa_shape_t* sh, const flo
   p.LW = g->grid_l * g->grid_w;
   p.K = sh->channels * g->n_layers;
   p.boxes = d_boxes;
+  p.y_bf16 = 0;
   for (int s = 0; s < VFA_MAX_SCALES; ++s) {
     p.feats[s] = nullptr;
     p.wprep[s] = nullptr;
@@ -242,8 +243,6 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
   VFA_REQUIRE((reinterpret_cast<uintptr_t>(d_boxes) & 15) == 0, VFA_ERR_INVALID_ARGUMENT, "d_boxes not 16-byte aligned");
   VFA_REQUIRE(!((flags & VFA_FLAG_FORCE_SIMT) && (flags & VFA_FLAG_FORCE_UMMA)), VFA_ERR_INVALID_ARGUMENT,
               "FORCE_SIMT and FORCE_UMMA are exclusive");
-  VFA_REQUIRE(!(flags & VFA_FLAG_BF16_MMA), VFA_ERR_UNSUPPORTED,
-              "VFA_FLAG_BF16_MMA (single-pass bf16 collapse) is reserved and not implemented in this build");
   for (int s = 0; s < shape->n_scales; ++s)
     VFA_REQUIRE(d_weight[s] != nullptr, VFA_ERR_INVALID_ARGUMENT, "scale %d: NULL weight", s);
   if (int rc = check_device()) return rc;
@@ -260,6 +259,9 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
               "VFA_FLAG_OUT_NHWC is implemented by the feature-side forward (C = 256, without VFA_FLAG_GRID_SIDE) only");
   VFA_REQUIRE(!(flags & (VFA_FLAG_OUT_ACCUMULATE | VFA_FLAG_OUT_MULTICAST)) || (flags & VFA_FLAG_OUT_NHWC),
               VFA_ERR_UNSUPPORTED, "VFA_FLAG_OUT_ACCUMULATE / _MULTICAST need VFA_FLAG_OUT_NHWC (16-byte channel vectors)");
+  VFA_REQUIRE(!(flags & VFA_FLAG_BF16_MMA) || (use_umma && !(flags & VFA_FLAG_GRID_SIDE) && d_relu_mask == nullptr),
+              VFA_ERR_UNSUPPORTED, "VFA_FLAG_BF16_MMA is a forward-only variant of the feature-side path (C = 256, without "
+              "VFA_FLAG_GRID_SIDE, no ReLU mask)");
   if ((flags & VFA_FLAG_FORCE_UMMA) && !use_umma) {
     set_error("tcgen05 path requested but unsupported for channels=%d layers=%d", shape->channels, geom->n_layers);
     return VFA_ERR_UNSUPPORTED;
@@ -291,7 +293,7 @@ int vfa_prepare_weights(const vfa_geometry_t* geom, const vfa_shape_t* shape, co
   const bool use_umma = !(flags & VFA_FLAG_FORCE_SIMT) && umma_supported(geom, shape, flags);
   const size_t need = use_umma ? umma_workspace_bytes(geom, shape, flags) : simt_workspace_bytes(geom, shape);
   VFA_REQUIRE(workspace_bytes >= need, VFA_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
-  return use_umma ? prep_weights_umma(p, d_weight, d_workspace, (cudaStream_t)stream)
+  return use_umma ? prep_weights_umma(p, d_weight, d_workspace, flags, (cudaStream_t)stream)
                   : prep_weights_simt(p, d_weight, d_workspace, (cudaStream_t)stream);
 }
 

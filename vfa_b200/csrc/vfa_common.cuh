@@ -192,6 +192,7 @@ struct AggParams {
   const float* bias[VFA_MAX_SCALES];     // [C]
   const float* boxes;                    // [V, nl, LW, 4]
   float* out;                            // [B, C, L, W]
+  int y_bf16;                            // feature-side forward: the intermediate Y is stored in bf16 (VFA_FLAG_BF16_MMA)
   uint32_t* mask;                        // nullptr or [B, V, S, ceil(C/32), LW]: ReLU pass bits (word o/32, bit o%32)
 };
 

@@ -23,6 +23,7 @@
 //
 // Y (fp32, [plane, layer, texel, o]) lives in the caller's workspace for a chunk of frames (678 MB per MultiviewC frame);
 // it is 5x the feature maps but a quarter of the [V, C, nl, L, W] tensor the reference materialises per scale.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "vfa_common.cuh"
@@ -505,7 +506,24 @@ static_assert(8 % QTB == 0, "");
 
 // OVF = true: the completion pass behind pool_list_kernel -- only the quads whose texel list did not fit its slot are
 // walked (normally none: the warp returns at once); the list kernel leaves exactly those quads alone.
-template <bool MASK, bool OVF = false>
+// row of Y as two float4 per lane (channels chan_of(lane, 0..7)); YB: Y is stored in bf16 (widening is a 16-bit shift)
+template <bool YB>
+__device__ __forceinline__ void load_y_row(const void* ybase, size_t row, int lane, float4& va, float4& vb) {
+  if (YB) {
+    const uint8_t* r = static_cast<const uint8_t*>(ybase) + row * (CH * 2);
+    const uint2 x = __ldg(reinterpret_cast<const uint2*>(r + lane * 8)), y = __ldg(reinterpret_cast<const uint2*>(r + CH + lane * 8));
+    va = make_float4(__uint_as_float(x.x << 16), __uint_as_float(x.x & 0xffff0000u), __uint_as_float(x.y << 16),
+                     __uint_as_float(x.y & 0xffff0000u));
+    vb = make_float4(__uint_as_float(y.x << 16), __uint_as_float(y.x & 0xffff0000u), __uint_as_float(y.y << 16),
+                     __uint_as_float(y.y & 0xffff0000u));
+  } else {
+    const float* r = static_cast<const float*>(ybase) + row * CH + lane * 4;
+    va = __ldg(reinterpret_cast<const float4*>(r));
+    vb = __ldg(reinterpret_cast<const float4*>(r + CH / 2));
+  }
+}
+
+template <bool MASK, bool OVF = false, bool YB = false>
 __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_kernel(const PoolArgs a) {
   __shared__ float out_s[QWARPS][4][CH];
   const AggParams& p = a.p;
@@ -541,13 +559,13 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
   for (int v = 0; v < p.V; ++v) {
     for (int s = 0; s < p.S; ++s) {
       const int fw = p.sc[s].fw, hw = p.sc[s].fh * p.sc[s].fw;
-      const float* yplane = static_cast<const float*>(a.y[s]) + ((size_t)(bl * p.V + v) * p.nl) * hw * CH + lane * 4;
+      size_t yplane = ((size_t)(bl * p.V + v) * p.nl) * hw;      // first row of the layer plane inside Y of scale s
       float acc[4][8];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
-      for (int n = 0; n < p.nl; ++n, ++j_rec, yplane += (size_t)hw * CH) {
+      for (int n = 0; n < p.nl; ++n, ++j_rec, yplane += (size_t)hw) {
         const uint4 r0 = n0, r1 = n1;
         if (j_rec + 1 < total) {
           rp += rec_stride;
@@ -569,8 +587,8 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
         for (int cb = 0; cb <= ux1 - ux0; cb += 8) {
           const int rx = ux0 + cb + jl - x0;
           const float wx = (vis && rx >= 0 && rx < nx) ? (rx == 0 ? wx_first : (rx == nx - 1 ? wx_last : 1.0f)) : 0.f;
-          const float* rowp = yplane + ((size_t)uy0 * fw + ux0) * CH;
-          for (int ty = uy0; ty <= uy1; ++ty, rowp += (size_t)fw * CH) {
+          size_t rowp = yplane + (size_t)uy0 * fw + ux0;
+          for (int ty = uy0; ty <= uy1; ++ty, rowp += (size_t)fw) {
             const int ry = ty - y0;
             const float wy = (ry >= 0 && ry < ny) ? (ry == 0 ? wy_first : (ry == ny - 1 ? wy_last : wy_mid)) : 0.f;
             float wl = wy * wx;                         // weight of (cell cl, column cb + jl) in this row
@@ -579,17 +597,12 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
 #pragma unroll          // j static: the shuffles get immediate lane indices
             for (int j = 0; j < 8; j += QTB) {
               if ((bm >> (4 * j)) == 0u) break;
-              const float* tp = rowp + (size_t)(cb + j) * CH;
+              const size_t tp = rowp + (size_t)(cb + j);
               float4 va[QTB], vb[QTB];
 #pragma unroll
               for (int k = 0; k < QTB; ++k) {
                 if ((bm >> (4 * (j + k))) & 0xfu) {     // texels no box of the quad covers are never fetched
-                  va[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH));
-                  vb[k] = __ldg(reinterpret_cast<const float4*>(tp + k * CH + CH / 2));
-#if VFA_QUAD_PREFETCH
-                  // the same column of the next union row: one warp-wide prefetch covers the texel's 8 lines
-                  if (ty < uy1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k * CH + (size_t)fw * CH));
-#endif
+                  load_y_row<YB>(a.y[s], tp + k, lane, va[k], vb[k]);
                 }
               }
 #pragma unroll
@@ -1392,6 +1405,275 @@ __global__ void __launch_bounds__(THREADS, 1) ygemm_compact_kernel(const YCompac
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
+// ---- bf16 tensor-core variant (VFA_FLAG_BF16_MMA) -------------------------------------------------------------------------
+// The same row-compacted image-plane GEMM with bf16 operands: ONE tcgen05.mma kind::f16 pass (fp32 accumulate in TMEM)
+// instead of three TF32 passes, and Y stored in bf16 -- a sixth of the tensor-core work, half the Y bytes written here and
+// read by the pooling.  Not the parity path: operands are rounded to 8 bits of mantissa (tolerance stated and tested in
+// tests/test_gpu_frame_parity.py::test_bf16_mma_variant).  A stage = 64 K elements: A tile 128 rows x 128 B, this CTA's half
+// of the weight slab 128 rows x 128 B (SWIZZLE_128B both); 4 stages per unit, 4 MMAs (K = 16) per stage.
+namespace bfmma {
+constexpr int KE = 64;                                   // K elements per stage (128 bytes of bf16)
+constexpr int A_BYTES = TILE_M * 128;                    // 16 KB
+constexpr int B_BYTES = CH * 128;                        // 32 KB slab (N = 256); each CTA of the pair stages half
+constexpr int B_LOCAL_BYTES = B_BYTES / 2;
+constexpr int STAGE_BYTES = A_BYTES + B_LOCAL_BYTES;     // 32 KB
+constexpr int STAGES = 5;
+constexpr int CHUNKS = CH / KE;                          // 4 stages per unit (one layer of 256 listed rows)
+constexpr int ITEMS = TILE_M * 8 / (NUM_PRODUCER_WARPS * 32);      // 16-byte smem items per producer thread and stage
+constexpr int PATCH_BYTES = 32 * 64;                     // per epilogue warp: 32 rows x 32 bf16
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 512 + (size_t)NUM_EPILOGUE_WARPS * PATCH_BYTES;
+constexpr uint32_t IDESC = make_idesc_bf16(CH, 2 * TILE_M);
+struct __align__(16) Tail {
+  unsigned long long full[STAGES], empty[STAGES], peer_full[STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Tail) <= 512, "");
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // low half = a
+  return r;
+}
+
+// collapse.weight [C, C*nl] (column c*nl + n) -> per K chunk kc = n * CHUNKS + c / 64 a 32 KB block [256 rows x 128 B], bf16
+__global__ void __launch_bounds__(256) prep_weight_bf16_kernel(const float* __restrict__ w, uint8_t* __restrict__ wp, int nl) {
+  const int K = CH * nl;
+  const long long total = (long long)CH * K;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % KE);
+    const int o = (int)((idx / KE) % CH);
+    const int kc = (int)(idx / ((long long)KE * CH));
+    const int n = kc / CHUNKS, c = (kc % CHUNKS) * KE + kk;
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[(long long)o * K + (long long)c * nl + n]);
+    *reinterpret_cast<__nv_bfloat16*>(wp + (long long)kc * B_BYTES + swz(o, kk >> 3) + (kk & 7) * 2) = v;
+  }
+}
+
+template <bool BF16>      // BF16: the feature maps are stored in bf16; else fp32, rounded to bf16 by the producers
+__global__ void __launch_bounds__(THREADS, 1) ygemm_compact_bf16_kernel(const YCompactArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Tail* tail = reinterpret_cast<Tail*>(smem + (size_t)STAGES * STAGE_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int nuf = __ldg(a.n_units_frame);
+  const int n_units = nuf * a.nb;
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&tail->full[i], NUM_PRODUCER_WARPS + 1);
+      mbar_init(&tail->empty[i], 1);
+      mbar_init(&tail->peer_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tail->acc_full[i], 1);
+      mbar_init(&tail->acc_empty[i], 2 * NUM_EPILOGUE_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp == 0) {
+    // ================= weight loader =================
+    if (lane == 0) {
+      int it = 0;
+      for (int u = cluster; u < n_units; u += n_clusters) {
+        const RowUnit w = a.tab[u % nuf];
+        const uint8_t* wp = pick(a.wprep, w.s) + (size_t)(w.vn % a.nl) * CHUNKS * B_BYTES;
+        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&tail->full[st], B_LOCAL_BYTES);
+          bulk_g2s(smem + (size_t)st * STAGE_BYTES + A_BYTES, wp + (size_t)cc * B_BYTES + cta_rank * B_LOCAL_BYTES,
+                   B_LOCAL_BYTES, &tail->full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && cta_rank != 0) {
+      int it = 0;
+      for (int u = cluster; u < n_units; u += n_clusters)
+        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->full[st], (it / STAGES) & 1);
+          mbar_arrive_remote(&tail->peer_full[st], 0);
+        }
+    } else if (lane == 0) {
+      // ================= MMA issuer (pair leader) =================
+      int it = 0, ln = 0;
+      for (int u = cluster; u < n_units; u += n_clusters, ++ln) {
+        const int slot = ln & 1;
+        mbar_wait_cluster(&tail->acc_empty[slot], ((ln >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)slot * CH;
+        for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+          const int st = it % STAGES;
+          mbar_wait(&tail->full[st], (it / STAGES) & 1);
+          mbar_wait_cluster(&tail->peer_full[st], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+          const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KE / 16; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+            tc_mma_f16_pair(d_tmem, da + adv, db + adv, IDESC, (cc | ks) ? 1u : 0u);
+          }
+          tc_commit_t<true>(&tail->empty[st]);
+        }
+        tc_commit_t<true>(&tail->acc_full[slot]);
+      }
+    }
+  } else if (warp >= FIRST_PRODUCER_WARP && warp < FIRST_EPILOGUE_WARP) {
+    // ================= A producers: listed texel rows -> bf16 operand tile =================
+    const int pw = warp - FIRST_PRODUCER_WARP;
+    const int j = lane & 7;                          // 16-byte chunk (8 K elements) of the 128-byte tile row
+    const uint8_t* src[ITEMS];
+    uint32_t off[ITEMS];
+    bool ok[ITEMS];
+    int nidx[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) off[i] = swz((uint32_t)(32 * i + 4 * pw + (lane >> 3)), (uint32_t)j);
+    auto fetch_rows = [&](int u, int(&idx)[ITEMS]) {
+      const RowUnit w = a.tab[u % nuf];
+      const int* rl = a.rowlist + pick(a.rl_base, w.s) + (size_t)w.vn * pick(a.rl_stride, w.s);
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        const int e = w.j * (2 * TILE_M) + (int)cta_rank * TILE_M + 32 * i + 4 * pw + (lane >> 3);
+        idx[i] = e < w.cnt ? __ldg(rl + e) : -1;
+      }
+    };
+    constexpr int ES = BF16 ? 2 : 4;
+    auto bind = [&](int u, const int(&idx)[ITEMS]) {
+      const RowUnit w = a.tab[u % nuf];
+      const int plane = (u / nuf) * a.V + w.vn / a.nl;
+      const uint8_t* f = pick(a.feats, w.s) + ((size_t)plane * pick(a.hw, w.s)) * CH * ES + j * 8 * ES;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        ok[i] = idx[i] >= 0;
+        src[i] = f + (size_t)(ok[i] ? idx[i] : 0) * CH * ES;
+      }
+    };
+    auto load_stage = [&](uint4(&v)[ITEMS], int cc) {
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok[i]) {
+          const uint8_t* sp = src[i] + (size_t)cc * KE * ES;
+          if (BF16) {
+            v[i] = __ldg(reinterpret_cast<const uint4*>(sp));
+          } else {
+            const float4 lo = __ldg(reinterpret_cast<const float4*>(sp)), hi = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+            v[i] = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+          }
+        }
+      }
+    };
+    uint4 cur[ITEMS], nxt[ITEMS];
+    int u = cluster;
+    if (u < n_units) {
+      int idx0[ITEMS];
+      fetch_rows(u, idx0);
+      bind(u, idx0);
+      load_stage(cur, 0);
+      if (u + n_clusters < n_units) fetch_rows(u + n_clusters, nidx);
+    }
+    int it = 0;
+    for (; u < n_units; u += n_clusters) {
+      for (int cc = 0; cc < CHUNKS; ++cc, ++it) {
+        const int st = it % STAGES;
+        bool more = true;
+        if (cc + 1 < CHUNKS) {
+          load_stage(nxt, cc + 1);
+        } else if (u + n_clusters < n_units) {
+          bind(u + n_clusters, nidx);
+          load_stage(nxt, 0);
+          if (u + 2 * n_clusters < n_units) fetch_rows(u + 2 * n_clusters, nidx);
+        } else {
+          more = false;
+        }
+        mbar_wait(&tail->empty[st], ((it / STAGES) & 1) ^ 1);
+        uint8_t* at = smem + (size_t)st * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) *reinterpret_cast<uint4*>(at + off[i]) = cur[i];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->full[st]);
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < ITEMS; ++i) cur[i] = nxt[i];
+        }
+      }
+    }
+  } else if (warp >= FIRST_EPILOGUE_WARP) {
+    // ================= epilogue: accumulator -> bf16 -> the listed rows of Y[plane][layer] =================
+    const int e = warp - FIRST_EPILOGUE_WARP;
+    const int quarter = warp & 3;
+    const int col_begin = (e >> 2) * (CH / 2);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* patch = smem + (size_t)STAGES * STAGE_BYTES + 512 + (size_t)e * PATCH_BYTES;
+    const int sub = lane >> 2, chunk = lane & 3;      // store phase: patch row 8 * rr + sub, 16-byte chunk of its 64 bytes
+    int ln = 0;
+    for (int u = cluster; u < n_units; u += n_clusters, ++ln) {
+      const RowUnit w = a.tab[u % nuf];
+      const int hw = pick(a.hw, w.s);
+      const int* rl = a.rowlist + pick(a.rl_base, w.s) + (size_t)w.vn * pick(a.rl_stride, w.s);
+      const int plane = (u / nuf) * a.V + w.vn / a.nl;
+      uint32_t yrow[4];                               // Y row of patch row 8 * rr + sub; ~0u = beyond the list
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int en = w.j * (2 * TILE_M) + (int)cta_rank * TILE_M + quarter * 32 + 8 * rr + sub;
+        yrow[rr] = en < w.cnt ? (uint32_t)((plane * a.nl + w.vn % a.nl) * hw + __ldg(rl + en)) : 0xffffffffu;
+      }
+      const int slot = ln & 1;
+      mbar_wait_sleep(&tail->acc_full[slot], (ln >> 1) & 1);
+      tc_fence_after();
+      uint8_t* dst = reinterpret_cast<uint8_t*>(pick(a.y, w.s)) + (size_t)(col_begin) * 2 + chunk * 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CH / 2; c0 += 32) {
+        float v[32];
+        tc_ld32(lane_addr + (uint32_t)(slot * CH + col_begin + c0), v);
+        tc_wait_ld();
+        __syncwarp();                                 // the previous chunk has left the patch
+#pragma unroll
+        for (int i = 0; i < 4; ++i)                   // row `lane`: 4 x 16 bytes, chunk XOR-swizzled with the row pair
+          *reinterpret_cast<uint4*>(patch + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                         pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int prow = 8 * rr + sub;
+          const uint4 q = *reinterpret_cast<const uint4*>(patch + prow * 64 + ((chunk ^ ((prow >> 1) & 3)) << 4));
+          if (yrow[rr] != 0xffffffffu) *reinterpret_cast<uint4*>(dst + ((size_t)yrow[rr] * CH + c0) * 2) = q;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank != 0) mbar_arrive_remote(&tail->acc_empty[slot], 0);
+        else mbar_arrive(&tail->acc_empty[slot]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+}  // namespace bfmma
+
 // One persistent launch over all cluster tiles of `g` (tile_begin must be filled for g.S scales).
 static int launch_ygemm(YGemmArgs& g, int mode, bool bf16, cudaStream_t st) {
   // function attributes are per device: set on every launch (a host-side table update, no device work)
@@ -1476,8 +1758,15 @@ static int launch_rowlists(const AggParams& p, void* cover_ws, int frames, cudaS
 
 static int launch_ygemm_compact(const AggParams& p, const YGemmArgs& g, void* cover_ws, int frames_layout, int nb, bool bf16,
                                 cudaStream_t st) {
+  const bool mma_bf16 = p.y_bf16 != 0;
   VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   VFA_CUDA(cudaFuncSetAttribute(ygemm_compact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  if (mma_bf16) {
+    VFA_CUDA(cudaFuncSetAttribute(bfmma::ygemm_compact_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)bfmma::SMEM_BYTES));
+    VFA_CUDA(cudaFuncSetAttribute(bfmma::ygemm_compact_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)bfmma::SMEM_BYTES));
+  }
   const CoverMap cm = make_cover_map(p);
   const CoverLayout L = cover_layout(p, frames_layout);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(cover_ws);
@@ -1520,6 +1809,15 @@ static int launch_ygemm_compact(const AggParams& p, const YGemmArgs& g, void* co
   }
   long long max_units = (long long)L.max_units * nb;     // the real count lives on the device; this bounds the grid
   cfg.gridDim = dim3(2 * (int)(max_units < resident_clusters ? max_units : resident_clusters));
+  if (mma_bf16) {
+    cfg.dynamicSmemBytes = bfmma::SMEM_BYTES;
+    if (bf16)
+      VFA_CUDA(cudaLaunchKernelEx(&cfg, bfmma::ygemm_compact_bf16_kernel<true>, a));
+    else
+      VFA_CUDA(cudaLaunchKernelEx(&cfg, bfmma::ygemm_compact_bf16_kernel<false>, a));
+    VFA_LAUNCH_CHECK("ygemm_compact_bf16_kernel");
+    return VFA_OK;
+  }
   if (bf16)
     VFA_CUDA(cudaLaunchKernelEx(&cfg, ygemm_compact_kernel<true>, a));
   else
@@ -1532,7 +1830,7 @@ static int launch_ygemm_compact(const AggParams& p, const YGemmArgs& g, void* co
 size_t fside_y_bytes_per_frame(const AggParams& p) {
   size_t texels = 0;
   for (int s = 0; s < p.S; ++s) texels += (size_t)p.sc[s].fh * p.sc[s].fw;
-  return texels * p.V * p.nl * CH * sizeof(float);
+  return texels * p.V * p.nl * CH * (p.y_bf16 ? 2 : sizeof(float));
 }
 
 // frames per chunk for a Y budget (the workspace holds Y of one chunk)
@@ -1610,8 +1908,19 @@ size_t fside_workspace_bytes(const AggParams& p) {
   return fside_cover_bytes(p, cb) + pool_lists_bytes(p) + (size_t)cb * fside_y_bytes_per_frame(p);
 }
 
-int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
+// prepared bf16 weight slabs of the bf16 tensor-core variant (one slot of `per_scale` bytes per scale, as the tf32 slabs)
+int prep_weights_bf16(const AggParams& p, const float* const* d_weight, void* ws, size_t per_scale, cudaStream_t st) {
+  for (int s = 0; s < p.S; ++s) {
+    bfmma::prep_weight_bf16_kernel<<<148 * 4, 256, 0, st>>>(d_weight[s], reinterpret_cast<uint8_t*>(ws) + s * per_scale, p.nl);
+    VFA_LAUNCH_CHECK("prep_weight_bf16_kernel");
+  }
+  return VFA_OK;
+}
+
+int launch_fwd_fside(const AggParams& p_in, const uint8_t* const* wprep, const TapRec* recs, void* fs_ws, size_t fs_bytes,
                      uint32_t flags, int variant, cudaStream_t st) {
+  AggParams p = p_in;
+  p.y_bf16 = (flags & VFA_FLAG_BF16_MMA) ? 1 : 0;
   const bool bf16 = (flags & VFA_FLAG_BF16_FEATURES) != 0;
   {
     VFA_CUDA(cudaFuncSetAttribute(pool_y_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1623,6 +1932,7 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    VFA_CUDA(cudaFuncSetAttribute(pool_quad_kernel<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_list_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     VFA_CUDA(cudaFuncSetAttribute(pool_list_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
   }
@@ -1631,6 +1941,10 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
   ListLayout LL = list_layout(p);
   if (tile_bytes != 0) LL = ListLayout{};                  // the tiles' chunk lists replace the quads' texel lists
   const size_t lists_bytes = tile_bytes != 0 ? tile_bytes : LL.total;
+  if (p.y_bf16 && tile_bytes == 0) {
+    set_error("VFA_FLAG_BF16_MMA needs the staged-tile pooling (views * scales <= 32, feature maps below 4 M texel-layers)");
+    return VFA_ERR_UNSUPPORTED;
+  }
   int cb = fside_chunk_frames(p);
   while (cb > 1 && fside_cover_bytes(p, cb) + lists_bytes + (size_t)cb * per_frame > fs_bytes) --cb;
   const size_t cover_bytes = fside_cover_bytes(p, cb);
@@ -1666,7 +1980,8 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
     q.tiles_x = (p.W + POOL_TW - 1) / POOL_TW;
     g.nl = p.nl;
     g.S = p.S;
-    size_t y_off = 0;      // floats
+    size_t y_off = 0;      // bytes
+    const size_t y_es = p.y_bf16 ? 2 : 4;
     g.tile_begin[0] = 0;
     for (int s = 0; s < VFA_MAX_SCALES; ++s) {
       const int ss = s < p.S ? s : 0;
@@ -1675,17 +1990,20 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       g.rows[s] = nb * p.V * hw;
       g.feats[s] = reinterpret_cast<const uint8_t*>(p.feats[ss]) + (size_t)b0 * p.V * hw * CH * es;
       g.wprep[s] = wprep[ss];
-      g.y[s] = y_ws + (s < p.S ? y_off : 0);
+      g.y[s] = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(y_ws) + (s < p.S ? y_off : 0));
       q.y[s] = g.y[s];
       g.need_tile0[s] = g.tile_begin[s < p.S ? s : 0];
       if (s < p.S) {
-        y_off += (size_t)cb * p.V * p.nl * hw * CH;
+        y_off += (size_t)cb * p.V * p.nl * hw * CH * y_es;
         g.tile_begin[s + 1] = g.tile_begin[s] + (g.rows[s] + 2 * TILE_M - 1) / (2 * TILE_M);
       }
     }
     if (!(variant & 128)) {
       if (compact) {
         if (int rc = launch_ygemm_compact(p, g, fs_ws, cb, nb, bf16, st)) return rc;
+      } else if (p.y_bf16) {
+        set_error("VFA_FLAG_BF16_MMA runs the row-compacted GEMM only (VFA_FSIDE_COMPACT=0 / VFA_FSIDE_NO_SKIP=1 are fp32 switches)");
+        return VFA_ERR_UNSUPPORTED;
       } else {
         if (int rc = launch_tile_need(p, fs_ws, nb, &g.need, st, !(variant & 256))) return rc;
         if (int rc = launch_ygemm(g, 0, bf16, st)) return rc;
@@ -1698,10 +2016,12 @@ int launch_fwd_fside(const AggParams& p, const uint8_t* const* wprep, const TapR
       if (quad && tile_bytes != 0) {
         q.tiles_x = (p.W + 2 * QX - 1) / (2 * QX);
         q.seg_off = nullptr;
-        if (int rc = launch_pool_tile(q, list_ws, nb, false, st)) return rc;
+        if (int rc = launch_pool_tile(q, list_ws, nb, p.y_bf16 != 0, st)) return rc;
         tile_pool_overflow_view(p, list_ws, &q.tile_ovf, &q.ptiles_x);
         const dim3 grid(q.tiles_x * ((p.L + 2 * QY - 1) / (2 * QY)), nb);
-        if (p.mask != nullptr)
+        if (p.y_bf16)
+          pool_quad_kernel<false, true, true><<<grid, QWARPS * 32, 0, st>>>(q);      // (forward-only variant: no mask)
+        else if (p.mask != nullptr)
           pool_quad_kernel<true, true><<<grid, QWARPS * 32, 0, st>>>(q);
         else
           pool_quad_kernel<false, true><<<grid, QWARPS * 32, 0, st>>>(q);

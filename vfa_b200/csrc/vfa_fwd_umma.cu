@@ -836,6 +836,7 @@ size_t umma_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh, uint
     p.L = g->grid_l;                    // the quads' texel lists are sized by the grid
     p.W = g->grid_w;
     p.LW = g->grid_l * g->grid_w;
+    p.y_bf16 = (flags & VFA_FLAG_BF16_MMA) ? 1 : 0;
     for (int s = 0; s < sh->n_scales; ++s) {
       p.sc[s].fh = sh->feat_h[s];
       p.sc[s].fw = sh->feat_w[s];
@@ -845,8 +846,12 @@ size_t umma_workspace_bytes(const vfa_geometry_t* g, const vfa_shape_t* sh, uint
   return bytes;
 }
 
-int prep_weights_umma(const AggParams& p, const float* const* d_weight, void* ws, cudaStream_t st) {
+int prep_weights_bf16(const AggParams& p, const float* const* d_weight, void* ws, size_t per_scale, cudaStream_t st);
+
+int prep_weights_umma(const AggParams& p, const float* const* d_weight, void* ws, uint32_t flags, cudaStream_t st) {
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
+  if ((flags & VFA_FLAG_BF16_MMA) && !grid_side_requested(flags))      // bf16 slabs in the same (larger) per-scale slots
+    return prep_weights_bf16(p, d_weight, ws, per_scale, st);
   for (int s = 0; s < p.S; ++s) {
     prep_weight_umma_kernel<<<148 * 4, 256, 0, st>>>(d_weight[s], reinterpret_cast<uint8_t*>(ws) + s * per_scale, p.nl);
     VFA_LAUNCH_CHECK("prep_weight_umma_kernel");
@@ -856,7 +861,7 @@ int prep_weights_umma(const AggParams& p, const float* const* d_weight, void* ws
 
 int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   if (!(flags & VFA_FLAG_WEIGHTS_PREPARED)) {
-    if (int rc = prep_weights_umma(p, d_weight, ws, st)) return rc;
+    if (int rc = prep_weights_umma(p, d_weight, ws, flags, st)) return rc;
   }
   const bool bf16 = (flags & VFA_FLAG_BF16_FEATURES) != 0;
   if (grid_side_requested(flags)) {
@@ -889,7 +894,8 @@ int launch_fwd_umma(AggParams p, const float* const* d_weight, void* ws, size_t 
     if (int rc = launch_fwd_fside(p, a.wprep, a.recs, reinterpret_cast<uint8_t*>(ws) + fixed,
                                   ws_bytes - fixed, flags, a.variant, st))
       return rc;
-    set_path(bf16 ? "fside_tf32x3_bf16feat" : "fside_tf32x3");
+    set_path((flags & VFA_FLAG_BF16_MMA) ? (bf16 ? "fside_bf16mma_bf16feat" : "fside_bf16mma")
+                                         : (bf16 ? "fside_tf32x3_bf16feat" : "fside_tf32x3"));
     return VFA_OK;
   }
   a.tiles_x = (p.W + TILE_W - 1) / TILE_W;

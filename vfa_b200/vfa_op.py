@@ -286,10 +286,11 @@ def aggregate(feats, table: ProjectionTable, weights, biases, flags: int = 0, ch
         cl.append(f if channels_last else to_channels_last(f))
     for t in list(weights) + list(biases):
         _require_cuda(t, 'collapse parameter')
-    if cl[0].dtype == torch.bfloat16:
-        # bf16 feature storage: inference only (the backward kernels read fp32 maps)
+    if cl[0].dtype == torch.bfloat16 or (int(flags) & _lib.FLAG_BF16_MMA):
+        # bf16 feature storage / bf16 tensor-core variant: inference only (the backward kernels are fp32)
         if any(t.requires_grad for t in list(cl) + list(weights) + list(biases)) and torch.is_grad_enabled():
-            raise RuntimeError('bfloat16 feature maps are forward-only; run under torch.no_grad() or pass float32')
+            raise RuntimeError('bfloat16 feature maps / FLAG_BF16_MMA are forward-only; run under torch.no_grad() or use '
+                               'the float32 path')
         return aggregate_forward_raw([t.contiguous() for t in cl], table, [w.detach() for w in weights],
                                      [b.detach() for b in biases], flags)
     # the PREPARED bits describe a caller-owned workspace; the autograd path allocates its own
