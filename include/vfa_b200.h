@@ -169,6 +169,35 @@ int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
                       float* const* d_grad_bias, void* d_workspace, size_t workspace_bytes, uint32_t flags,
                       void* stream);
 
+/* ---- decode tail --------------------------------------------------------------------
+ * The heads' maps -> at most `topk` detections per frame: sigmoid, 5 x 5 max-pool NMS, top-k by confidence, centre / size /
+ * orientation decoded at the selected cells only.  Replaces reference vfa/data/encoder.py:230-273 (decode3d; pass
+ * dim_offset = rotation = NULL for decode2d, :275-305) up to the final `conf > cls_thresh` mask, which the caller applies.
+ * Head tensors are addressed as p[b * stride[0] + c * stride[1] + cell * stride[2]] (elements), cell = y * W + x, so
+ * [B,C,L,W], [B,L,W,C] (the reference's permuted views) and channels-last storage all pass without a copy. */
+typedef struct {
+  int32_t batch, grid_l, grid_w;     /* heatmap is [B, 1, L, W] contiguous fp32 logits                               */
+  int32_t topk;                      /* 1..1024 (reference default 50, train.py:126)                                 */
+  int32_t n_angles;                  /* channels of `rotation` (reference: 360)                                      */
+  const float* heatmap;
+  const float* loc_offset;           /* 2 channels (ty, tx) logits                                                   */
+  int64_t loc_stride[3];
+  const float* dim_offset;           /* 3 channels (th, tw, tl), or NULL                                             */
+  int64_t dim_stride[3];
+  const float* rotation;             /* n_angles channels of logits, or NULL                                         */
+  int64_t rot_stride[3];
+  float grid_size[2], world_size[2]; /* encoder.grid_size, encoder.world_size (reference encoder.py:244-245)         */
+  float dim_mean[3];                 /* classAverage mean (h, w, l) (encoder.py:247-250)                             */
+} vfa_decode_t;
+
+size_t vfa_decode_workspace_bytes(int32_t batch);
+
+/* d_out_vals [B, topk, 7] fp32 = (conf, cy, cx, h, w, l, orientation bin), sorted by conf descending (equal conf: lower
+ * cell first); d_out_cell [B, topk] int32 = cell index y * W + x, or -1 (and conf = 0) where a frame has fewer than topk
+ * NMS survivors. */
+int vfa_decode_topk(const vfa_decode_t* dec, float* d_out_vals, int32_t* d_out_cell, void* d_workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

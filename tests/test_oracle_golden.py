@@ -3,6 +3,7 @@
 Bit-exact items: boxes, area, visible, tap indices.  Floating point: fp64 hybrid features to 1e-11.
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -11,6 +12,8 @@ import torch
 from oracle import ref_port
 from oracle import vfa_oracle as onp
 from vfa_b200 import geometry, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 NAMES = ['MultiviewC', 'MultiviewX', 'Wildtrack']
 SMALL_SIZES = [(45, 80), (30, 52), (23, 40)]
@@ -147,3 +150,23 @@ def test_golden_has_ghosts_and_infinite_projections(golden):
     # principal-plane camera (index 3): h2 == 0 on layer-0 top corners -> boxes pinned at the clamp limits
     b = golden[f'{name}/boxes3'][0]
     assert np.isfinite(b).all() and ((b[:, 2] == np.float32(0.95)) | (b[:, 0] == -1)).any()
+
+
+def test_decode_port_matches_the_unmodified_reference_decode():
+    """oracle/decode_port.py vs the outputs of the reference's own `ObjectEncoder.decode3d` / `decode2d`
+    (tests/golden/make_golden_decode.py -> decode_case.npz): identical detections, bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    from decode_case_inputs import CLS_THRESH, DIM_MEAN, GRID_SIZE, TOPK, WORLD_SIZE, case_pred
+    from oracle import decode_port
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'decode_case.npz'))
+    for seed in (0, 1):
+        pred = case_pred(seed)
+        got = {'3d': decode_port.decode3d(pred, CLS_THRESH, TOPK, GRID_SIZE, WORLD_SIZE, DIM_MEAN),
+               '2d': decode_port.decode2d(pred, CLS_THRESH, TOPK, GRID_SIZE, WORLD_SIZE),
+               '2dw': decode_port.decode2d(pred, CLS_THRESH, TOPK, GRID_SIZE, WORLD_SIZE, wildtrack=True)}
+        for name, d in got.items():
+            for k, v in d.items():
+                want = gold[f's{seed}/{name}/{k}']
+                assert v.shape == want.shape and 0 < want.shape[0] < TOPK, (seed, name, k, want.shape)
+                assert np.array_equal(v.numpy(), want), (seed, name, k)

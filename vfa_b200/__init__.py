@@ -16,5 +16,6 @@ from .vfa_op import (VFA, ProjectionTable, aggregate, aggregate_forward_raw, bui
 from .streaming import StreamingAggregator                          # noqa: F401
 from .graphed import GraphedAggregator                              # noqa: F401
 from .vfanet import MultiScaleVFA                                   # noqa: F401
+from .decode import decode_topk, decode3d, decode2d                 # noqa: F401
 
 __version__ = '0.1.0'

@@ -30,7 +30,7 @@ LIB_PATH = os.environ.get('VFA_B200_LIB') or os.path.join(os.path.dirname(os.pat
 
 EXPORTS = ['vfa_version', 'vfa_last_error', 'vfa_last_path', 'vfa_reload_env', 'vfa_table_build', 'vfa_table_scale',
            'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_workspace_bytes', 'vfa_prepare_weights', 'vfa_aggregate_fwd',
-           'vfa_aggregate_bwd']
+           'vfa_aggregate_bwd', 'vfa_decode_workspace_bytes', 'vfa_decode_topk']
 
 
 class Geometry(C.Structure):
@@ -43,6 +43,14 @@ class Geometry(C.Structure):
 class Shape(C.Structure):
     _fields_ = [('batch', C.c_int32), ('n_views', C.c_int32), ('channels', C.c_int32), ('n_scales', C.c_int32),
                 ('feat_h', C.c_int32 * VFA_MAX_SCALES), ('feat_w', C.c_int32 * VFA_MAX_SCALES)]
+
+
+class Decode(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('grid_l', C.c_int32), ('grid_w', C.c_int32), ('topk', C.c_int32),
+                ('n_angles', C.c_int32), ('heatmap', C.c_void_p), ('loc_offset', C.c_void_p), ('loc_stride', C.c_int64 * 3),
+                ('dim_offset', C.c_void_p), ('dim_stride', C.c_int64 * 3), ('rotation', C.c_void_p),
+                ('rot_stride', C.c_int64 * 3), ('grid_size', C.c_float * 2), ('world_size', C.c_float * 2),
+                ('dim_mean', C.c_float * 3)]
 
 
 class VFAError(RuntimeError):
@@ -79,6 +87,10 @@ def lib():
     L.vfa_aggregate_fwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, PP, fp, vp, vp, sz, u32, vp]
     L.vfa_aggregate_bwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, vp, fp, PP, PP, PP, vp, sz,
                                     u32, vp]
+    L.vfa_decode_workspace_bytes.argtypes = [i32]
+    L.vfa_decode_workspace_bytes.restype = sz
+    L.vfa_decode_topk.argtypes = [C.POINTER(Decode), fp, vp, vp, sz, vp]
+    L.vfa_decode_topk.restype = C.c_int
     for name in ('vfa_prepare_weights', 'vfa_table_build', 'vfa_table_scale', 'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_fwd',
                  'vfa_aggregate_bwd'):
         getattr(L, name).restype = C.c_int

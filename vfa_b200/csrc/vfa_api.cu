@@ -104,6 +104,9 @@ size_t bwd_workspace_bytes(const vfa_geometry_t*, const vfa_shape_t*);
 int launch_bwd(AggParams, const float* const*, const float*, float* const*, float* const*, float* const*, void*, size_t,
                uint32_t, cudaStream_t);
 
+size_t decode_workspace_bytes(int B);
+int launch_decode(const vfa_decode_t* d, float* out_vals, int32_t* out_cell, void* ws, cudaStream_t st);
+
 static int validate_geometry(const vfa_geometry_t* g) {
   VFA_REQUIRE(g != nullptr, VFA_ERR_INVALID_ARGUMENT, "geometry is NULL");
   VFA_REQUIRE(g->n_layers >= 1 && g->n_layers <= VFA_MAX_LAYERS, VFA_ERR_INVALID_ARGUMENT,
@@ -295,6 +298,23 @@ int vfa_prepare_weights(const vfa_geometry_t* geom, const vfa_shape_t* shape, co
   VFA_REQUIRE(workspace_bytes >= need, VFA_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
   return use_umma ? prep_weights_umma(p, d_weight, d_workspace, flags, (cudaStream_t)stream)
                   : prep_weights_simt(p, d_weight, d_workspace, (cudaStream_t)stream);
+}
+
+size_t vfa_decode_workspace_bytes(int32_t batch) { return batch > 0 ? decode_workspace_bytes(batch) : 0; }
+
+int vfa_decode_topk(const vfa_decode_t* dec, float* d_out_vals, int32_t* d_out_cell, void* d_workspace,
+                    size_t workspace_bytes, void* stream) {
+  VFA_REQUIRE(dec != nullptr && d_out_vals != nullptr && d_out_cell != nullptr, VFA_ERR_INVALID_ARGUMENT, "NULL argument");
+  VFA_REQUIRE(dec->batch >= 1 && dec->grid_l >= 1 && dec->grid_w >= 1, VFA_ERR_INVALID_ARGUMENT, "empty heatmap %d x %d x %d",
+              dec->batch, dec->grid_l, dec->grid_w);
+  VFA_REQUIRE(dec->topk >= 1 && dec->topk <= 1024, VFA_ERR_INVALID_ARGUMENT, "topk=%d outside [1, 1024]", dec->topk);
+  VFA_REQUIRE(dec->heatmap != nullptr && dec->loc_offset != nullptr, VFA_ERR_INVALID_ARGUMENT, "heatmap / loc_offset is NULL");
+  VFA_REQUIRE(dec->rotation == nullptr || dec->n_angles >= 1, VFA_ERR_INVALID_ARGUMENT, "n_angles=%d", dec->n_angles);
+  VFA_REQUIRE((long long)dec->grid_l * dec->grid_w < 0x7fffffffll, VFA_ERR_UNSUPPORTED, "grid too large");
+  VFA_REQUIRE(d_workspace != nullptr && workspace_bytes >= decode_workspace_bytes(dec->batch), VFA_ERR_WORKSPACE,
+              "decode workspace %zu < required %zu", workspace_bytes, decode_workspace_bytes(dec->batch));
+  if (int rc = check_device()) return rc;
+  return launch_decode(dec, d_out_vals, d_out_cell, d_workspace, (cudaStream_t)stream);
 }
 
 int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, const float* d_boxes,
