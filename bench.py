@@ -670,7 +670,8 @@ def main():
         S_ = setup(args.workload, B, (sv0, sv1), seed=777)        # this rank's cameras of the same B frames
         try:
             fused = vd.FusedViewAggregator(cgeom, B, C)
-            kind = 'fused multimem.red in pool_tile_kernel (NVSwitch multicast), 1 barrier per step, no NCCL call'
+            kind = ('fused reduce-scatter in pool_tile_kernel (red.add.v4 into the band owner\'s replica over NVLink) + multimem.st '
+                    'all-gather of the bands (vfa_multicast_copy), 2 barriers per step, no NCCL call')
         except Exception as exc:                                  # no multicast support: NCCL all-reduce of the partial maps
             fused, kind = None, f'NCCL all-reduce of partial maps (fused path unavailable: {exc})'
 
@@ -695,9 +696,12 @@ def main():
                   'max_speedup_from_camera_split': V / max(vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0]
                                                            for r in range(world)),
                   'reduced_bytes_per_rank_per_step': map_bytes,
-                  'note': 'each rank pushes its partial [B,L,W,C] map once through its NVLink egress; the switch adds it into '
-                          'every replica while the kernel still pools the next tiles (not separately timeable); step time '
-                          'includes the table + weight prep of the rank\'s cameras and the barrier'}
+                  'nvlink_bytes_per_rank_per_step': {'reduce_scatter_out': map_bytes * (world - 1) // world,
+                                                     'all_gather_in': map_bytes * (world - 1) // world},
+                  'note': 'each rank red.adds (N-1)/N of its partial [B,L,W,C] map into the owners\' bands while the kernel '
+                          'still pools the next tiles (overlapped, not separately timeable), then broadcasts its own band '
+                          '(1/N of the map out, (N-1)/N in); step time includes the table + weight prep of the rank\'s cameras '
+                          'and both barriers'}
         del S_, fused
 
     # ---- BASELINE config 4: batch 64 forward + backward, sharded over the GPUs (64 / N frames per rank; dWeight / dBias

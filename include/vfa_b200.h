@@ -99,6 +99,10 @@ typedef struct {
                                         (cuMulticast / torch symmetric memory): multimem.red.add -- the NVSwitch adds the
                                         tile into every GPU's replica (in-switch all-reduce fused into the kernel)         */
 
+#define VFA_FLAG_OUT_PEERS 4096u      /* as OUT_ACCUMULATE, but d_out points to a vfa_peer_outputs_t in DEVICE memory: the BEV rows
+                                        are split into bands, one per rank, and every finished tile is red.add-ed into the
+                                        replica of the rank that owns its band (peer memory over NVLink): a reduce-scatter
+                                        fused into the pooling kernel.  vfa_multicast_copy then broadcasts each rank's band  */
 #define VFA_FLAG_WS_FORWARD 1024u     /* vfa_aggregate_workspace_bytes only: size for vfa_aggregate_fwd alone (the kernel
                                         family the other flags select: e.g. 90 MB with VFA_FLAG_GRID_SIDE)               */
 #define VFA_FLAG_WS_BACKWARD 2048u    /* vfa_aggregate_workspace_bytes only: size for vfa_aggregate_bwd alone            */
@@ -168,6 +172,19 @@ int vfa_aggregate_bwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
                       const float* d_grad_out, float* const* d_grad_feats, float* const* d_grad_weight,
                       float* const* d_grad_bias, void* d_workspace, size_t workspace_bytes, uint32_t flags,
                       void* stream);
+
+/* Destination table of VFA_FLAG_OUT_PEERS (lives in device memory; all fields 64-bit): BEV row cy belongs to rank
+ * min(cy / band_rows, n_ranks - 1); out[r] is rank r's [B, L, W, C] replica as mapped into THIS device's address space. */
+typedef struct {
+  uint64_t n_ranks;
+  uint64_t band_rows;
+  uint64_t out[16];
+} vfa_peer_outputs_t;
+
+/* d_mc_dst[i] = d_src[i] for n_bytes (a multiple of 16) where d_mc_dst is the MULTICAST address of a symmetric allocation:
+ * multimem.st -- one read of local memory, the NVSwitch writes every GPU's replica (the all-gather half of the fused
+ * all-reduce: each rank broadcasts the band of the BEV map it owns). */
+int vfa_multicast_copy(const void* d_src, void* d_mc_dst, size_t n_bytes, void* stream);
 
 /* ---- decode tail --------------------------------------------------------------------
  * The heads' maps -> at most `topk` detections per frame: sigmoid, 5 x 5 max-pool NMS, top-k by confidence, centre / size /

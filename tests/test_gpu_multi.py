@@ -136,17 +136,18 @@ def _fused_views_worker(rank, world, port, results):
         params = synthetic.collapse_params(g, seed=23)
         ws, bs = [w.to(dev) for w, _ in params], [b.to(dev) for _, b in params]
         v0, v1 = vd.view_bounds(V, world, rank)                          # 3 + 2 cameras
-        agg = vd.FusedViewAggregator(cgeom, B)
+        aggs = [vd.FusedViewAggregator(cgeom, B, mode=m) for m in ('reduce_scatter', 'multicast_red')]
         table_local = vfa_b200.build_table(cgeom, calibs[v0:v1], grid)
         table_all = vfa_b200.build_table(cgeom, calibs, grid)
         ok = True
         for step in range(3):                                            # both buffer slots, and a reuse
             feats = [vfa_b200.to_channels_last(f.to(dev)) for f in synthetic.features(g, batch=B, n_views=V, seed=40 + step)]
             local = [f[:, v0:v1].contiguous() for f in feats]
-            got = agg(local, table_local, ws, bs).clone()
             want = vfa_b200.aggregate_forward_raw(feats, table_all, ws, bs)
-            err = (got - want).abs()
-            ok = ok and bool((err <= 2e-6 + 2e-6 * want.abs()).all())     # the same terms, summed in another order
+            for agg in aggs:
+                got = agg(local, table_local, ws, bs).clone()
+                err = (got - want).abs()
+                ok = ok and bool((err <= 2e-6 + 2e-6 * want.abs()).all())     # the same terms, summed in another order
         results[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -154,8 +155,9 @@ def _fused_views_worker(rank, world, port, results):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 def test_fused_multicast_camera_sharding_two_gpus_matches_single_gpu():
-    """Camera shards reduced inside the pooling kernel through the NVLink multicast address (multimem.red): same map as one
-    GPU aggregating all cameras, on every rank, for three consecutive steps."""
+    """Camera shards reduced inside the pooling kernel over NVLink -- fused reduce-scatter into the owners' bands (red.add on
+    peer memory) + multicast all-gather, and multimem.red on the multicast address: same map as one GPU aggregating all
+    cameras, on every rank, for three consecutive steps."""
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     results = mgr.dict()

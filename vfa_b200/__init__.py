@@ -9,7 +9,7 @@ entry, `MultiScaleVFA` the same as an nn.Module (feats [B,V,C,H,W] per scale, ca
 from . import geometry, synthetic                                    # noqa: F401
 from ._lib import (VFAError, reload_env, FLAG_BF16_MMA, FLAG_FORCE_SIMT, FLAG_FORCE_UMMA,   # noqa: F401
                    FLAG_WEIGHTS_PREPARED, FLAG_BF16_FEATURES, FLAG_GRID_SIDE, FLAG_TABLE_PREPARED, FLAG_OUT_NHWC,
-                   FLAG_OUT_ACCUMULATE, FLAG_OUT_MULTICAST)
+                   FLAG_OUT_ACCUMULATE, FLAG_OUT_MULTICAST, FLAG_OUT_PEERS)
 from .vfa_op import (VFA, ProjectionTable, aggregate, aggregate_forward_raw, build_table, last_kernel_path,  # noqa: F401
                      make_geometry, make_shape, prepare_weights, to_channels_last, workspace_for)
 

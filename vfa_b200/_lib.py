@@ -22,6 +22,7 @@ FLAG_OUT_NHWC = 128
 FLAG_OUT_ACCUMULATE = 256
 FLAG_OUT_MULTICAST = 512
 FLAG_WS_FORWARD = 1024
+FLAG_OUT_PEERS = 4096
 FLAG_WS_BACKWARD = 2048
 
 # VFA_B200_LIB: another build of the same library (A/B timing of compile-time kernel variants, scripts/build_variant.sh)
@@ -30,7 +31,7 @@ LIB_PATH = os.environ.get('VFA_B200_LIB') or os.path.join(os.path.dirname(os.pat
 
 EXPORTS = ['vfa_version', 'vfa_last_error', 'vfa_last_path', 'vfa_reload_env', 'vfa_table_build', 'vfa_table_scale',
            'vfa_nchw_to_nhwc', 'vfa_nhwc_to_nchw', 'vfa_aggregate_workspace_bytes', 'vfa_prepare_weights', 'vfa_aggregate_fwd',
-           'vfa_aggregate_bwd', 'vfa_decode_workspace_bytes', 'vfa_decode_topk']
+           'vfa_aggregate_bwd', 'vfa_decode_workspace_bytes', 'vfa_decode_topk', 'vfa_multicast_copy']
 
 
 class Geometry(C.Structure):
@@ -87,6 +88,8 @@ def lib():
     L.vfa_aggregate_fwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, PP, fp, vp, vp, sz, u32, vp]
     L.vfa_aggregate_bwd.argtypes = [C.POINTER(Geometry), C.POINTER(Shape), fp, PP, PP, vp, fp, PP, PP, PP, vp, sz,
                                     u32, vp]
+    L.vfa_multicast_copy.argtypes = [vp, vp, sz, vp]
+    L.vfa_multicast_copy.restype = C.c_int
     L.vfa_decode_workspace_bytes.argtypes = [i32]
     L.vfa_decode_workspace_bytes.restype = sz
     L.vfa_decode_topk.argtypes = [C.POINTER(Decode), fp, vp, vp, sz, vp]

@@ -105,6 +105,7 @@ int launch_bwd(AggParams, const float* const*, const float*, float* const*, floa
                uint32_t, cudaStream_t);
 
 size_t decode_workspace_bytes(int B);
+int launch_multicast_copy(const void* src, void* mc_dst, size_t n_bytes, cudaStream_t st);
 int launch_decode(const vfa_decode_t* d, float* out_vals, int32_t* out_cell, void* ws, cudaStream_t st);
 
 static int validate_geometry(const vfa_geometry_t* g) {
@@ -260,8 +261,8 @@ int vfa_aggregate_fwd(const vfa_geometry_t* geom, const vfa_shape_t* shape, cons
               "bf16 feature maps are supported by the tcgen05 forward (C = 256) only, without the backward mask");
   VFA_REQUIRE(!(flags & VFA_FLAG_OUT_NHWC) || (use_umma && !(flags & VFA_FLAG_GRID_SIDE)), VFA_ERR_UNSUPPORTED,
               "VFA_FLAG_OUT_NHWC is implemented by the feature-side forward (C = 256, without VFA_FLAG_GRID_SIDE) only");
-  VFA_REQUIRE(!(flags & (VFA_FLAG_OUT_ACCUMULATE | VFA_FLAG_OUT_MULTICAST)) || (flags & VFA_FLAG_OUT_NHWC),
-              VFA_ERR_UNSUPPORTED, "VFA_FLAG_OUT_ACCUMULATE / _MULTICAST need VFA_FLAG_OUT_NHWC (16-byte channel vectors)");
+  VFA_REQUIRE(!(flags & (VFA_FLAG_OUT_ACCUMULATE | VFA_FLAG_OUT_MULTICAST | VFA_FLAG_OUT_PEERS)) || (flags & VFA_FLAG_OUT_NHWC),
+              VFA_ERR_UNSUPPORTED, "VFA_FLAG_OUT_ACCUMULATE / _MULTICAST / _PEERS need VFA_FLAG_OUT_NHWC (16-byte channel vectors)");
   VFA_REQUIRE(!(flags & VFA_FLAG_BF16_MMA) || (use_umma && !(flags & VFA_FLAG_GRID_SIDE) && d_relu_mask == nullptr),
               VFA_ERR_UNSUPPORTED, "VFA_FLAG_BF16_MMA is a forward-only variant of the feature-side path (C = 256, without "
               "VFA_FLAG_GRID_SIDE, no ReLU mask)");
@@ -298,6 +299,15 @@ int vfa_prepare_weights(const vfa_geometry_t* geom, const vfa_shape_t* shape, co
   VFA_REQUIRE(workspace_bytes >= need, VFA_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
   return use_umma ? prep_weights_umma(p, d_weight, d_workspace, flags, (cudaStream_t)stream)
                   : prep_weights_simt(p, d_weight, d_workspace, (cudaStream_t)stream);
+}
+
+int vfa_multicast_copy(const void* d_src, void* d_mc_dst, size_t n_bytes, void* stream) {
+  VFA_REQUIRE(d_src != nullptr && d_mc_dst != nullptr, VFA_ERR_INVALID_ARGUMENT, "NULL pointer");
+  VFA_REQUIRE((n_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(d_src) | reinterpret_cast<uintptr_t>(d_mc_dst)) & 15) == 0,
+              VFA_ERR_INVALID_ARGUMENT, "multicast copy needs 16-byte aligned pointers and size");
+  if (n_bytes == 0) return VFA_OK;
+  if (int rc = check_device()) return rc;
+  return launch_multicast_copy(d_src, d_mc_dst, n_bytes, (cudaStream_t)stream);
 }
 
 size_t vfa_decode_workspace_bytes(int32_t batch) { return batch > 0 ? decode_workspace_bytes(batch) : 0; }

@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_QUAD_MINBLOCKS) pool_quad_ker
     const float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
     const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
     if (a.out_nhwc) {          // 512 contiguous bytes per warp store
-      float* o = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
+      float* o = (a.out_mode == 3 ? owner_base(p.out, cy) : p.out) + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
       if (a.out_mode == 0) {
         *reinterpret_cast<float4*>(o) = o0;
         *reinterpret_cast<float4*>(o + CH / 2) = o1;
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(QWARPS * 32, VFA_LIST_MINBLOCKS) pool_list_ker
     const float4 o0 = *reinterpret_cast<const float4*>(outw + c * CH);
     const float4 o1 = *reinterpret_cast<const float4*>(outw + c * CH + 4);
     if (a.out_nhwc) {          // 512 contiguous bytes per warp store
-      float* o = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
+      float* o = (a.out_mode == 3 ? owner_base(p.out, cy) : p.out) + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
       if (a.out_mode == 0) {
         *reinterpret_cast<float4*>(o) = o0;
         *reinterpret_cast<float4*>(o + CH / 2) = o1;
@@ -1973,7 +1973,7 @@ int launch_fwd_fside(const AggParams& p_in, const uint8_t* const* wprep, const T
     YGemmArgs g;
     PoolArgs q = {};
     q.out_nhwc = (flags & VFA_FLAG_OUT_NHWC) ? 1 : 0;
-    q.out_mode = (flags & VFA_FLAG_OUT_MULTICAST) ? 2 : ((flags & VFA_FLAG_OUT_ACCUMULATE) ? 1 : 0);
+    q.out_mode = (flags & VFA_FLAG_OUT_PEERS) ? 3 : ((flags & VFA_FLAG_OUT_MULTICAST) ? 2 : ((flags & VFA_FLAG_OUT_ACCUMULATE) ? 1 : 0));
     q.p = p;
     q.recs = recs;
     q.b0 = b0;

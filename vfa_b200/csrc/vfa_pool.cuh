@@ -34,8 +34,18 @@ struct PoolArgs {
   int ptiles_x;
   int out_nhwc;              // 0: out [B, C, L, W]; 1: out [B, L, W, C]
   int out_mode;              // 0: store; 1: red.add into `out` (own, or a peer GPU's memory over NVLink); 2: multimem.red.add
-                             // on a multicast address (the NVSwitch adds into every GPU's replica).  1 / 2: [B, L, W, C] only
+                             // on a multicast address (every GPU's replica receives the add); 3: red.add into the replica of the
+                             // rank that OWNS the cell's band of BEV rows (p.out = vfa_peer_outputs_t in device memory).
+                             // 1 - 3: [B, L, W, C] only
 };
+
+// mode 3: base pointer of the replica that owns BEV row `cy` (bands of `band_rows` rows, the last rank takes the rest)
+__device__ __forceinline__ float* owner_base(const float* desc_ptr, int cy) {
+  const unsigned long long* d = reinterpret_cast<const unsigned long long*>(desc_ptr);
+  const int n = (int)__ldg(d), band = (int)__ldg(d + 1);
+  const int owner = min(cy / band, n - 1);
+  return reinterpret_cast<float*>(__ldg(d + 2 + owner));
+}
 constexpr uint32_t LIST_OVERFLOW = 0xffffffffu;
 
 __device__ __forceinline__ void fma8(float (&acc)[8], float w, const float4& a, const float4& b) {
@@ -69,7 +79,7 @@ __device__ __forceinline__ void store_mask_words(uint32_t* words, size_t word_st
 }
 
 // 16-byte reduction into global memory: plain (mode 1) or through the NVLink multicast object (mode 2)
-__device__ __forceinline__ void red_add_v4(float* dst, const float4& v, int mode) {
+__device__ __forceinline__ void red_add_v4(float* dst, const float4& v, int mode) {      // mode 1 / 3: plain red
   if (mode == 2)
     asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)

@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
           const int cy = ty0 + cy0 + (c >> 1), cx = tx0 + cx0 + (c & 1);
           if (cy >= p.L || cx >= p.W) continue;
           const float* o = out_s + (q * 4 + c) * CH + ((lane ^ cell_key(q, c)) << 2);
-          float* g = p.out + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
+          float* g = (a.q.out_mode == 3 ? fside::owner_base(p.out, cy) : p.out) + ((size_t)b * p.LW + cy * p.W + cx) * CH + lane * 4;
           const float4 o0 = *reinterpret_cast<const float4*>(o), o1 = *reinterpret_cast<const float4*>(o + CH / 2);
           if (a.q.out_mode == 0) {
             *reinterpret_cast<float4*>(g) = o0;
@@ -829,6 +829,24 @@ int launch_pool_tile(fside::PoolArgs q, void* ws, int nb, bool y_bf16, cudaStrea
   }
 #undef VFA_LAUNCH_POOL_TILE
   VFA_LAUNCH_CHECK("pool_tile_kernel");
+  return VFA_OK;
+}
+
+// ---- multicast copy (all-gather half of the fused all-reduce) ---------------------------------------------------------
+__global__ void __launch_bounds__(256) multicast_copy_kernel(const float4* __restrict__ src, float* mc_dst, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + 4 * i), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+}
+
+int launch_multicast_copy(const void* src, void* mc_dst, size_t n_bytes, cudaStream_t st) {
+  const size_t n16 = n_bytes / 16;
+  const int blocks = (int)((n16 + 255) / 256 < 148 * 8 ? (n16 + 255) / 256 : 148 * 8);
+  multicast_copy_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float*>(mc_dst), n16);
+  VFA_LAUNCH_CHECK("multicast_copy_kernel");
   return VFA_OK;
 }
 

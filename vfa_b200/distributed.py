@@ -192,31 +192,49 @@ class FusedViewAggregator:
     """Camera-sharded aggregation with the cross-GPU sum fused INTO the pooling kernel (inference / latency mode).
 
     Rank g owns cameras [v0, v1) (`view_bounds`).  Its pooling kernel does not store the partial BEV map: every finished
-    8 x 8-cell tile is added straight into a symmetric [B, L, W, C] buffer through the NVLink multicast address
-    (`multimem.red.add.v4.f32`, VFA_FLAG_OUT_MULTICAST) -- the NVSwitch performs the reduction and writes the sum into every
-    GPU's replica while the SMs are still pooling the next tiles.  No NCCL call, no separate all-reduce pass, no partial map
-    in HBM: the collective costs one cross-rank barrier per step.  (Sum over cameras: reference vfanet.py:82; every term is
-    already past its ReLU, so partial sums of camera subsets add exactly, up to fp32 summation order.)
+    8 x 8-cell tile goes straight over NVLink into a symmetric [B, L, W, C] buffer (torch symmetric memory), while the SMs
+    are still pooling the next tiles.  No NCCL call, no partial map in HBM.  (Sum over cameras: reference vfanet.py:82;
+    every term is already past its ReLU, so partial sums of camera subsets add exactly, up to fp32 summation order.)
 
-    Two buffer slots alternate: the slot of step i + 1 is zeroed before the barrier that ends step i, so one barrier per
-    step orders both "all adds of step i have landed" and "every replica of the next slot is zero".
+    mode='reduce_scatter' (default): the BEV rows are split into one band per rank; a tile is `red.add`-ed into the replica
+      of the rank that OWNS its band (VFA_FLAG_OUT_PEERS: peer memory, 16-byte vector reductions) -- a reduce-scatter fused
+      into the kernel, (N-1)/N of the map per rank in each direction.  After a barrier each rank broadcasts its finished
+      band to every replica with `multimem.st` (vfa_multicast_copy; the NVSwitch replicates the stores): the all-gather
+      half, map/N out and one map in per rank.  Two barriers per step.
+    mode='multicast_red': `multimem.red.add` of every tile on the multicast address (VFA_FLAG_OUT_MULTICAST) -- one barrier,
+      but every replica receives all N partial maps (N x the ingress): fine for 2 ranks, link-bound beyond.
 
-    Needs torch symmetric memory with multicast support (NVSwitch); `available()` tells.  Results come back as a
+    Two buffer slots alternate; the slot of step i + 1 is zeroed before the (first) barrier of step i, so no extra barrier
+    orders "every accumulator is zero".  Needs NVSwitch multicast support (`multicast_ptr`).  Results come back as a
     [B, C, L, W] view with channels-last strides of the local replica (valid until the slot is reused two steps later).
     """
 
-    def __init__(self, geom, batch: int, channels: int = 256, group=None, flags: int = 0):
+    def __init__(self, geom, batch: int, channels: int = 256, group=None, flags: int = 0, mode: str = 'reduce_scatter'):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
+        if mode not in ('reduce_scatter', 'multicast_red'):
+            raise ValueError(f'unknown mode {mode!r}')
         self.group = group if group is not None else dist.group.WORLD
-        self.geom, self.B, self.C = geom, int(batch), int(channels)
-        self.flags = int(flags) | _lib.FLAG_OUT_NHWC | _lib.FLAG_OUT_MULTICAST
+        self.geom, self.B, self.C, self.mode = geom, int(batch), int(channels), mode
+        self.flags = int(flags) | _lib.FLAG_OUT_NHWC | (_lib.FLAG_OUT_PEERS if mode == 'reduce_scatter'
+                                                        else _lib.FLAG_OUT_MULTICAST)
         dev = torch.device('cuda', torch.cuda.current_device())
-        self.buf = symm_mem.empty(2, self.B, geom.grid_l, geom.grid_w, self.C, dtype=torch.float32, device=dev)
+        L, W = geom.grid_l, geom.grid_w
+        self.buf = symm_mem.empty(2, self.B, L, W, self.C, dtype=torch.float32, device=dev)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         if not self.hdl.multicast_ptr:
             raise RuntimeError('symmetric memory has no multicast address on this system (no NVSwitch multicast support)')
         self.slot_bytes = self.buf[0].numel() * 4
+        n, rank = self.hdl.world_size, self.hdl.rank
+        if n > 16:
+            raise ValueError('vfa_peer_outputs_t holds up to 16 ranks')
+        # bands of whole 8-row tiles: rank r owns BEV rows [r0, r1)
+        band = -(-(-(-L // 8)) // n) * 8
+        self.band_rows = band
+        self.r0 = min(rank * band, L)
+        self.r1 = L if rank == n - 1 else min((rank + 1) * band, L)
+        self.desc = [torch.tensor([n, band] + [int(p_) + s * self.slot_bytes for p_ in self.hdl.buffer_ptrs]
+                                  + [0] * (16 - n), dtype=torch.int64, device=dev) for s in range(2)]
         self.buf.zero_()
         self.hdl.barrier(channel=0)
         self._step = 0
@@ -233,15 +251,30 @@ class FusedViewAggregator:
     def __call__(self, feats_local_cl, table_local, weights, biases):
         """feats_local_cl: S channels-last tensors [B, V_g, fH, fW, C] of this rank's cameras (V_g may be 0);
         table_local: ProjectionTable of the same cameras (None when V_g == 0).  Collective: every rank calls it."""
-        from . import vfa_op
+        import ctypes as C
+        from . import _lib, vfa_op
         s = self._step & 1
-        self.buf[1 - s].zero_()                                  # the other slot: next step's accumulator
+        rs = self.mode == 'reduce_scatter'
+        if rs:
+            self.buf[1 - s][:, self.r0:self.r1].zero_()          # next step's accumulator: the band this rank owns
+        else:
+            self.buf[1 - s].zero_()
         if table_local is not None and feats_local_cl[0].shape[1] > 0:
             if self.workspace is None:
                 shape = vfa_op.make_shape(feats_local_cl, self.geom.n_layers)
                 self.workspace = vfa_op.workspace_for(table_local.geom, shape, self.flags, feats_local_cl[0].device)
+            dst = self.desc[s].data_ptr() if rs else self.hdl.multicast_ptr + s * self.slot_bytes
             vfa_op.aggregate_forward_raw(feats_local_cl, table_local, weights, biases, self.flags, workspace=self.workspace,
-                                         out_ptr=self.hdl.multicast_ptr + s * self.slot_bytes)
-        self.hdl.barrier(channel=0)
+                                         out_ptr=dst)
+        self.hdl.barrier(channel=0)                              # every partial tile has landed in its owner's band
+        if rs:
+            if self.r1 > self.r0:
+                row_bytes = self.geom.grid_w * self.C * 4
+                stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                for b in range(self.B):
+                    off = s * self.slot_bytes + (b * self.geom.grid_l + self.r0) * row_bytes
+                    _lib.check(_lib.lib().vfa_multicast_copy(self.buf.data_ptr() + off, self.hdl.multicast_ptr + off,
+                                                             (self.r1 - self.r0) * row_bytes, stream))
+            self.hdl.barrier(channel=0)                          # every band has been broadcast
         self._step += 1
         return self.buf[s].permute(0, 3, 1, 2)
