@@ -671,7 +671,10 @@ def main():
         try:
             fused = vd.FusedViewAggregator(cgeom, B, C)
             kind = ('fused reduce-scatter in pool_tile_kernel (red.add.v4 into the band owner\'s replica over NVLink) + multimem.st '
-                    'all-gather of the bands (vfa_multicast_copy), 2 barriers per step, no NCCL call')
+                    'all-gather of the bands (vfa_multicast_copy), 2 barriers per step, no NCCL call'
+                    if fused.mode == 'reduce_scatter' else
+                    'fused multimem.red.add in pool_tile_kernel on the NVLink multicast address (every replica receives every '
+                    'partial tile), 1 barrier per step, no NCCL call')
         except Exception as exc:                                  # no multicast support: NCCL all-reduce of the partial maps
             fused, kind = None, f'NCCL all-reduce of partial maps (fused path unavailable: {exc})'
 
@@ -689,15 +692,18 @@ def main():
         ms = time_steps(strong_step, args.steps, barrier, dev, world) / args.steps
         one_gpu_ms = total_ms / args.steps                        # the dp step above: B frames, all V cameras, one GPU
         map_bytes = B * C * grid.shape[0] * grid.shape[1] * 4
-        strong = {'mode': 'views (camera sharding)', 'collective': kind, 'frames_per_step': B, 'n_gpus': world,
+        strong_kind_mode = None if fused is None else fused.mode
+        strong = {'mode': 'views (camera sharding)', 'collective': kind, 'collective_mode': strong_kind_mode, 'frames_per_step': B, 'n_gpus': world,
                   'cameras_per_rank': [vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0] for r in range(world)],
                   'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'one_gpu_ms_per_step': one_gpu_ms,
                   'speedup': one_gpu_ms / ms, 'efficiency': one_gpu_ms / ms / world,
                   'max_speedup_from_camera_split': V / max(vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0]
                                                            for r in range(world)),
                   'reduced_bytes_per_rank_per_step': map_bytes,
-                  'nvlink_bytes_per_rank_per_step': {'reduce_scatter_out': map_bytes * (world - 1) // world,
-                                                     'all_gather_in': map_bytes * (world - 1) // world},
+                  'nvlink_bytes_per_rank_per_step': ({'reduce_scatter_out': map_bytes * (world - 1) // world,
+                                                      'all_gather_in': map_bytes * (world - 1) // world}
+                                                     if fused is not None and fused.mode == 'reduce_scatter' else
+                                                     {'multicast_red_out': map_bytes, 'in': map_bytes * (world - 1)}),
                   'note': 'each rank red.adds (N-1)/N of its partial [B,L,W,C] map into the owners\' bands while the kernel '
                           'still pools the next tiles (overlapped, not separately timeable), then broadcasts its own band '
                           '(1/N of the map out, (N-1)/N in); step time includes the table + weight prep of the rank\'s cameras '

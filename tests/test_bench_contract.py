@@ -60,6 +60,8 @@ def test_our_arm_line():
     assert [c['workload'].split('-')[0] for c in d['configs']] == ['MultiviewX', 'Wildtrack']
     assert all(c['value'] > 0 and c['batch'] == 1 for c in d['configs'])
     assert d['config4']['frames_per_rank'] == 64 and d['config4']['value'] > 0 and d['strong'] is None
+    v = d['variants']
+    assert v['static_cameras']['value'] > d['value'] and v['bf16_mma']['kernel_path'] == 'fside_bf16mma' and v['bf16_mma']['tolerance']
     assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['value'] > 0 and cb['cores'] >= 1

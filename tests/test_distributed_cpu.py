@@ -148,3 +148,23 @@ def test_camera_sharding_without_a_process_group_is_the_plain_call():
     compute = _port_compute('MultiviewC')
     got = vd.aggregate_views(feats, calibs, grid, [w.double()], [b.double()], compute, out_channels=4, frames_per_chunk=2)
     assert torch.equal(got, compute(feats, calibs, grid, [w.double()], [b.double()]))
+
+
+def test_row_bands_partition_the_grid_like_the_kernel_routes_rows():
+    """FusedViewAggregator's reduce-scatter: every BEV row has exactly one owner, bands are whole 8-row tiles, and the
+    owner the pooling kernel computes (min(cy // band_rows, world - 1), csrc/vfa_pool.cuh owner_base) is the rank whose
+    [r0, r1) holds the row -- for grids that do and do not divide evenly, and for more ranks than tile rows."""
+    from vfa_b200.distributed import row_band
+    for L in (156, 160, 120, 39, 7, 8, 9):
+        for world in (1, 2, 3, 4, 8, 16):
+            bands = [row_band(L, world, r) for r in range(world)]
+            band = bands[0][2]
+            assert band % 8 == 0 and all(b[2] == band for b in bands)
+            owner = [-1] * L
+            for r, (r0, r1, _) in enumerate(bands):
+                assert 0 <= r0 <= r1 <= L
+                for cy in range(r0, r1):
+                    assert owner[cy] == -1
+                    owner[cy] = r
+            assert all(o >= 0 for o in owner)
+            assert owner == [min(cy // band, world - 1) for cy in range(L)]

@@ -118,6 +118,16 @@ class _SumOverRanks(torch.autograd.Function):
         return g, None, None
 
 
+def row_band(n_rows: int, world: int, rank: int, tile: int = 8):
+    """BEV rows [r0, r1) whose reduction rank `rank` owns in the fused reduce-scatter (FusedViewAggregator): bands of whole
+    `tile`-row tiles of equal height, the last rank takes what is left (possibly nothing).  Returns (r0, r1, band_rows);
+    the kernel routes row cy to rank min(cy // band_rows, world - 1)."""
+    band = -(-(-(-n_rows // tile)) // world) * tile
+    r0 = min(rank * band, n_rows)
+    r1 = n_rows if rank == world - 1 else min((rank + 1) * band, n_rows)
+    return r0, r1, band
+
+
 def view_bounds(n_views: int, world: int, rank: int):
     """Cameras [v0, v1) of rank `rank` (even split; with more ranks than cameras the last ranks hold none)."""
     return slab_bounds(n_views, world, rank)
@@ -196,7 +206,8 @@ class FusedViewAggregator:
     are still pooling the next tiles.  No NCCL call, no partial map in HBM.  (Sum over cameras: reference vfanet.py:82;
     every term is already past its ReLU, so partial sums of camera subsets add exactly, up to fp32 summation order.)
 
-    mode='reduce_scatter' (default): the BEV rows are split into one band per rank; a tile is `red.add`-ed into the replica
+    mode='auto' (default): 'multicast_red' up to 4 ranks, 'reduce_scatter' beyond.
+    mode='reduce_scatter': the BEV rows are split into one band per rank; a tile is `red.add`-ed into the replica
       of the rank that OWNS its band (VFA_FLAG_OUT_PEERS: peer memory, 16-byte vector reductions) -- a reduce-scatter fused
       into the kernel, (N-1)/N of the map per rank in each direction.  After a barrier each rank broadcasts its finished
       band to every replica with `multimem.st` (vfa_multicast_copy; the NVSwitch replicates the stores): the all-gather
@@ -209,12 +220,17 @@ class FusedViewAggregator:
     [B, C, L, W] view with channels-last strides of the local replica (valid until the slot is reused two steps later).
     """
 
-    def __init__(self, geom, batch: int, channels: int = 256, group=None, flags: int = 0, mode: str = 'reduce_scatter'):
+    def __init__(self, geom, batch: int, channels: int = 256, group=None, flags: int = 0, mode: str = 'auto'):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
-        if mode not in ('reduce_scatter', 'multicast_red'):
+        if mode not in ('auto', 'reduce_scatter', 'multicast_red'):
             raise ValueError(f'unknown mode {mode!r}')
         self.group = group if group is not None else dist.group.WORLD
+        if mode == 'auto':
+            # multicast_red costs every replica N maps of NVLink ingress, hidden behind the pooling while N x map / 750 GB/s
+            # stays below the rank's compute time: measured (MultiviewC, B = 4) +0.03 / +0.11 ms at 2 / 4 ranks against
+            # +0.2 ms for the reduce-scatter's second phase; at 8 ranks the ingress (800 MB) is exposed
+            mode = 'multicast_red' if dist.get_world_size(self.group) <= 4 else 'reduce_scatter'
         self.geom, self.B, self.C, self.mode = geom, int(batch), int(channels), mode
         self.flags = int(flags) | _lib.FLAG_OUT_NHWC | (_lib.FLAG_OUT_PEERS if mode == 'reduce_scatter'
                                                         else _lib.FLAG_OUT_MULTICAST)
@@ -229,10 +245,8 @@ class FusedViewAggregator:
         if n > 16:
             raise ValueError('vfa_peer_outputs_t holds up to 16 ranks')
         # bands of whole 8-row tiles: rank r owns BEV rows [r0, r1)
-        band = -(-(-(-L // 8)) // n) * 8
+        self.r0, self.r1, band = row_band(L, n, rank)
         self.band_rows = band
-        self.r0 = min(rank * band, L)
-        self.r1 = L if rank == n - 1 else min((rank + 1) * band, L)
         self.desc = [torch.tensor([n, band] + [int(p_) + s * self.slot_bytes for p_ in self.hdl.buffer_ptrs]
                                   + [0] * (16 - n), dtype=torch.int64, device=dev) for s in range(2)]
         self.buf.zero_()

@@ -309,6 +309,11 @@ class VFA(nn.Module):
     Same constructor arguments, same buffers (`z_corners` int64 [nl,1,1,3], `corners_offset` fp32 [1,1,1,1,8,3]) and
     parameters (`collapse.weight` [C, C*nl], `collapse.bias` [C]); `args` is any object with `.data` in
     {'MultiviewC','MultiviewX','Wildtrack'} and `.image_size = (H, W)`.
+
+    Smallest input: with the default `crange = (-1, 0.95)` every feature map needs MORE THAN 20 texels along each axis
+    (the reference's 720 x 1280 configs give 23 x 40 at stride 32); smaller maps or a `crange[1]` nearer 1 raise
+    `VFAError` (UNSUPPORTED) -- there the reference samples its integral image outside the map and reads zero padding,
+    which the direct pooling form does not reproduce.
     """
 
     def __init__(self, channel, grid_height=160, cube_size=(25, 25, 32), feat_scale=1, args=None):
