@@ -598,148 +598,160 @@ def main():
     # ---- two more lines of the same workload (same run, same inputs): static cameras, and the bf16 tensor-core variant ----
     extra = None
     if path.startswith('fside') and plain and not args.no_variants and args.features == 'f32':
-        extra = {}
-        table_s = vfa_b200.build_table(cgeom, calibs, grid)
-        vfa_b200.prepare_weights(cgeom, shape, weights, args.flags, workspace=ws)
-        vfa_b200.aggregate_forward_raw(feats_cl, table_s, weights, biases, args.flags, out=out, workspace=ws, prepared=True)
+        try:
+            extra = {}
+            table_s = vfa_b200.build_table(cgeom, calibs, grid)
+            vfa_b200.prepare_weights(cgeom, shape, weights, args.flags, workspace=ws)
+            vfa_b200.aggregate_forward_raw(feats_cl, table_s, weights, biases, args.flags, out=out, workspace=ws, prepared=True)
 
-        def static_step():          # cameras and weights fixed (inference on a fixed rig): everything derived from them is reused
-            vfa_b200.aggregate_forward_raw(feats_cl, table_s, weights, biases, args.flags, out=out, workspace=ws,
-                                           prepared=True, table_prepared=True)
-        for _ in range(3):
-            static_step()
-        ms = time_steps(static_step, args.steps, barrier, dev, world) / args.steps
-        extra['static_cameras'] = {
-            'value': world * B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'dtype': 'f32',
-            'note': 'VFA_FLAG_TABLE_PREPARED | VFA_FLAG_WEIGHTS_PREPARED: projection table, tap records, coverage, pooling lists '
-                    'and the weight re-layout of the previous call reused (the reference recomputes its boxes every forward, '
-                    'vfa_op.py:64-88, although calibrations are per-dataset constants); the headline `value` rebuilds all of it '
-                    'every step'}
-        bflags = args.flags | vfa_b200.FLAG_BF16_MMA
-        ws_b = vfa_b200.workspace_for(cgeom, shape, bflags, dev)
+            def static_step():          # cameras and weights fixed (inference on a fixed rig): everything derived from them is reused
+                vfa_b200.aggregate_forward_raw(feats_cl, table_s, weights, biases, args.flags, out=out, workspace=ws,
+                                               prepared=True, table_prepared=True)
+            for _ in range(3):
+                static_step()
+            ms = time_steps(static_step, args.steps, barrier, dev, world) / args.steps
+            extra['static_cameras'] = {
+                'value': world * B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'dtype': 'f32',
+                'note': 'VFA_FLAG_TABLE_PREPARED | VFA_FLAG_WEIGHTS_PREPARED: projection table, tap records, coverage, pooling lists '
+                        'and the weight re-layout of the previous call reused (the reference recomputes its boxes every forward, '
+                        'vfa_op.py:64-88, although calibrations are per-dataset constants); the headline `value` rebuilds all of it '
+                        'every step'}
+            bflags = args.flags | vfa_b200.FLAG_BF16_MMA
+            ws_b = vfa_b200.workspace_for(cgeom, shape, bflags, dev)
 
-        def bf16_step():
-            tb = vfa_b200.build_table(cgeom, calibs, grid)
-            vfa_b200.prepare_weights(cgeom, shape, weights, bflags, workspace=ws_b)
-            vfa_b200.aggregate_forward_raw(feats_cl, tb, weights, biases, bflags, out=out, workspace=ws_b, prepared=True)
-        for _ in range(3):
-            bf16_step()
-        ms = time_steps(bf16_step, args.steps, barrier, dev, world) / args.steps
-        extra['bf16_mma'] = {
-            'value': world * B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'kernel_path': vfa_b200.last_kernel_path(),
-            'dtype': 'bf16 (one tcgen05 kind::f16 pass, fp32 accumulate; Y stored in bf16; pooling and sums in fp32)',
-            'tolerance': 'max |err| <= 4e-3, mean <= 5e-4 of max|out| vs the float64 port (measured 1.6e-3 / 2e-4): '
-                         'tests/test_gpu_frame_parity.py::test_bf16_mma_variant',
-            'table': 'rebuilt every step'}
-        del ws_b
-        step()                       # leave `out` / the workspace as the fp32 step left them
+            def bf16_step():
+                tb = vfa_b200.build_table(cgeom, calibs, grid)
+                vfa_b200.prepare_weights(cgeom, shape, weights, bflags, workspace=ws_b)
+                vfa_b200.aggregate_forward_raw(feats_cl, tb, weights, biases, bflags, out=out, workspace=ws_b, prepared=True)
+            for _ in range(3):
+                bf16_step()
+            ms = time_steps(bf16_step, args.steps, barrier, dev, world) / args.steps
+            extra['bf16_mma'] = {
+                'value': world * B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'kernel_path': vfa_b200.last_kernel_path(),
+                'dtype': 'bf16 (one tcgen05 kind::f16 pass, fp32 accumulate; Y stored in bf16; pooling and sums in fp32)',
+                'tolerance': 'max |err| <= 4e-3, mean <= 5e-4 of max|out| vs the float64 port (measured 1.6e-3 / 2e-4): '
+                             'tests/test_gpu_frame_parity.py::test_bf16_mma_variant',
+                'table': 'rebuilt every step'}
+            del ws_b
+            step()                       # leave `out` / the workspace as the fp32 step left them
+        except Exception as exc:      # an optional block must never cost the headline line
+            extra = {'error': f'{type(exc).__name__}: {exc}'}
 
     # ---- BASELINE configs 2-3: MultiviewX / Wildtrack, one frame, one GPU (same run; N = 1 only) ----
     configs = None
     if plain and world == 1 and args.workload == 'MultiviewC' and not args.no_configs:
-        configs = []
-        for wl in ('MultiviewX', 'Wildtrack'):
-            Q = setup(wl, 1, seed=4321)
-            q_shape = vfa_b200.make_shape(Q['feats'], Q['cgeom'].n_layers)
-            q_ws = vfa_b200.workspace_for(Q['cgeom'], q_shape, args.flags, dev)
-            q_out = torch.empty(1, C, Q['grid'].shape[0], Q['grid'].shape[1], device=dev)
+        try:
+            configs = []
+            for wl in ('MultiviewX', 'Wildtrack'):
+                Q = setup(wl, 1, seed=4321)
+                q_shape = vfa_b200.make_shape(Q['feats'], Q['cgeom'].n_layers)
+                q_ws = vfa_b200.workspace_for(Q['cgeom'], q_shape, args.flags, dev)
+                q_out = torch.empty(1, C, Q['grid'].shape[0], Q['grid'].shape[1], device=dev)
 
-            def q_step():
-                tb = vfa_b200.build_table(Q['cgeom'], Q['calibs'], Q['grid'])
-                vfa_b200.prepare_weights(Q['cgeom'], q_shape, Q['ws'], args.flags, workspace=q_ws)
-                vfa_b200.aggregate_forward_raw(Q['feats'], tb, Q['ws'], Q['bs'], args.flags, out=q_out, workspace=q_ws,
-                                               prepared=True)
-            for _ in range(3):
-                q_step()
-            ms = time_steps(q_step, args.steps, barrier, dev, world) / args.steps
-            qn = workload_numbers(Q['g'], 1)
-            configs.append({'workload': f'{wl}-shaped aggregation forward (BASELINE config {2 if wl == "MultiviewX" else 3})',
-                            'batch': 1, 'n_gpus': 1, 'views': Q['g'].n_views, 'grid': list(Q['grid'].shape[:2]) + [len(Q['zs'])],
-                            'value': 1e3 / ms, 'unit': UNIT, 'ms_per_step': ms, 'kernel_path': vfa_b200.last_kernel_path(),
-                            'table': 'rebuilt every step',
-                            'algorithmic_bytes_per_frame': qn['bytes'],
-                            'hbm_frac_of_step': qn['bytes'] / (ms * 1e-3) / 1e9 / load_peaks()['hbm_gbs']})
-            del Q, q_ws, q_out
-        torch.cuda.empty_cache()
+                def q_step():
+                    tb = vfa_b200.build_table(Q['cgeom'], Q['calibs'], Q['grid'])
+                    vfa_b200.prepare_weights(Q['cgeom'], q_shape, Q['ws'], args.flags, workspace=q_ws)
+                    vfa_b200.aggregate_forward_raw(Q['feats'], tb, Q['ws'], Q['bs'], args.flags, out=q_out, workspace=q_ws,
+                                                   prepared=True)
+                for _ in range(3):
+                    q_step()
+                ms = time_steps(q_step, args.steps, barrier, dev, world) / args.steps
+                qn = workload_numbers(Q['g'], 1)
+                configs.append({'workload': f'{wl}-shaped aggregation forward (BASELINE config {2 if wl == "MultiviewX" else 3})',
+                                'batch': 1, 'n_gpus': 1, 'views': Q['g'].n_views, 'grid': list(Q['grid'].shape[:2]) + [len(Q['zs'])],
+                                'value': 1e3 / ms, 'unit': UNIT, 'ms_per_step': ms, 'kernel_path': vfa_b200.last_kernel_path(),
+                                'table': 'rebuilt every step',
+                                'algorithmic_bytes_per_frame': qn['bytes'],
+                                'hbm_frac_of_step': qn['bytes'] / (ms * 1e-3) / 1e9 / load_peaks()['hbm_gbs']})
+                del Q, q_ws, q_out
+            torch.cuda.empty_cache()
+        except Exception as exc:      # an optional block must never cost the headline line
+            configs = {'error': f'{type(exc).__name__}: {exc}'}
 
     # ---- strong scaling of ONE frame batch over the GPUs: camera sharding, the cross-GPU sum fused into the pooling
     #      kernel (multimem.red over the NVLink multicast address); B frames total, every rank owns V/N cameras ----
     strong = None
     if plain and world > 1 and not args.no_strong:
-        sv0, sv1 = vd.view_bounds(V, world, rank)
-        S_ = setup(args.workload, B, (sv0, sv1), seed=777)        # this rank's cameras of the same B frames
         try:
-            fused = vd.FusedViewAggregator(cgeom, B, C)
-            kind = ('fused reduce-scatter in pool_tile_kernel (red.add.v4 into the band owner\'s replica over NVLink) + multimem.st '
-                    'all-gather of the bands (vfa_multicast_copy), 2 barriers per step, no NCCL call'
-                    if fused.mode == 'reduce_scatter' else
-                    'fused multimem.red.add in pool_tile_kernel on the NVLink multicast address (every replica receives every '
-                    'partial tile), 1 barrier per step, no NCCL call')
-        except Exception as exc:                                  # no multicast support: NCCL all-reduce of the partial maps
-            fused, kind = None, f'NCCL all-reduce of partial maps (fused path unavailable: {exc})'
+            sv0, sv1 = vd.view_bounds(V, world, rank)
+            S_ = setup(args.workload, B, (sv0, sv1), seed=777)        # this rank's cameras of the same B frames
+            try:
+                fused = vd.FusedViewAggregator(cgeom, B, C)
+                kind = ('fused reduce-scatter in pool_tile_kernel (red.add.v4 into the band owner\'s replica over NVLink) + multimem.st '
+                        'all-gather of the bands (vfa_multicast_copy), 2 barriers per step, no NCCL call'
+                        if fused.mode == 'reduce_scatter' else
+                        'fused multimem.red.add in pool_tile_kernel on the NVLink multicast address (every replica receives every '
+                        'partial tile), 1 barrier per step, no NCCL call')
+            except Exception as exc:                                  # no multicast support: NCCL all-reduce of the partial maps
+                fused, kind = None, f'NCCL all-reduce of partial maps (fused path unavailable: {exc})'
 
-        def strong_step():
-            if sv1 > sv0:
-                tb = vfa_b200.build_table(cgeom, S_['calibs'], grid)
-            if fused is not None:
-                return fused(S_['feats'], tb if sv1 > sv0 else None, weights, biases)
-            part = (vfa_b200.aggregate_forward_raw(S_['feats'], tb, weights, biases, args.flags) if sv1 > sv0
-                    else torch.zeros(B, C, grid.shape[0], grid.shape[1], device=dev))
-            dist.all_reduce(part)
-            return part
-        for _ in range(3):
-            strong_step()
-        ms = time_steps(strong_step, args.steps, barrier, dev, world) / args.steps
-        one_gpu_ms = total_ms / args.steps                        # the dp step above: B frames, all V cameras, one GPU
-        map_bytes = B * C * grid.shape[0] * grid.shape[1] * 4
-        strong_kind_mode = None if fused is None else fused.mode
-        strong = {'mode': 'views (camera sharding)', 'collective': kind, 'collective_mode': strong_kind_mode, 'frames_per_step': B, 'n_gpus': world,
-                  'cameras_per_rank': [vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0] for r in range(world)],
-                  'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'one_gpu_ms_per_step': one_gpu_ms,
-                  'speedup': one_gpu_ms / ms, 'efficiency': one_gpu_ms / ms / world,
-                  'max_speedup_from_camera_split': V / max(vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0]
-                                                           for r in range(world)),
-                  'reduced_bytes_per_rank_per_step': map_bytes,
-                  'nvlink_bytes_per_rank_per_step': ({'reduce_scatter_out': map_bytes * (world - 1) // world,
-                                                      'all_gather_in': map_bytes * (world - 1) // world}
-                                                     if fused is not None and fused.mode == 'reduce_scatter' else
-                                                     {'multicast_red_out': map_bytes, 'in': map_bytes * (world - 1)}),
-                  'note': 'each rank red.adds (N-1)/N of its partial [B,L,W,C] map into the owners\' bands while the kernel '
-                          'still pools the next tiles (overlapped, not separately timeable), then broadcasts its own band '
-                          '(1/N of the map out, (N-1)/N in); step time includes the table + weight prep of the rank\'s cameras '
-                          'and both barriers'}
-        del S_, fused
+            def strong_step():
+                if sv1 > sv0:
+                    tb = vfa_b200.build_table(cgeom, S_['calibs'], grid)
+                if fused is not None:
+                    return fused(S_['feats'], tb if sv1 > sv0 else None, weights, biases)
+                part = (vfa_b200.aggregate_forward_raw(S_['feats'], tb, weights, biases, args.flags) if sv1 > sv0
+                        else torch.zeros(B, C, grid.shape[0], grid.shape[1], device=dev))
+                dist.all_reduce(part)
+                return part
+            for _ in range(3):
+                strong_step()
+            ms = time_steps(strong_step, args.steps, barrier, dev, world) / args.steps
+            one_gpu_ms = total_ms / args.steps                        # the dp step above: B frames, all V cameras, one GPU
+            map_bytes = B * C * grid.shape[0] * grid.shape[1] * 4
+            strong_kind_mode = None if fused is None else fused.mode
+            strong = {'mode': 'views (camera sharding)', 'collective': kind, 'collective_mode': strong_kind_mode, 'frames_per_step': B, 'n_gpus': world,
+                      'cameras_per_rank': [vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0] for r in range(world)],
+                      'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'one_gpu_ms_per_step': one_gpu_ms,
+                      'speedup': one_gpu_ms / ms, 'efficiency': one_gpu_ms / ms / world,
+                      'max_speedup_from_camera_split': V / max(vd.view_bounds(V, world, r)[1] - vd.view_bounds(V, world, r)[0]
+                                                               for r in range(world)),
+                      'reduced_bytes_per_rank_per_step': map_bytes,
+                      'nvlink_bytes_per_rank_per_step': ({'reduce_scatter_out': map_bytes * (world - 1) // world,
+                                                          'all_gather_in': map_bytes * (world - 1) // world}
+                                                         if fused is not None and fused.mode == 'reduce_scatter' else
+                                                         {'multicast_red_out': map_bytes, 'in': map_bytes * (world - 1)}),
+                      'note': 'each rank red.adds (N-1)/N of its partial [B,L,W,C] map into the owners\' bands while the kernel '
+                              'still pools the next tiles (overlapped, not separately timeable), then broadcasts its own band '
+                              '(1/N of the map out, (N-1)/N in); step time includes the table + weight prep of the rank\'s cameras '
+                              'and both barriers'}
+            del S_, fused
+        except Exception as exc:      # an optional block must never cost the headline line
+            strong = {'error': f'{type(exc).__name__}: {exc}'}
 
     # ---- BASELINE config 4: batch 64 forward + backward, sharded over the GPUs (64 / N frames per rank; dWeight / dBias
     #      all-reduced over NCCL -- the only exchange; camera / slab sharding replicate or serialise work at this size) ----
     config4 = None
     if plain and not args.no_config4 and args.workload == 'MultiviewC':
-        B4 = 64
-        per = B4 // world
-        Q = setup(args.workload, per, seed=999)
-        for t_ in Q['feats'] + Q['ws'] + Q['bs']:
-            t_.requires_grad_(True)
-        g4 = torch.randn(per, C, grid.shape[0], grid.shape[1], device=dev)
-
-        def c4_step():
-            tb = vfa_b200.build_table(cgeom, Q['calibs'], grid)
-            res = vfa_b200.aggregate(Q['feats'], tb, Q['ws'], Q['bs'], flags=args.flags, channels_last=True)
+        try:
+            B4 = 64
+            per = B4 // world
+            Q = setup(args.workload, per, seed=999)
             for t_ in Q['feats'] + Q['ws'] + Q['bs']:
-                t_.grad = None
-            res.backward(g4)
-            if world > 1:
-                vd.allreduce_collapse_grads(Q['ws'] + Q['bs'])
-        for _ in range(2):
-            c4_step()
-        n4 = max(2, min(args.steps, 4))
-        ms = time_steps(c4_step, n4, barrier, dev, world) / n4
-        config4 = {'workload': 'MultiviewC batch-64 aggregation forward+backward (BASELINE config 4)', 'n_gpus': world,
-                   'frames_per_rank': per, 'value': per * world / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': n4,
-                   'sharding': 'frames (batch) over GPUs', 'collective': 'NCCL all-reduce of dWeight / dBias '
-                   f'({sum(w.numel() + b.numel() for w, b in zip(Q["ws"], Q["bs"])) * 4} bytes per step)',
-                   'scaling': 'strong (64 frames in total)'}
-        del Q, g4
-        torch.cuda.empty_cache()
+                t_.requires_grad_(True)
+            g4 = torch.randn(per, C, grid.shape[0], grid.shape[1], device=dev)
+
+            def c4_step():
+                tb = vfa_b200.build_table(cgeom, Q['calibs'], grid)
+                res = vfa_b200.aggregate(Q['feats'], tb, Q['ws'], Q['bs'], flags=args.flags, channels_last=True)
+                for t_ in Q['feats'] + Q['ws'] + Q['bs']:
+                    t_.grad = None
+                res.backward(g4)
+                if world > 1:
+                    vd.allreduce_collapse_grads(Q['ws'] + Q['bs'])
+            for _ in range(2):
+                c4_step()
+            n4 = max(2, min(args.steps, 4))
+            ms = time_steps(c4_step, n4, barrier, dev, world) / n4
+            config4 = {'workload': 'MultiviewC batch-64 aggregation forward+backward (BASELINE config 4)', 'n_gpus': world,
+                       'frames_per_rank': per, 'value': per * world / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': n4,
+                       'sharding': 'frames (batch) over GPUs', 'collective': 'NCCL all-reduce of dWeight / dBias '
+                       f'({sum(w.numel() + b.numel() for w, b in zip(Q["ws"], Q["bs"])) * 4} bytes per step)',
+                       'scaling': 'strong (64 frames in total)'}
+            del Q, g4
+            torch.cuda.empty_cache()
+        except Exception as exc:      # an optional block must never cost the headline line
+            config4 = {'error': f'{type(exc).__name__}: {exc}'}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
