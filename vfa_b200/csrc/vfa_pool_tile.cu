@@ -98,61 +98,34 @@ struct BuildArgs {
   int max_words;               // bitmap words of the largest scale (shared-memory layout)
 };
 
-// One (quad, layer) of the walk, done by one thread from the tile's records in shared memory.  Weights are those of the
-// walking kernel (wl = wy * wx per cell, zero outside the cell's box); a row is listed when any of the four is non-zero.
-// FILL = false: mark the row's slot in the (chunk, quad) mask.  FILL = true: write the entry at its position (= number of
-// lower slots of the same quad in the chunk).
+// The box of one (cell, layer), walked by one thread from the tile's records in shared memory: every texel with a non-zero
+// weight wy * wx (the walking kernel's weights) is an entry of the cell's quad.  FILL = false: mark the row's slot in the
+// (chunk, quad) mask.  FILL = true: write this cell's component of the entry's weights (the other three stay at the zero the
+// blob was initialised with, or are written by their own cells) and the slot byte, at the entry's position = number of lower
+// slots of the quad in the chunk.  Balanced (a box holds ~5 texels whatever the quad's union looks like) and, unlike a walk
+// of the quad's union, without divergent loop bounds inside a warp.
 template <bool FILL>
-__device__ __forceinline__ void quad_walk(const uint4* __restrict__ recs_s, int q, int n, int sub, int nsub, int fw, int hw,
+__device__ __forceinline__ void cell_walk(const uint4* __restrict__ recs_s, int cell, int n, int fw, int hw,
                                           const uint32_t* __restrict__ bits, const uint32_t* __restrict__ pref,
                                           uint32_t* __restrict__ qmask, const uint16_t* __restrict__ segbeg,
                                           const uint32_t* __restrict__ blob_off16, const uint16_t* __restrict__ nent_s,
                                           uint8_t* __restrict__ blob) {
-  int nx[4], ny[4], x0[4], y0[4];
-  float wxf[4], wxl[4], wyf[4], wyl[4], wym[4];
-  int ux0 = 0x7fff, uy0 = 0x7fff, ux1 = -1, uy1 = -1;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int cell = (2 * (q >> 2) + (c >> 1)) * TC + 2 * (q & 3) + (c & 1);
-    const uint4 r0 = recs_s[(n * TC * TC + cell) * 2], r1 = recs_s[(n * TC * TC + cell) * 2 + 1];
-    nx[c] = (int)r0.y & 0xffff;
-    ny[c] = (int)r0.y >> 16;
-    x0[c] = (int)r0.x & 0xffff;
-    y0[c] = (int)r0.x >> 16;
-    wxf[c] = __uint_as_float(r0.z);
-    wxl[c] = __uint_as_float(r0.w);
-    wyf[c] = __uint_as_float(r1.x);
-    wyl[c] = __uint_as_float(r1.y);
-    wym[c] = __uint_as_float(r1.z);
-    if (nx[c] != 0) {
-      ux0 = min(ux0, x0[c]);
-      uy0 = min(uy0, y0[c]);
-      ux1 = max(ux1, x0[c] + nx[c] - 1);
-      uy1 = max(uy1, y0[c] + ny[c] - 1);
-    }
-  }
-  if (ux1 < 0) return;
-  for (int ty = uy0 + sub; ty <= uy1; ty += nsub) {       // `nsub` threads share the rows of one (quad, layer)
-    float wy[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int ry = ty - y0[c];
-      wy[c] = (nx[c] != 0 && ry >= 0 && ry < ny[c]) ? (ry == 0 ? wyf[c] : (ry == ny[c] - 1 ? wyl[c] : wym[c])) : 0.f;
-    }
-    for (int tx = ux0; tx <= ux1; ++tx) {
-      float wl[4];
-      bool any = false;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int rx = tx - x0[c];
-        const float wx = (nx[c] != 0 && rx >= 0 && rx < nx[c]) ? (rx == 0 ? wxf[c] : (rx == nx[c] - 1 ? wxl[c] : 1.0f)) : 0.f;
-        wl[c] = __fmul_rn(wy[c], wx);
-        any = any || wl[c] != 0.f;
-      }
-      if (!any) continue;
-      const int idx = n * hw + ty * fw + tx;
+  const uint4 r0 = recs_s[(n * TC * TC + cell) * 2], r1 = recs_s[(n * TC * TC + cell) * 2 + 1];
+  const int nx = (int)r0.y & 0xffff, ny = (int)r0.y >> 16;
+  if (nx == 0) return;
+  const int x0 = (int)r0.x & 0xffff, y0 = (int)r0.x >> 16;
+  const float wxf = __uint_as_float(r0.z), wxl = __uint_as_float(r0.w);
+  const float wyf = __uint_as_float(r1.x), wyl = __uint_as_float(r1.y), wym = __uint_as_float(r1.z);
+  const int cy = cell / TC, cx = cell % TC;
+  const int q = (cy >> 1) * 4 + (cx >> 1), c = (cy & 1) * 2 + (cx & 1);       // quad of the tile, cell of the quad
+  for (int ry = 0; ry < ny; ++ry) {
+    const float wy = ry == 0 ? wyf : (ry == ny - 1 ? wyl : wym);
+    for (int rx = 0; rx < nx; ++rx) {
+      const float wx = rx == 0 ? wxf : (rx == nx - 1 ? wxl : 1.0f);
+      const float wl = __fmul_rn(wy, wx);
+      if (!(wl != 0.f)) continue;                        // zero weights are not listed (NaN is: it propagates as in the reference)
+      const int idx = n * hw + (y0 + ry) * fw + x0 + rx;
       const uint32_t word = bits[idx >> 5], bit = (uint32_t)idx & 31u;
-      if (!((word >> bit) & 1u)) continue;               // cannot happen for finite weights: the row is in some box
       const uint32_t rank = pref[idx >> 5] + __popc(word & ((1u << bit) - 1u));
       const uint32_t chunk = rank / TR, slot = rank % TR;
       if (!FILL) {
@@ -160,7 +133,7 @@ __device__ __forceinline__ void quad_walk(const uint4* __restrict__ recs_s, int 
       } else {
         const uint32_t pos = segbeg[chunk * TQ + q] + __popc(qmask[chunk * TQ + q] & ((1u << slot) - 1u));
         uint8_t* b = blob + (size_t)blob_off16[chunk] * 16;
-        reinterpret_cast<float4*>(b + BLOB_HDR)[pos] = make_float4(wl[0], wl[1], wl[2], wl[3]);
+        reinterpret_cast<float*>(b + BLOB_HDR)[4 * pos + c] = wl;
         b[BLOB_HDR + 16 * (uint32_t)nent_s[chunk] + pos] = (uint8_t)slot;
       }
     }
@@ -257,10 +230,8 @@ __global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
   for (int i = tid; i < (int)nchunks * TQ; i += 256) qmask[i] = 0u;
   __syncthreads();
   // pass 3: which slots of which chunk every quad lists
-  const int nsub = max(1, 256 / (TQ * p.nl));
-  for (int item = tid; item < TQ * p.nl * nsub; item += 256)
-    quad_walk<false>(recs_s, item % TQ, (item / TQ) % p.nl, item / (TQ * p.nl), nsub, fw, hw, bits, pref, qmask, nullptr,
-                     nullptr, nullptr, nullptr);
+  for (int item = tid; item < p.nl * TC * TC; item += 256)
+    cell_walk<false>(recs_s, item % (TC * TC), item / (TC * TC), fw, hw, bits, pref, qmask, nullptr, nullptr, nullptr, nullptr);
   __syncthreads();
   // pass 4: entries per chunk, segment starts, blob sizes -> blob offsets; one allocation per CTA
   uint32_t nent = 0, bytes16 = 0;
@@ -331,10 +302,14 @@ __global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
     hdr_s.z |= nruns << 8;
     a.hdr[base_desc + tid] = hdr_s;
   }
-  // pass 6: the entries
-  for (int item = tid; item < TQ * p.nl * nsub; item += 256)
-    quad_walk<true>(recs_s, item % TQ, (item / TQ) % p.nl, item / (TQ * p.nl), nsub, fw, hw, bits, pref, qmask, segbeg,
-                    blob_off16, nent_s, a.blob);
+  // pass 6: the entries -- weights zero-initialised, then every cell writes its own component
+  for (int c = 0; c < (int)nchunks; ++c) {
+    float4* wv = reinterpret_cast<float4*>(a.blob + (size_t)blob_off16[c] * 16 + BLOB_HDR);
+    for (int e = tid; e < (int)nent_s[c]; e += 256) wv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  for (int item = tid; item < p.nl * TC * TC; item += 256)
+    cell_walk<true>(recs_s, item % (TC * TC), item / (TC * TC), fw, hw, bits, pref, qmask, segbeg, blob_off16, nent_s, a.blob);
 }
 
 // ---- pooling ----------------------------------------------------------------------------------------------------------
