@@ -2011,6 +2011,10 @@ int launch_fwd_fside(const AggParams& p_in, const uint8_t* const* wprep, const T
     }
     if (!(variant & 64)) {
       const int quad = runtime_config().pool_quad != 0;     // 0 selects the one-cell-per-warp kernel (debug / comparison)
+      if (!quad && q.out_mode != 0) {
+        set_error("VFA_POOL_QUAD=0 (debug kernel) does not implement VFA_FLAG_OUT_ACCUMULATE / _MULTICAST / _PEERS");
+        return VFA_ERR_UNSUPPORTED;
+      }
       q.tile_ovf = nullptr;
       q.ptiles_x = 0;
       if (quad && tile_bytes != 0) {
