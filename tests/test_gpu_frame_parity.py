@@ -241,3 +241,50 @@ def test_bf16_mma_variant(storage):
     with pytest.raises(RuntimeError, match='forward-only'):
         vfa_b200.aggregate([t.float().requires_grad_(True) for t in cl], table, ws, bs, flags=vfa_b200.FLAG_BF16_MMA,
                            channels_last=True)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_random_rigs_tile_pooling_vs_float64_port(name):
+    """Randomised cameras (outside the field, inside it and low -- voxels behind the camera, boxes tens of texels wide --,
+    looking along a grid axis), random ragged sub-grids, batch 2, C = 256, three scales: the default path (compacted GEMM +
+    staged-tile pooling, including tiles whose chunk lists overflow into the walking kernel) against the float64 port on
+    every cell.  The rigs are the generator of tests/test_gpu_parity.py::test_table_bit_exact_random_rigs."""
+    g = geometry.GEOMETRIES[name]
+    full = geometry.grid_for(g)
+    L, W = full.shape[:2]
+    rng = np.random.RandomState(4321 + NAMES.index(name))
+    from oracle import vfa_oracle as onp
+    world = onp.to_world(full.numpy().reshape(-1, 3).astype(np.float64), name).reshape(L, W, 3)
+    lo, hi = world.reshape(-1, 3).min(0), world.reshape(-1, 3).max(0)
+    span = float(max(hi[0] - lo[0], hi[1] - lo[1]))
+    cams = []
+    for k in range(3):
+        if k == 0:        # outside the field, elevated
+            ang = rng.uniform(0, 2 * np.pi)
+            eye = np.array([(lo[0] + hi[0]) / 2 + np.cos(ang) * span * rng.uniform(0.6, 1.0),
+                            (lo[1] + hi[1]) / 2 + np.sin(ang) * span * rng.uniform(0.6, 1.0), span * rng.uniform(0.1, 0.3)])
+            target = np.array([rng.uniform(lo[0], hi[0]), rng.uniform(lo[1], hi[1]), 0.0])
+        elif k == 1:      # inside the field, low
+            eye = np.array([rng.uniform(lo[0], hi[0]), rng.uniform(lo[1], hi[1]), span * rng.uniform(0.01, 0.05)])
+            target = np.array([rng.uniform(lo[0], hi[0]), rng.uniform(lo[1], hi[1]), 0.0])
+        else:             # above a cell origin, looking along +x
+            i, j = rng.randint(L), rng.randint(W)
+            eye = np.array([world[i, j, 0], world[i, j, 1], span * 0.03])
+            target = eye + np.array([1.0, 0.0, 0.0])
+        cams.append(synthetic.look_at(eye, target, rng.uniform(0.6, 1.4) * g.image_size[1] * 0.7, g.image_size).astype(np.float32))
+    calibs = torch.from_numpy(np.stack(cams))
+    i0, j0 = rng.randint(0, L // 2), rng.randint(0, W // 2)
+    grid = full[i0:i0 + rng.randint(17, 30), j0:j0 + rng.randint(17, 30)].contiguous()        # partial tiles on both sides
+    feats = synthetic.features(g, batch=2, n_views=3, seed=81)
+    params = synthetic.collapse_params(g, seed=81)
+    table = vfa_b200.build_table(_geom(name, grid.shape[:2]), calibs.cuda(), grid.cuda())
+    out = vfa_b200.aggregate([f.cuda() for f in feats], table, [w.cuda() for w, _ in params], [b.cuda() for _, b in params])
+    assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
+    want = _port(name, feats, calibs, grid, params).numpy()
+    got = out.cpu().numpy().astype(np.float64)
+    finite = np.isfinite(want)                 # a 0/0 projection makes the reference's row NaN (documented deviation)
+    err = np.abs(got - want)[finite]
+    bad = err > ATOL + RTOL * np.abs(want[finite])
+    print(f'{name}: grid {tuple(grid.shape[:2])}, {finite.mean():.4f} finite, outside tol {bad.mean():.2e}, worst abs {err.max():.2e}, '
+          f'max|out| {np.abs(want[finite]).max():.2f}')
+    assert not bad.any(), f'{bad.sum()} of {bad.size} outside tolerance (worst {err.max():.3e})'
