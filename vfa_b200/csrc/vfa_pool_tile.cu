@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
     const int cy0 = 2 * (q >> 2), cx0 = 2 * (q & 3);              // inside the tile
     uint32_t st = 0, ph = 0;                       // stage and the parity the consumers wait for on full[st]
 #ifdef VFA_TILE_PROFILE
-    long long t_full = 0, t_work = 0, t_epi = 0, t_out = 0, n_chunks = 0;
+    long long t_full = 0, t_work = 0, t_epi = 0, t_out = 0, n_chunks = 0, w_big = 0, n_big = 0, w_max = 0, n_first = 0, w_first = 0; bool first_chunk = true;
     const long long t_begin = clock64();
 #endif
     for (int round = 0;; ++round) {
@@ -574,6 +574,9 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
 #ifdef VFA_TILE_PROFILE
         const long long c2 = clock64();
         t_full += c1 - c0;
+        if (c1 - c0 > 1000) { w_big += c1 - c0; ++n_big; }
+        if (c1 - c0 > w_max) w_max = c1 - c0;
+        if (first_chunk) { w_first += c1 - c0; ++n_first; first_chunk = false; }
         t_work += c2 - c1;
         ++n_chunks;
 #endif
@@ -615,6 +618,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
       }
 #ifdef VFA_TILE_PROFILE
       const long long c3 = clock64();
+      first_chunk = true;
 #endif
       // ---- the tile's 8 x 8 x 256 block of partial sums -> global memory ----
       if (a.q.out_nhwc) {
@@ -668,10 +672,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
       named_bar_sync(2, POOL_THREADS);
     }
 #ifdef VFA_TILE_PROFILE
-    if (lane == 0 && (blockIdx.x % 37) == 0 && (warp == 0 || warp == 9))
-      printf("cta %3d warp %2d: %lld chunks, total %lld cyc; per chunk: full wait %lld, work %lld, epilogue %lld; tile store total %lld\n",
+    if (lane == 0 && (blockIdx.x % 74) == 0)
+      printf("cta %3d warp %2d: %lld chunks, total %lld cyc; per chunk: full wait %lld, work %lld, epilogue %lld; tile store total %lld; waits>1000: %lld totalling %lld, max %lld; first-chunk-of-tile waits %lld totalling %lld\n",
              blockIdx.x, warp, n_chunks, clock64() - t_begin, t_full / max(n_chunks, 1ll), t_work / max(n_chunks, 1ll),
-             t_epi / max(n_chunks, 1ll), t_out);
+             t_epi / max(n_chunks, 1ll), t_out, n_big, w_big, w_max, n_first, w_first);
 #endif
   }
 }
