@@ -65,6 +65,7 @@ def parse():
     ap.add_argument('--no-configs', action='store_true', help='skip the MultiviewX / Wildtrack B = 1 lines (BASELINE configs 2-3)')
     ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the strong-scaling (camera-sharded, fused) block')
     ap.add_argument('--no-config4', action='store_true', help='skip the batch-64 forward+backward block (BASELINE config 4)')
+    ap.add_argument('--no-config5', action='store_true', help='skip the whole-detector training-step block (BASELINE config 5)')
     return ap.parse_args()
 
 
@@ -195,13 +196,7 @@ def run_reference(args):
 
 
 def run_train(args):
-    """`--mode train` (BASELINE config 5): one optimiser step of the whole detector -- GroupNorm ResNet-18 trunk, batched
-    laterals, the fused aggregation (forward + backward kernels of this repo), `fuse` and the four heads, a stand-in
-    detection loss, SGD -- on synthetic camera images, data parallel over the GPUs of one box (DistributedDataParallel:
-    gradients of every parameter, the collapse weights included, all-reduced over NCCL during the backward).  The
-    backbone, heads and loss are stock PyTorch / cuDNN (torch default precision settings, as the reference trains);
-    they are outside the hand-written path and are here so the aggregation is measured inside its real consumer."""
-    import torch.nn.functional as F
+    """`--mode train`: the BASELINE config 5 line on its own (see train_measure)."""
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -209,12 +204,28 @@ def run_train(args):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    line = train_measure(args, world, rank, local_rank, dev, args.batch, args.steps, args.warmup, breakdown=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_measure(args, world, rank, local_rank, dev, B, steps, warmup, breakdown):
+    """BASELINE config 5: one optimiser step of the whole detector -- GroupNorm ResNet-18 trunk, batched
+    laterals, the fused aggregation (forward + backward kernels of this repo), `fuse` and the four heads, a stand-in
+    detection loss, SGD -- on synthetic camera images, data parallel over the GPUs of one box (DistributedDataParallel:
+    gradients of every parameter, the collapse weights included, all-reduced over NCCL during the backward).  The
+    backbone, heads and loss are stock PyTorch / cuDNN (torch default precision settings, as the reference trains);
+    they are outside the hand-written path and are here so the aggregation is measured inside its real consumer.
+    Needs an initialised process group when world > 1; returns the JSON line as a dict (every rank)."""
+    import torch.nn.functional as F
     import vfa_b200
     from types import SimpleNamespace
     from vfa_b200 import geometry, synthetic
     from vfa_b200.network import VFANet
     geom = geometry.BENCH_WORKLOADS[args.workload]
-    B, V = args.batch, geom.n_views
+    V = geom.n_views
     H, W = geom.resize_size
     torch.manual_seed(0)                                  # identical initial weights on every rank
     net = VFANet(SimpleNamespace(data=geom.name, image_size=geom.image_size), 'resnet18', geom.grid_height,
@@ -264,22 +275,55 @@ def run_train(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         loss = train_step(images)
     path = vfa_b200.last_kernel_path()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    total_ms = timed(lambda: train_step(images), args.steps)
+    total_ms = timed(lambda: train_step(images), steps)
     clocks = sampler.stop()
-    value = world * B * args.steps / (total_ms * 1e-3)
+    value = world * B * steps / (total_ms * 1e-3)
 
     def e2e_step():
         x = host_images.to(dev, non_blocking=True)        # pinned host -> device, every step
         return float(train_step(x).item())                # the loss read back on the host, every step
-    n_e2e = max(3, min(args.steps, 10))
+    n_e2e = max(3, min(steps, 10))
     e2e_ms = timed(e2e_step, n_e2e)
+    final_loss = float(loss.item())
+    n_params = sum(p.numel() for p in net.parameters())
+    breakdown_ms = None
+    if breakdown:
+        breakdown_ms = train_breakdown(args, net, images, calibs, grid, B, V, L, Wg, dev, timed, total_ms / steps)
 
-    # where the step goes: forward of the whole network, and of the aggregation stage alone, on the same inputs
+    line = {
+        'metric': 'training_frames_per_s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
+        'warmup': max(3, warmup), 'ms_per_step': total_ms / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'f32 (aggregation: 3xTF32 tcgen05 + fp32 sums; backbone / heads: cuDNN with torch default settings)',
+        'data': 'synthetic',
+        'config': {'workload': f'full VFA training step on synthetic {args.workload}-shaped frames (GroupNorm ResNet-18 '
+                               f'trunk + laterals + fused aggregation + fuse/heads + stand-in loss + SGD)',
+                   'batch_per_gpu': B, 'views': V, 'image': [H, W], 'grid': [L, Wg, geom.n_layers], 'parameters': n_params,
+                   'parallelism': f'ddp{world}', 'kernel_path': path,
+                   'l2': f'images {host_images.numel() * 4 / 1e6:.0f} MB/step/GPU and every activation exceed the 126 MB L2'},
+        'clocks': clocks,
+        'e2e': {'value': world * B * n_e2e / (e2e_ms * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': host_images.numel() * 4, 'd2h_bytes_per_step': 4, 'steps': n_e2e,
+                'note': 'pinned-host fp32 images copied H2D and the loss read back with .item() every step'},
+        'breakdown_ms': breakdown_ms,
+        'final_loss': final_loss,
+        # this repo's kernels per step: forward 10 (table, 3 weight re-layouts, tap records, coverage / row lists / unit
+        # table, compacted GEMM, pooling) + backward >= 16 (3 transposed weight re-layouts, tap records, tile needs, 5 CSR
+        # launches, mask_grad, dy_gather, overflow, dFeature GEMM, dWeight GEMM, layout); cuDNN / ATen launches not counted
+        'gpu_launches': 26 * steps,
+        'roofline': None, 'cpu_baseline': None,
+    }
+    return line
+
+
+def train_breakdown(args, net, images, calibs, grid, B, V, L, Wg, dev, timed, step_ms):
+    """Where the training step goes: forward of the whole network, and of the aggregation stage alone, on the same inputs."""
+    import vfa_b200
     net.eval()
     with torch.no_grad():
         fwd_ms = timed(lambda: net(images, calibs, grid, batch=B), 5) / 5
@@ -300,37 +344,10 @@ def run_train(args):
             vfa_b200.aggregate(fg, table, wts, bs, flags=args.flags).backward(gout)
         agg_fb()
         agg_fb_ms = timed(agg_fb, 5) / 5
-    if rank == 0:
-        n_params = sum(p.numel() for p in net.parameters())
-        line = {
-            'metric': 'training_frames_per_s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None,
-            'dtype': 'f32 (aggregation: 3xTF32 tcgen05 + fp32 sums; backbone / heads: cuDNN with torch default settings)',
-            'data': 'synthetic',
-            'config': {'workload': f'full VFA training step on synthetic {args.workload}-shaped frames (GroupNorm ResNet-18 '
-                                   f'trunk + laterals + fused aggregation + fuse/heads + stand-in loss + SGD)',
-                       'batch_per_gpu': B, 'views': V, 'image': [H, W], 'grid': [L, Wg, geom.n_layers], 'parameters': n_params,
-                       'parallelism': f'ddp{world}', 'kernel_path': path,
-                       'l2': f'images {host_images.numel() * 4 / 1e6:.0f} MB/step/GPU and every activation exceed the 126 MB L2'},
-            'clocks': clocks,
-            'e2e': {'value': world * B * n_e2e / (e2e_ms * 1e-3), 'unit': UNIT,
-                    'h2d_bytes_per_step': host_images.numel() * 4, 'd2h_bytes_per_step': 4, 'steps': n_e2e,
-                    'note': 'pinned-host fp32 images copied H2D and the loss read back with .item() every step'},
-            'breakdown_ms': {'train_step': total_ms / args.steps, 'network_forward_eval': fwd_ms,
-                             'aggregation_forward': agg_ms, 'aggregation_forward_backward': agg_fb_ms,
-                             'note': 'aggregation = table + fused forward (+ backward kernels) on the lateral maps of this '
-                                     'batch; the rest of the step is cuDNN convolutions / GroupNorm / optimiser'},
-            'final_loss': float(loss.item()),
-            # this repo's kernels per step: forward 10 (table, 3 weight re-layouts, tap records, coverage / row lists / unit
-            # table, compacted GEMM, pooling) + backward >= 16 (3 transposed weight re-layouts, tap records, tile needs, 5 CSR
-            # launches, mask_grad, dy_gather, overflow, dFeature GEMM, dWeight GEMM, layout); cuDNN / ATen launches not counted
-            'gpu_launches': 26 * args.steps,
-            'roofline': None, 'cpu_baseline': None,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return {'train_step': step_ms, 'network_forward_eval': fwd_ms,
+            'aggregation_forward': agg_ms, 'aggregation_forward_backward': agg_fb_ms,
+            'note': 'aggregation = table + fused forward (+ backward kernels) on the lateral maps of this '
+                    'batch; the rest of the step is cuDNN convolutions / GroupNorm / optimiser'}
 
 
 def time_steps(fn, n, barrier, dev, world):
@@ -485,9 +502,9 @@ def main():
     tile_pool = path.startswith('fside') and B >= 2 and os.environ.get('VFA_POOL_TILE', '1') != '0'
     pool_name = 'pool_tile_kernel' if tile_pool else 'pool_list_kernel'
     # launches of this repo's kernels per step: table_build + 3 x prep_weight + tap records + {fused grid-side kernel |
-    # coverage bitmap + row lists + unit table + pooling lists (tile_build_kernel or qlist_build_kernel) + per frame chunk:
-    # compacted ygemm + pooling kernel + its completion pass (pool_quad_kernel<OVF>)}; memsets are not counted
-    launches_per_step = 5 + (4 + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
+    # coverage bitmap + row lists + unit table + pooling lists (tile_build_kernel + tile_order_kernel, or qlist_build_kernel)
+    # + per frame chunk: compacted ygemm + pooling kernel + its completion pass (pool_quad_kernel<OVF>)}; memsets not counted
+    launches_per_step = 5 + (4 + (1 if tile_pool else 0) + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
     if args.mode == 'views':                          # every frame chunk is a complete call (table and weights included)
         launches_per_step *= -(-B // (args.view_chunk or B))
     barrier()
@@ -753,6 +770,24 @@ def main():
         except Exception as exc:      # an optional block must never cost the headline line
             config4 = {'error': f'{type(exc).__name__}: {exc}'}
 
+    # ---- BASELINE config 5: one optimiser step of the whole detector, data parallel (DDP over NCCL), 1 frame per GPU ----
+    config5 = None
+    if plain and not args.no_config5 and args.workload == 'MultiviewC':
+        try:
+            t5 = train_measure(args, world, rank, local_rank, dev, 1, max(3, min(args.steps, 5)), 3, breakdown=False)
+            config5 = {'workload': 'full VFA training step, data parallel (BASELINE config 5): ' + t5['config']['workload'],
+                       'n_gpus': world, 'batch_per_gpu': 1, 'value': t5['value'], 'unit': UNIT, 'ms_per_step': t5['ms_per_step'],
+                       'steps': t5['steps'], 'e2e': t5['e2e'], 'final_loss': t5['final_loss'],
+                       'collective': f"NCCL all-reduce of the gradients of {t5['config']['parameters']} parameters "
+                                     f"({t5['config']['parameters'] * 4} bytes per step), overlapped with the backward by DDP",
+                       'scaling': 'weak (1 frame per GPU)', 'kernel_path': t5['config']['kernel_path'],
+                       'note': 'trunk / heads / loss are stock cuDNN / ATen; `bench.py --mode train` prints the same step '
+                               'with its breakdown'}
+            del t5
+            torch.cuda.empty_cache()
+        except Exception as exc:      # an optional block must never cost the headline line
+            config5 = {'error': f'{type(exc).__name__}: {exc}'}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         views = max(1, min(args.cpu_views, V))
@@ -879,6 +914,7 @@ def main():
             'configs': configs,
             'strong': strong,
             'config4': config4,
+            'config5': config5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

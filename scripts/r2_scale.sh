@@ -9,6 +9,7 @@ d=json.loads([l for l in open("gpurun_out/bench_r2_n$N.json") if l.startswith("{
 print("dp", d["value"], d["ms_per_step"])
 s=d["strong"]; print("strong", {k:s[k] for k in ("value","ms_per_step","speedup","efficiency","cameras_per_rank","collective")})
 print("config4", {k:d["config4"][k] for k in ("value","ms_per_step","frames_per_rank")})
+print("config5", {k:d["config5"].get(k) for k in ("value","ms_per_step","error")})
 print("e2e", d["e2e"]["value"], {k:v["value"] for k,v in d["e2e"]["variants"].items()})
 print("variants", {k:v["value"] for k,v in d["variants"].items()})
 PY

@@ -38,7 +38,7 @@ def test_our_arm_line():
     assert d['metric'] == 'aggregation_frames_per_s' and d['n_gpus'] == 1 and d['steps'] == 3 and d['value'] > 0
     assert d['vs_baseline'] is None and d['data'] == 'synthetic' and d['scaling'] == 'weak'
     assert d['config']['kernel_path'] == 'fside_tf32x3' and 'workload' in d['config']
-    assert d["gpu_launches"] == 12 * 3
+    assert d["gpu_launches"] == 13 * 3
     e = d['e2e']
     assert e['value'] > 0 and e['h2d_bytes_per_step'] == 4 * 7 * 256 * (90 * 160 + 45 * 80 + 23 * 40) * 4
     assert e['d2h_bytes_per_step'] == 4 * 256 * 156 * 156 * 4 and e['value'] < d['value']
@@ -56,10 +56,12 @@ def test_our_arm_line():
     assert abs(st['t_measured_ms'] - d['ms_per_step']) < 1e-9
     pk = r['kernels'][0]
     assert pk['algorithmic_bytes_per_launch'] == st['algorithmic_bytes'] and pk['formulation_bytes'] > pk['algorithmic_bytes_per_launch']
-    # BASELINE configs 2-4 ride on the same line
+    # BASELINE configs 2-5 ride on the same line
     assert [c['workload'].split('-')[0] for c in d['configs']] == ['MultiviewX', 'Wildtrack']
     assert all(c['value'] > 0 and c['batch'] == 1 for c in d['configs'])
     assert d['config4']['frames_per_rank'] == 64 and d['config4']['value'] > 0 and d['strong'] is None
+    c5 = d['config5']
+    assert c5['value'] > 0 and c5['batch_per_gpu'] == 1 and c5['kernel_path'] == 'fside_tf32x3' and c5['e2e']['value'] > 0
     v = d['variants']
     assert v['static_cameras']['value'] > d['value'] and v['bf16_mma']['kernel_path'] == 'fside_bf16mma' and v['bf16_mma']['tolerance']
     assert {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])

@@ -51,7 +51,8 @@ constexpr int MAX_ENT = VFA_TILE_MAXENT;    // entries of a chunk (a quad lists 
                                             // can be); a chunk with more -> the tile is left to the walking kernel
 constexpr int BLOB_HDR = 80;                // segpair[16] (begin | end << 16), nent, info, 8 bytes pad
 constexpr int META_CAP = (BLOB_HDR + 17 * MAX_ENT + 127) / 128 * 128;
-constexpr int CAPV = 4096 / TR;              // chunks of one (tile, view, scale) the builder handles; more -> overflow
+constexpr int CAPV = 3584 / TR;              // chunks of one (tile, view, scale) the builder handles; more -> overflow (sized so
+                                             // that four builder CTAs fit the shared memory of an SM on the shipped rigs)
 #ifndef VFA_TILE_PRODUCERS
 #define VFA_TILE_PRODUCERS 2
 #endif
@@ -80,6 +81,7 @@ struct TileLists {
   const uint32_t* rowoff;      // [chunk][TR]: the chunk's rows as RUNS of consecutive rows of Y (one bulk copy each):
                                // first row inside the (frame, view) stack of nl planes | first slot << 22 | (len - 1) << 27
   const uint8_t* blob;
+  const int* order;            // [n_tiles]: tiles by descending chunk count (the dynamic scheduler deals the heavy ones first)
   int tiles_x, n_tiles, VS;
 };
 
@@ -89,6 +91,7 @@ struct BuildArgs {
   const TapRec* recs;
   uint32_t* cursors;           // [0] chunk ids handed out, [1] blob pool used (16-byte units)
   uint8_t* tile_ovf;
+  uint32_t* tile_work;         // [n_tiles]: chunks of the tile over its (view, scale) pairs (zeroed before the launch)
   uint2* tvs;
   uint4* hdr;
   uint32_t* rowoff;
@@ -120,13 +123,15 @@ __device__ __forceinline__ void cell_walk(const uint4* __restrict__ recs_s, int 
   const int q = (cy >> 1) * 4 + (cx >> 1), c = (cy & 1) * 2 + (cx & 1);       // quad of the tile, cell of the quad
   for (int ry = 0; ry < ny; ++ry) {
     const float wy = ry == 0 ? wyf : (ry == ny - 1 ? wyl : wym);
+    // pass 1 marked the whole box row x0 .. x0 + nx - 1, so its ranks are consecutive: one bitmap lookup per box row
+    const int idx0 = n * hw + (y0 + ry) * fw + x0;
+    const uint32_t bit0 = (uint32_t)idx0 & 31u;
+    const uint32_t rank0 = pref[idx0 >> 5] + __popc(bits[idx0 >> 5] & ((1u << bit0) - 1u));
     for (int rx = 0; rx < nx; ++rx) {
       const float wx = rx == 0 ? wxf : (rx == nx - 1 ? wxl : 1.0f);
       const float wl = __fmul_rn(wy, wx);
       if (!(wl != 0.f)) continue;                        // zero weights are not listed (NaN is: it propagates as in the reference)
-      const int idx = n * hw + (y0 + ry) * fw + x0 + rx;
-      const uint32_t word = bits[idx >> 5], bit = (uint32_t)idx & 31u;
-      const uint32_t rank = pref[idx >> 5] + __popc(word & ((1u << bit) - 1u));
+      const uint32_t rank = rank0 + (uint32_t)rx;
       const uint32_t chunk = rank / TR, slot = rank % TR;
       if (!FILL) {
         atomicOr(&qmask[chunk * TQ + q], 1u << slot);
@@ -161,8 +166,23 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* w
   return before + inc - x;
 }
 
+#ifdef VFA_BUILD_PROFILE
+__device__ unsigned long long g_build_prof[16];
+#define BUILD_PHASE(k)                                                        \
+  do {                                                                        \
+    __syncthreads();                                                          \
+    if (tid == 0) {                                                           \
+      const long long now_ = clock64();                                       \
+      atomicAdd(&g_build_prof[k], (unsigned long long)(now_ - t_phase));      \
+      t_phase = now_;                                                         \
+    }                                                                         \
+  } while (0)
+#else
+#define BUILD_PHASE(k)
+#endif
+
 // grid = n_tiles * VS CTAs of 256 threads; dynamic shared memory: records, bitmap, prefix, masks, segment starts.
-__global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
+__global__ void __launch_bounds__(256, 4) tile_build_kernel(const BuildArgs a) {
   extern __shared__ uint4 bsm[];
   __shared__ uint32_t warp_sums[8];
   __shared__ uint32_t base_s[2];
@@ -181,9 +201,13 @@ __global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
   uint16_t* segbeg = reinterpret_cast<uint16_t*>(qmask + CAPV * TQ);       // [CAPV][TQ]
   uint32_t* rank_idx = reinterpret_cast<uint32_t*>(segbeg + CAPV * TQ);    // [CAPV * TR] row of every rank
   const int tid = threadIdx.x;
+#ifdef VFA_BUILD_PROFILE
+  long long t_phase = clock64();
+#endif
 
   for (int w = tid; w < nwords; w += 256) bits[w] = 0u;
   __syncthreads();
+  BUILD_PHASE(0);
   // pass 1: the tile's records -> shared memory; rows of every visible box -> bitmap
   for (int item = tid; item < p.nl * TC * TC; item += 256) {
     const int n = item / (TC * TC), c = item % (TC * TC);
@@ -209,6 +233,7 @@ __global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
     }
   }
   __syncthreads();
+  BUILD_PHASE(1);
   // pass 2: rank of every covered row = exclusive prefix of the popcounts (a thread scans a contiguous span of words)
   const int span = (nwords + 255) / 256;
   uint32_t local = 0;
@@ -227,29 +252,41 @@ __global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
     }
     return;
   }
+  if (tid == 0) base_s[0] = atomicAdd(&a.cursors[0], nchunks);            // chunk ids: the atomic's latency hides behind pass 3
   for (int i = tid; i < (int)nchunks * TQ; i += 256) qmask[i] = 0u;
   __syncthreads();
+  BUILD_PHASE(2);
   // pass 3: which slots of which chunk every quad lists
   for (int item = tid; item < p.nl * TC * TC; item += 256)
     cell_walk<false>(recs_s, item % (TC * TC), item / (TC * TC), fw, hw, bits, pref, qmask, nullptr, nullptr, nullptr, nullptr);
   __syncthreads();
-  // pass 4: entries per chunk, segment starts, blob sizes -> blob offsets; one allocation per CTA
+  BUILD_PHASE(3);
+  // pass 4: entries per chunk, segment starts (16 lanes per chunk, one per quad), blob sizes -> blob offsets; one
+  // allocation per CTA
+  for (int base = 0; base < (int)nchunks * TQ; base += 256) {
+    const int i = base + tid;
+    const uint32_t cnt = i < (int)nchunks * TQ ? __popc(qmask[i]) : 0u;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < TQ; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d, TQ);
+      if ((tid & (TQ - 1)) >= d) inc += t;
+    }
+    if (i < (int)nchunks * TQ) {
+      segbeg[i] = (uint16_t)(inc - cnt);
+      if ((i & (TQ - 1)) == TQ - 1) nent_s[i / TQ] = (uint16_t)inc;
+    }
+  }
+  __syncthreads();
   uint32_t nent = 0, bytes16 = 0;
   if (tid < (int)nchunks) {
-    for (int q = 0; q < TQ; ++q) {
-      segbeg[tid * TQ + q] = (uint16_t)nent;
-      nent += __popc(qmask[tid * TQ + q]);
-    }
-    nent_s[tid] = (uint16_t)nent;
+    nent = nent_s[tid];
     bytes16 = (BLOB_HDR + 16 * nent + ((nent + 15) & ~15u)) >> 4;
   }
   uint32_t total16 = 0;
   // (a chunk with more than MAX_ENT entries would not fit its stage: flagged through the top bit of the scanned sizes)
   const uint32_t my_off16 = block_exclusive_scan(bytes16 | (nent > (uint32_t)MAX_ENT ? 0x40000000u : 0u), warp_sums, &total16);
-  if (tid == 0) {
-    base_s[0] = atomicAdd(&a.cursors[0], nchunks);
-    base_s[1] = atomicAdd(&a.cursors[1], total16);
-  }
+  if (tid == 0) base_s[1] = atomicAdd(&a.cursors[1], total16);
   __syncthreads();
   const uint32_t base_desc = base_s[0], base_blob16 = base_s[1];
   if (total16 >= 0x40000000u || base_desc + nchunks > a.desc_cap || base_blob16 + total16 > a.blob_cap16) {   // pools exhausted
@@ -259,26 +296,28 @@ __global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
     }
     return;
   }
+  BUILD_PHASE(4);
   // pass 5: descriptors, blob headers, row offsets
-  uint4 hdr_s = make_uint4(0u, 0u, 0u, 0u);
   if (tid < (int)nchunks) {
-    const uint32_t nrows = U == 0 ? 0u : min((uint32_t)TR, U - (uint32_t)tid * TR);
     const bool last = tid == (int)nchunks - 1;
     const uint32_t info = (last ? INFO_LAST_VS : 0u) | ((last && vs == a.VS - 1) ? INFO_LAST_TILE : 0u) |
                           ((uint32_t)s << 8) | ((uint32_t)(vs / p.S) << 16);
     blob_off16[tid] = base_blob16 + my_off16;
-    hdr_s = make_uint4(base_blob16 + my_off16, bytes16 << 4, nrows | (nent << 16), info);
+    uint32_t* hd = reinterpret_cast<uint32_t*>(a.hdr + base_desc + tid);    // .z (rows, runs, entries) comes with the runs
+    hd[0] = base_blob16 + my_off16;
+    hd[1] = bytes16 << 4;
+    hd[3] = info;
     uint32_t* bh = reinterpret_cast<uint32_t*>(a.blob + (size_t)(base_blob16 + my_off16) * 16);
-    for (int q = 0; q < TQ; ++q) {
-      const uint32_t beg = segbeg[tid * TQ + q];
-      bh[q] = beg | ((beg + __popc(qmask[tid * TQ + q])) << 16);
-    }
     bh[16] = nent;
     bh[17] = info;
     bh[18] = 0u;
     bh[19] = 0u;
   }
-  if (tid == 0) a.tvs[(size_t)tile * a.VS + vs] = make_uint2(base_desc, nchunks);
+  if (tid == 0) {
+    a.tvs[(size_t)tile * a.VS + vs] = make_uint2(base_desc, nchunks);
+    atomicAdd(a.tile_work + tile, nchunks);
+  }
+  BUILD_PHASE(5);
   for (int w = tid; w < nwords; w += 256) {
     uint32_t m = bits[w], rank = pref[w];
     while (m) {
@@ -288,28 +327,43 @@ __global__ void __launch_bounds__(256, 3) tile_build_kernel(const BuildArgs a) {
     }
   }
   __syncthreads();                                                         // blob_off16 is read by every walker
-  // the chunk's rows as runs of consecutive rows (ranks follow the row index, so a run occupies consecutive slots)
-  if (tid < (int)nchunks) {
-    const uint32_t nrows = hdr_s.z & 0xffffu;
-    uint32_t* runs = a.rowoff + (size_t)(base_desc + tid) * TR;
-    uint32_t nruns = 0, start = 0;
-    for (uint32_t r = 1; r <= nrows; ++r) {
-      if (r == nrows || rank_idx[tid * TR + r] != rank_idx[tid * TR + r - 1] + 1) {
-        runs[nruns++] = rank_idx[tid * TR + start] | (start << 22) | ((r - start - 1) << 27);
-        start = r;
-      }
-    }
-    hdr_s.z |= nruns << 8;
-    a.hdr[base_desc + tid] = hdr_s;
+  BUILD_PHASE(6);
+  // the quads' segments of every chunk -> blob header (one thread per (chunk, quad))
+  for (int i = tid; i < (int)nchunks * TQ; i += 256) {
+    const uint32_t beg = segbeg[i];
+    reinterpret_cast<uint32_t*>(a.blob + (size_t)blob_off16[i / TQ] * 16)[i & (TQ - 1)] = beg | ((beg + __popc(qmask[i])) << 16);
   }
+  // the chunk's rows as runs of consecutive rows (ranks follow the row index, so a run occupies consecutive slots): one
+  // warp per chunk, one lane per slot; a lane that starts a run finds the run's end in the ballot of the starts
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int c = warp; c < (int)nchunks; c += 8) {
+      const uint32_t nrows = U == 0 ? 0u : min((uint32_t)TR, U - (uint32_t)c * TR);
+      const uint32_t mine = lane < (int)nrows ? rank_idx[c * TR + lane] : 0u;
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, mine, 1);
+      const bool start = lane < (int)nrows && (lane == 0 || mine != prev + 1u);
+      const uint32_t smask = __ballot_sync(0xffffffffu, start);
+      if (start) {
+        const uint32_t higher = lane == 31 ? 0u : smask & ~((2u << lane) - 1u);
+        const uint32_t end = higher ? (uint32_t)__ffs(higher) - 1u : nrows;
+        a.rowoff[(size_t)(base_desc + c) * TR + __popc(smask & ((1u << lane) - 1u))] =
+            mine | ((uint32_t)lane << 22) | ((end - (uint32_t)lane - 1u) << 27);
+      }
+      if (lane == 0)
+        reinterpret_cast<uint32_t*>(a.hdr + base_desc + c)[2] = nrows | ((uint32_t)__popc(smask) << 8) | ((uint32_t)nent_s[c] << 16);
+    }
+  }
+  BUILD_PHASE(7);
   // pass 6: the entries -- weights zero-initialised, then every cell writes its own component
   for (int c = 0; c < (int)nchunks; ++c) {
     float4* wv = reinterpret_cast<float4*>(a.blob + (size_t)blob_off16[c] * 16 + BLOB_HDR);
     for (int e = tid; e < (int)nent_s[c]; e += 256) wv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
+  BUILD_PHASE(8);
   for (int item = tid; item < p.nl * TC * TC; item += 256)
     cell_walk<true>(recs_s, item % (TC * TC), item / (TC * TC), fw, hw, bits, pref, qmask, segbeg, blob_off16, nent_s, a.blob);
+  BUILD_PHASE(9);
 }
 
 // ---- pooling ----------------------------------------------------------------------------------------------------------
@@ -397,7 +451,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
     for (int round = 0;; ++round) {
       const int item = item_s[round & 1];
       if (item >= n_items) break;
-      const int tile = item % t.n_tiles, bl = item / t.n_tiles;
+      const int tile = __ldg(t.order + item / a.nb), bl = item % a.nb;      // heavy tiles first, their frames together
       if (__ldg(t.tile_ovf + tile)) {
         named_bar_sync(2, POOL_THREADS);
         continue;
@@ -510,7 +564,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
       const int item = item_s[round & 1];
       if (item >= n_items) break;
       if (threadIdx.x == 0) item_s[(round + 1) & 1] = (int)atomicAdd(a.next_item, 1u);
-      const int tile = item % t.n_tiles, bl = item / t.n_tiles;
+      const int tile = __ldg(t.order + item / a.nb), bl = item % a.nb;      // heavy tiles first, their frames together
       if (__ldg(t.tile_ovf + tile)) {
         named_bar_sync(2, POOL_THREADS);
         continue;
@@ -680,9 +734,68 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
   }
 }
 
+// ---- schedule: tiles by descending work ---------------------------------------------------------------------------------
+// The pooling kernel deals (tile, frame) items to its CTAs from a global counter; an item is ~1 / 11 of a CTA's share, so the
+// order matters: with the heavy tiles (centre of the ground plane, seen by every camera) first and the light ones last the
+// CTAs finish within a light tile of each other (longest-processing-time-first).  One CTA sorts (chunks of the tile, tile)
+// descending in shared memory: by counting ranks up to RANK_CAP tiles, bitonic up to ORDER_CAP; beyond that identity order.
+constexpr int ORDER_CAP = 8192, RANK_CAP = 1024;
+
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_work,
+                                                          const uint8_t* __restrict__ tile_ovf, int n_tiles,
+                                                          int* __restrict__ order) {
+  extern __shared__ unsigned long long okeys[];
+  if (n_tiles > ORDER_CAP) {
+    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) order[i] = i;
+    return;
+  }
+  if (n_tiles <= RANK_CAP) {
+    // few tiles (every shipped rig): rank = number of larger keys, 32-bit keys read four at a time -- ~2 us instead of the
+    // ~10 us of the 45 barrier-separated bitonic stages
+    uint32_t* k32 = reinterpret_cast<uint32_t*>(okeys);
+    const int n4 = (n_tiles + 3) & ~3;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+      k32[i] = i < n_tiles ? (min(tile_ovf[i] ? 0u : tile_work[i], 0xffffu) << 16) | (0xffffu - (unsigned)i) : 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+      const uint32_t mine = k32[i];
+      int r = 0;
+      for (int j = 0; j < n4; j += 4) {
+        const uint4 o = *reinterpret_cast<const uint4*>(k32 + j);
+        r += (o.x > mine) + (o.y > mine) + (o.z > mine) + (o.w > mine);
+      }
+      order[r] = i;
+    }
+    return;
+  }
+  int np2 = 1;
+  while (np2 < n_tiles) np2 <<= 1;
+  // padding keys are 0 and sort behind every real key (the low word ~tile of a real key is never 0)
+  for (int i = threadIdx.x; i < np2; i += blockDim.x)
+    okeys[i] = i < n_tiles ? ((unsigned long long)(tile_ovf[i] ? 0u : tile_work[i]) << 32) | (unsigned)(~(unsigned)i) : 0ull;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = okeys[i], y = okeys[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? x < y : x > y) {
+            okeys[i] = y;
+            okeys[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) order[i] = (int)(~(unsigned)(okeys[i] & 0xffffffffull));
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 struct TileLayout {
-  size_t off_cursors, off_ovf, off_tvs, off_hdr, off_rowoff, off_blob, total;
+  size_t off_cursors, off_ovf, off_work, off_tvs, off_order, off_hdr, off_rowoff, off_blob, total;
   int tiles_x, n_tiles, VS, max_words;
   uint32_t desc_cap, blob_cap16;
   size_t build_smem;
@@ -720,7 +833,9 @@ static TileLayout tile_layout(const AggParams& p) {
   size_t o = 0;
   L.off_cursors = o; o += 256;
   L.off_ovf = o;     o += align256((size_t)L.n_tiles);
+  L.off_work = o;    o += align256((size_t)L.n_tiles * sizeof(uint32_t));
   L.off_tvs = o;     o += align256((size_t)L.n_tiles * L.VS * sizeof(uint2));
+  L.off_order = o;   o += align256((size_t)L.n_tiles * sizeof(int));
   L.off_hdr = o;     o += align256((size_t)L.desc_cap * sizeof(uint4));
   L.off_rowoff = o;  o += align256((size_t)L.desc_cap * TR * sizeof(uint32_t));
   L.off_blob = o;    o += align256((size_t)L.blob_cap16 * 16);
@@ -739,12 +854,13 @@ int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStre
   const TileLayout L = tile_layout(p);
   if (L.total == 0) return VFA_OK;
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
-  VFA_CUDA(cudaMemsetAsync(w8, 0, L.off_tvs, st));                         // cursors + overflow flags
+  VFA_CUDA(cudaMemsetAsync(w8, 0, L.off_tvs, st));                         // cursors + overflow flags + chunk counts
   BuildArgs a;
   a.p = p;
   a.recs = recs;
   a.cursors = reinterpret_cast<uint32_t*>(w8 + L.off_cursors);
   a.tile_ovf = w8 + L.off_ovf;
+  a.tile_work = reinterpret_cast<uint32_t*>(w8 + L.off_work);
   a.tvs = reinterpret_cast<uint2*>(w8 + L.off_tvs);
   a.hdr = reinterpret_cast<uint4*>(w8 + L.off_hdr);
   a.rowoff = reinterpret_cast<uint32_t*>(w8 + L.off_rowoff);
@@ -757,6 +873,27 @@ int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStre
   VFA_CUDA(cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.build_smem));
   tile_build_kernel<<<L.n_tiles * L.VS, 256, L.build_smem, st>>>(a);
   VFA_LAUNCH_CHECK("tile_build_kernel");
+#ifdef VFA_BUILD_PROFILE
+  {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_build_prof, sizeof(h));
+    const double n = (double)L.n_tiles * L.VS;
+    static const char* names[10] = {"zero bitmap", "records + mark", "rank scan", "quad masks walk", "entry counts + alloc",
+                                    "headers", "rank -> row index", "runs + descriptors", "zero weights", "fill walk"};
+    for (int k = 0; k < 10; ++k) fprintf(stderr, "tile_build phase %d %-22s %8.0f cycles / CTA\n", k, names[k], (double)h[k] / n);
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_build_prof, z, sizeof(z));
+  }
+#endif
+  int np2 = 1;
+  while (np2 < L.n_tiles && np2 < ORDER_CAP) np2 <<= 1;
+  const size_t osm = (size_t)np2 * sizeof(unsigned long long);
+  if (osm > 48 * 1024)
+    VFA_CUDA(cudaFuncSetAttribute(tile_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
+  tile_order_kernel<<<1, np2 < 1024 ? (np2 < 32 ? 32 : np2) : 1024, osm, st>>>(a.tile_work, a.tile_ovf, L.n_tiles,
+                                                                            reinterpret_cast<int*>(w8 + L.off_order));
+  VFA_LAUNCH_CHECK("tile_order_kernel");
   return VFA_OK;
 }
 
@@ -771,6 +908,7 @@ int launch_pool_tile(fside::PoolArgs q, void* ws, int nb, bool y_bf16, cudaStrea
   a.t.hdr = reinterpret_cast<const uint4*>(w8 + L.off_hdr);
   a.t.rowoff = reinterpret_cast<const uint32_t*>(w8 + L.off_rowoff);
   a.t.blob = w8 + L.off_blob;
+  a.t.order = reinterpret_cast<const int*>(w8 + L.off_order);
   a.t.tiles_x = L.tiles_x;
   a.t.n_tiles = L.n_tiles;
   a.t.VS = L.VS;
