@@ -598,26 +598,43 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
         const float4* wv = reinterpret_cast<const float4*>(meta + BLOB_HDR);
         const uint8_t* sl = meta + BLOB_HDR + 16 * nent;
         const uint32_t e1 = (a.variant & 2) ? 0u : seg >> 16;
-        // entries in groups of two, software-pipelined over two static register sets (A / B): the slot, weight and row
-        // loads of the next group are in flight while the packed FMAs of the current one issue
-        for (uint32_t e = seg & 0xffffu; e < e1; e += 2) {
-          const bool two = e + 1 < e1;
-          const uint32_t s0 = sl[e], s1 = two ? sl[e + 1] : s0;
-          const float4 w0 = wv[e];
-          const float4 w1 = wv[two ? e + 1 : e];
+        // entries two at a time: the six row / weight loads of a pair issue back to back ahead of its 32 packed FMAs (a
+        // branch-free body -- with the odd tail inside the loop the compiler sinks the second entry's loads below the first
+        // entry's FMAs and every entry pays a shared-memory round trip), and the slot bytes of the NEXT pair are fetched
+        // before the FMAs so that the slot -> row address -> row chain of a pair starts one level down
+        uint32_t e = seg & 0xffffu;
+        uint32_t s0 = 0, s1 = 0;
+        if (e + 2 <= e1) {
+          s0 = sl[e];
+          s1 = sl[e + 1];
+        }
+        for (; e + 2 <= e1; e += 2) {
+          const float4 w0 = wv[e], w1 = wv[e + 1];
           float4 va0, vb0, va1, vb1;
           load_row8<YT>(sb + s0 * ROWB, lane, va0, vb0);
           load_row8<YT>(sb + s1 * ROWB, lane, va1, vb1);
+          if (e + 4 <= e1) {
+            s0 = sl[e + 2];
+            s1 = sl[e + 3];
+          }
           fside::fma8(acc[0], w0.x, va0, vb0);
           fside::fma8(acc[1], w0.y, va0, vb0);
           fside::fma8(acc[2], w0.z, va0, vb0);
           fside::fma8(acc[3], w0.w, va0, vb0);
-          if (two) {
-            fside::fma8(acc[0], w1.x, va1, vb1);
-            fside::fma8(acc[1], w1.y, va1, vb1);
-            fside::fma8(acc[2], w1.z, va1, vb1);
-            fside::fma8(acc[3], w1.w, va1, vb1);
-          }
+          fside::fma8(acc[0], w1.x, va1, vb1);
+          fside::fma8(acc[1], w1.y, va1, vb1);
+          fside::fma8(acc[2], w1.z, va1, vb1);
+          fside::fma8(acc[3], w1.w, va1, vb1);
+        }
+        if (e < e1) {                                      // odd tail
+          const uint32_t st_ = sl[e];
+          const float4 w0 = wv[e];
+          float4 va0, vb0;
+          load_row8<YT>(sb + st_ * ROWB, lane, va0, vb0);
+          fside::fma8(acc[0], w0.x, va0, vb0);
+          fside::fma8(acc[1], w0.y, va0, vb0);
+          fside::fma8(acc[2], w0.z, va0, vb0);
+          fside::fma8(acc[3], w0.w, va0, vb0);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
