@@ -54,13 +54,16 @@ constexpr int META_CAP = (BLOB_HDR + 17 * MAX_ENT + 127) / 128 * 128;
 constexpr int CAPV = 3584 / TR;              // chunks of one (tile, view, scale) the builder handles; more -> overflow (sized so
                                              // that four builder CTAs fit the shared memory of an SM on the shipped rigs)
 #ifndef VFA_TILE_PRODUCERS
-#define VFA_TILE_PRODUCERS 2
+#define VFA_TILE_PRODUCERS 4
 #endif
 constexpr int NPROD = VFA_TILE_PRODUCERS;   // producer warps
+#ifndef VFA_TILE_SPLIT_RUNS
+#define VFA_TILE_SPLIT_RUNS 1
+#endif
 constexpr int CONSUMER_THREADS = TQ * 32;
 constexpr int POOL_THREADS = CONSUMER_THREADS + 32 * NPROD;
 constexpr int PREFETCH = 3;                 // chunk descriptors a producer warp holds in registers ahead of the ring
-static_assert(NPROD >= 1 && NPROD <= VFA_TILE_STAGES, "");
+static_assert(NPROD >= 1 && (VFA_TILE_SPLIT_RUNS || NPROD <= VFA_TILE_STAGES), "");
 static_assert(TR <= 32 && TR % 8 == 0, "one producer lane per row; slot masks are 32-bit");
 
 constexpr uint32_t INFO_LAST_VS = 1u, INFO_LAST_TILE = 2u;     // info = flags | s << 8 | v << 16
@@ -437,12 +440,21 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
 
   if (warp >= TQ) {
     // ================= producers: chunk descriptors -> bulk copies =================
-    // NPROD warps share the chunk stream round-robin (warp j issues the chunks whose CTA-wide running index is j mod
-    // NPROD): a bulk copy is issued from uniform registers, one lane at a time, ~100 cycles each -- one warp alone cannot
-    // feed the ring.  The stage of a chunk is its running index mod TSTAGES, whichever warp issues it.
+    // A bulk copy is issued from uniform registers, one lane at a time, ~100 cycles each, and a chunk has ~9 runs: issued by
+    // one warp they put ~900 cycles between "the consumers released the stage" and "the last copy is on its way", and that
+    // refill latency is what the leading consumer warps wait for (the ring couples them to the slowest warp).  So every
+    // producer warp visits every chunk and issues the runs pj, pj + NPROD, ... (VFA_TILE_SPLIT_RUNS; four warps: -0.06 ms
+    // per launch against two warps taking alternate chunks, which is what VFA_TILE_SPLIT_RUNS=0 still builds).  The stage
+    // of a chunk is its running index mod TSTAGES.
     const int pj = warp - TQ;
+#if VFA_TILE_SPLIT_RUNS
+    constexpr uint32_t PSTEP = 1;                  // every producer warp visits every chunk and issues runs pj, pj + NPROD, ...
+    uint32_t seq = 0, st = 0, ph = 1u;
+#else
+    constexpr uint32_t PSTEP = NPROD;
     uint32_t seq = (uint32_t)pj;                   // running index of the next chunk this warp issues
     uint32_t st = (uint32_t)pj % TSTAGES, ph = 1u ^ (((uint32_t)pj / TSTAGES) & 1u);   // parity awaited on empty[st]
+#endif
     uint32_t tile_seq0 = 0;                        // running index of the current tile's first chunk
 #ifdef VFA_TILE_PROFILE
     long long t_desc = 0, t_empty = 0, t_issue = 0, n_chunks = 0;
@@ -483,8 +495,8 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
           const uint32_t id = pf_first + pf_k;
           h = __ldg(t.hdr + id);
           r = lane < TR ? __ldg(t.rowoff + (size_t)id * TR + lane) : 0u;
-          pf_seq += NPROD;
-          pf_k += NPROD;
+          pf_seq += PSTEP;
+          pf_k += PSTEP;
           settle();
         } else {
           h = make_uint4(0u, 0u, 0u, 0u);
@@ -514,22 +526,30 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
           uint8_t* sb = stages + (size_t)st * STAGE;
           const uint32_t nrows = h.z & 0xffu, nruns = (h.z >> 8) & 0xffu;
           const int s = (int)((h.w >> 8) & 0xffu), v = (int)(h.w >> 16);
+#if VFA_TILE_SPLIT_RUNS
+          if (lane == 0 && pj == 0) {
+#else
           if (lane == 0) {
+#endif
             mbar_arrive_expect_tx(&full[st], h.y + ((a.variant & 1) ? 0u : nrows * ROWB));
             bulk_g2s(sb + TR * ROWB, t.blob + (size_t)h.x * 16, h.y, &full[st]);
           }
           __syncwarp();
+#if VFA_TILE_SPLIT_RUNS
+          if (lane < (int)nruns && (lane % NPROD) == pj && !(a.variant & 1)) {
+#else
           if (lane < (int)nruns && !(a.variant & 1)) {   // one bulk copy per run of consecutive rows
+#endif
             const uint8_t* ybase = reinterpret_cast<const uint8_t*>(pick(a.q.y, s)) +
                                    (size_t)(bl * p.V + v) * pick(a.plane_bytes, s);
             bulk_g2s(sb + ((r >> 22) & 31u) * ROWB, ybase + (size_t)(r & 0x3fffffu) * ROWB, ((r >> 27) + 1u) * ROWB, &full[st]);
           }
-          st += NPROD;
+          st += PSTEP;
           if (st >= TSTAGES) {
             st -= TSTAGES;
             ph ^= 1u;
           }
-          seq += NPROD;
+          seq += PSTEP;
 #ifdef VFA_TILE_PROFILE
           t_desc += c1 - c0;
           t_empty += c2 - c1;
@@ -546,7 +566,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
       named_bar_sync(2, POOL_THREADS);
     }
 #ifdef VFA_TILE_PROFILE
-    if (lane == 0 && (blockIdx.x % 37) == 0)
+    if (lane == 0 && blockIdx.x == 74)
       printf("cta %3d producer %d: %lld chunks, total %lld cyc; per chunk: descriptor wait %lld, empty wait %lld, issue %lld\n",
              blockIdx.x, pj, n_chunks, clock64() - t_begin, t_desc / max(n_chunks, 1ll), t_empty / max(n_chunks, 1ll),
              t_issue / max(n_chunks, 1ll));
@@ -557,7 +577,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
     const int cy0 = 2 * (q >> 2), cx0 = 2 * (q & 3);              // inside the tile
     uint32_t st = 0, ph = 0;                       // stage and the parity the consumers wait for on full[st]
 #ifdef VFA_TILE_PROFILE
-    long long t_full = 0, t_work = 0, t_epi = 0, t_out = 0, n_chunks = 0, w_big = 0, n_big = 0, w_max = 0, n_first = 0, w_first = 0; bool first_chunk = true;
+    long long t_full = 0, t_work = 0, t_epi = 0, t_out = 0, n_chunks = 0, w_big = 0, n_big = 0, w_max = 0, n_first = 0, w_first = 0; bool first_chunk = true, after_vs = false; long long n_big_vs = 0, runs_big = 0, runs_all = 0;
     const long long t_begin = clock64();
 #endif
     for (int round = 0;; ++round) {
@@ -645,7 +665,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
 #ifdef VFA_TILE_PROFILE
         const long long c2 = clock64();
         t_full += c1 - c0;
-        if (c1 - c0 > 1000) { w_big += c1 - c0; ++n_big; }
+        if (c1 - c0 > 1000) { w_big += c1 - c0; ++n_big; if (after_vs) ++n_big_vs; }
         if (c1 - c0 > w_max) w_max = c1 - c0;
         if (first_chunk) { w_first += c1 - c0; ++n_first; first_chunk = false; }
         t_work += c2 - c1;
@@ -684,6 +704,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
         }
 #ifdef VFA_TILE_PROFILE
         t_epi += clock64() - c2;
+        after_vs = (info & INFO_LAST_VS) != 0;
 #endif
         if (info & INFO_LAST_TILE) break;
       }
@@ -743,10 +764,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
       named_bar_sync(2, POOL_THREADS);
     }
 #ifdef VFA_TILE_PROFILE
-    if (lane == 0 && (blockIdx.x % 74) == 0)
-      printf("cta %3d warp %2d: %lld chunks, total %lld cyc; per chunk: full wait %lld, work %lld, epilogue %lld; tile store total %lld; waits>1000: %lld totalling %lld, max %lld; first-chunk-of-tile waits %lld totalling %lld\n",
+    if (lane == 0 && blockIdx.x == 74 && (warp & 3) == 0)
+      printf("cta %3d warp %2d: %lld chunks, total %lld cyc; per chunk: full wait %lld, work %lld, epilogue %lld; tile store total %lld; waits>1000: %lld totalling %lld, max %lld; first-chunk-of-tile waits %lld totalling %lld; big waits right after a (view, scale) end: %lld\n",
              blockIdx.x, warp, n_chunks, clock64() - t_begin, t_full / max(n_chunks, 1ll), t_work / max(n_chunks, 1ll),
-             t_epi / max(n_chunks, 1ll), t_out, n_big, w_big, w_max, n_first, w_first);
+             t_epi / max(n_chunks, 1ll), t_out, n_big, w_big, w_max, n_first, w_first, n_big_vs);
 #endif
   }
 }
