@@ -551,7 +551,9 @@ def main():
                 if i >= 0:
                     evs[i][1].record()
             torch.cuda.synchronize()
-            per_kernel[kname] = sum(a.elapsed_time(b) for a, b in evs) / len(evs) / nums['fside_chunks']
+            # median over the launches: a launch that waited for the host (interpreter pause, NVML poll) is not the kernel
+            ts = sorted(a.elapsed_time(b) for a, b in evs)
+            per_kernel[kname] = ts[len(ts) // 2] / nums['fside_chunks']
         os.environ.pop('VFA_UMMA_VARIANT', None)
         os.environ.pop('VFA_FSIDE_NO_SKIP', None)
         vfa_b200.reload_env()

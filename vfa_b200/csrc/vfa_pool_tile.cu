@@ -778,6 +778,10 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
 // CTAs finish within a light tile of each other (longest-processing-time-first).  One CTA sorts (chunks of the tile, tile)
 // descending in shared memory: by counting ranks up to RANK_CAP tiles, bitonic up to ORDER_CAP; beyond that identity order.
 constexpr int ORDER_CAP = 8192, RANK_CAP = 1024;
+#ifndef VFA_ORDER_BINS
+#define VFA_ORDER_BINS 8
+#endif
+constexpr int ORDER_BINS = VFA_ORDER_BINS;
 
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_work,
                                                           const uint8_t* __restrict__ tile_ovf, int n_tiles,
@@ -790,10 +794,22 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __rest
   if (n_tiles <= RANK_CAP) {
     // few tiles (every shipped rig): rank = number of larger keys, 32-bit keys read four at a time -- ~2 us instead of the
     // ~10 us of the 45 barrier-separated bitonic stages
+    // The work is quantised to ORDER_BINS levels and tiles of one level keep their row-major order: neighbours (which
+    // share a fifth of their rows) are still pooled at the same time by different SMs and meet in L2, and the tail of the
+    // launch is made of the lightest level all the same.
     uint32_t* k32 = reinterpret_cast<uint32_t*>(okeys);
+    __shared__ uint32_t wmax_s;
+    if (threadIdx.x == 0) wmax_s = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_tiles; i += blockDim.x)
+      if (!tile_ovf[i]) atomicMax(&wmax_s, tile_work[i]);
+    __syncthreads();
+    const uint32_t wmax = wmax_s + 1u;
     const int n4 = (n_tiles + 3) & ~3;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x)
-      k32[i] = i < n_tiles ? (min(tile_ovf[i] ? 0u : tile_work[i], 0xffffu) << 16) | (0xffffu - (unsigned)i) : 0u;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const uint32_t w = i < n_tiles && !tile_ovf[i] ? tile_work[i] : 0u;
+      k32[i] = i < n_tiles ? (((uint32_t)((unsigned long long)w * ORDER_BINS / wmax)) << 16) | (0xffffu - (unsigned)i) : 0u;
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
       const uint32_t mine = k32[i];
