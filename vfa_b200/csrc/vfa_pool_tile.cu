@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TSTAGES; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], VFA_TILE_SPLIT_RUNS ? NPROD : 1);
       mbar_init(&empty[i], TQ);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -527,17 +527,23 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
           const uint32_t nrows = h.z & 0xffu, nruns = (h.z >> 8) & 0xffu;
           const int s = (int)((h.w >> 8) & 0xffu), v = (int)(h.w >> 16);
 #if VFA_TILE_SPLIT_RUNS
-          if (lane == 0 && pj == 0) {
+          // every producer warp arrives on full[st] with the bytes of ITS runs (warp 0: + the blob), so the stage cannot fill
+          // -- and the ring cannot move a whole turn -- without this warp: a warp that had no run in a chunk could otherwise
+          // be lapped by the consumers and would then wait on a parity of empty[st] that has come round again
+          const bool mine_run = lane < (int)nruns && (lane % NPROD) == pj && !(a.variant & 1);
+          const uint32_t my_rows = __reduce_add_sync(0xffffffffu, mine_run ? (r >> 27) + 1u : 0u);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[st], my_rows * ROWB + (pj == 0 ? h.y : 0u));
+            if (pj == 0) bulk_g2s(sb + TR * ROWB, t.blob + (size_t)h.x * 16, h.y, &full[st]);
+          }
+          __syncwarp();
+          if (mine_run) {
 #else
           if (lane == 0) {
-#endif
             mbar_arrive_expect_tx(&full[st], h.y + ((a.variant & 1) ? 0u : nrows * ROWB));
             bulk_g2s(sb + TR * ROWB, t.blob + (size_t)h.x * 16, h.y, &full[st]);
           }
           __syncwarp();
-#if VFA_TILE_SPLIT_RUNS
-          if (lane < (int)nruns && (lane % NPROD) == pj && !(a.variant & 1)) {
-#else
           if (lane < (int)nruns && !(a.variant & 1)) {   // one bulk copy per run of consecutive rows
 #endif
             const uint8_t* ybase = reinterpret_cast<const uint8_t*>(pick(a.q.y, s)) +
