@@ -312,8 +312,8 @@ def train_measure(args, world, rank, local_rank, dev, B, steps, warmup, breakdow
                 'note': 'pinned-host fp32 images copied H2D and the loss read back with .item() every step'},
         'breakdown_ms': breakdown_ms,
         'final_loss': final_loss,
-        # this repo's kernels per step: forward 10 (table, 3 weight re-layouts, tap records, coverage / row lists / unit
-        # table, compacted GEMM, pooling) + backward >= 16 (3 transposed weight re-layouts, tap records, tile needs, 5 CSR
+        # this repo's kernels per step: forward 10 (table, weight re-layout, tap records, chunk lists + tile order, row lists,
+        # unit table, compacted GEMM, pooling + completion pass) + backward >= 16 (3 transposed weight re-layouts, tap records, tile needs, 5 CSR
         # launches, mask_grad, dy_gather, overflow, dFeature GEMM, dWeight GEMM, layout); cuDNN / ATen launches not counted
         'gpu_launches': 26 * steps,
         'roofline': None, 'cpu_baseline': None,
@@ -488,7 +488,7 @@ def main():
         if args.mode in ('slab', 'views') or args.backward:
             return step_general(timed_events)
         table = vfa_b200.build_table(cgeom, calibs, grid)                           # 1 launch
-        vfa_b200.prepare_weights(cgeom, shape, weights, args.flags, workspace=ws)    # 3 launches
+        vfa_b200.prepare_weights(cgeom, shape, weights, args.flags, workspace=ws)    # 1 launch
         if timed_events is not None:
             timed_events[0].record()
         vfa_b200.aggregate_forward_raw(feats_cl, table, weights, biases, args.flags, out=out, workspace=ws,
@@ -501,10 +501,11 @@ def main():
     path = vfa_b200.last_kernel_path()
     tile_pool = path.startswith('fside') and B >= 2 and os.environ.get('VFA_POOL_TILE', '1') != '0'
     pool_name = 'pool_tile_kernel' if tile_pool else 'pool_list_kernel'
-    # launches of this repo's kernels per step: table_build + 3 x prep_weight + tap records + {fused grid-side kernel |
-    # coverage bitmap + row lists + unit table + pooling lists (tile_build_kernel + tile_order_kernel, or qlist_build_kernel)
-    # + per frame chunk: compacted ygemm + pooling kernel + its completion pass (pool_quad_kernel<OVF>)}; memsets not counted
-    launches_per_step = 5 + (4 + (1 if tile_pool else 0) + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
+    # launches of this repo's kernels per step: table_build + prep_weight (all scales) + tap records + {fused grid-side kernel |
+    # pooling lists with the coverage bitmap (tile_build_kernel + tile_order_kernel; single frames: cover_mark_kernel +
+    # qlist_build_kernel) + row lists + unit table + per frame chunk: compacted ygemm + pooling kernel + its completion pass
+    # (pool_quad_kernel<OVF>)}; memsets not counted
+    launches_per_step = 3 + (4 + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)
     if args.mode == 'views':                          # every frame chunk is a complete call (table and weights included)
         launches_per_step *= -(-B // (args.view_chunk or B))
     barrier()

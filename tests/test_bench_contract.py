@@ -38,7 +38,7 @@ def test_our_arm_line():
     assert d['metric'] == 'aggregation_frames_per_s' and d['n_gpus'] == 1 and d['steps'] == 3 and d['value'] > 0
     assert d['vs_baseline'] is None and d['data'] == 'synthetic' and d['scaling'] == 'weak'
     assert d['config']['kernel_path'] == 'fside_tf32x3' and 'workload' in d['config']
-    assert d["gpu_launches"] == 13 * 3
+    assert d["gpu_launches"] == 10 * 3
     e = d['e2e']
     assert e['value'] > 0 and e['h2d_bytes_per_step'] == 4 * 7 * 256 * (90 * 160 + 45 * 80 + 23 * 40) * 4
     assert e['d2h_bytes_per_step'] == 4 * 256 * 156 * 156 * 4 and e['value'] < d['value']

@@ -134,7 +134,7 @@ def test_tile_pooling_overflow_nhwc_and_determinism(libenv):
     """Staged-tile pooling (pool_tile_kernel, the default): bit-reproducible run to run; with its pools forced to overflow
     (VFA_POOL_TILE_CAP = 1 %: nearly every tile is left to the walking kernel) and with the quads' list kernel
     (VFA_POOL_TILE = 0) the sums only change their order (fp32 rounding); the [B, L, W, C] output (VFA_FLAG_OUT_NHWC) holds
-    the same bits as [B, C, L, W]; all on a ragged grid with an in-field camera, inference and training (mask) variants."""
+    the same bits as [B, C, L, W]; so does every tile order of the scheduler (VFA_TILE_ORDER); all on a ragged grid with an in-field camera, inference and training (mask) variants."""
     g = geometry.WILDTRACK
     grid = geometry.grid_for(g)[3:80, 5:132].contiguous()             # 77 x 127 cells: partial tiles on both sides
     calibs = synthetic.ring_calibs(g, n_views=3, in_field=True)
@@ -143,10 +143,16 @@ def test_tile_pooling_overflow_nhwc_and_determinism(libenv):
     ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
     feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=V, seed=8)]
     table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
-    for k in ('VFA_POOL_TILE_CAP', 'VFA_POOL_TILE'):
+    for k in ('VFA_POOL_TILE_CAP', 'VFA_POOL_TILE', 'VFA_TILE_ORDER'):
         libenv.delenv(k, raising=False)
     ref = vfa_b200.aggregate(feats, table, ws, bs)
     assert torch.equal(vfa_b200.aggregate(feats, table, ws, bs), ref)
+    # the order in which the scheduler deals the tiles (heavy first: rank sort; the bitonic sort for > 1024 tiles; identity
+    # for > 8192) changes no bit -- every tile is pooled exactly once, by one CTA
+    for mode in ('1', '2'):
+        libenv.setenv('VFA_TILE_ORDER', mode)
+        assert torch.equal(vfa_b200.aggregate(feats, table, ws, bs), ref), f'VFA_TILE_ORDER={mode}'
+    libenv.delenv('VFA_TILE_ORDER', raising=False)
     simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)
     err = (ref - simt).abs()
     assert bool((err <= ATOL + RTOL * simt.abs()).all()), f'worst {float(err.max()):.2e}'

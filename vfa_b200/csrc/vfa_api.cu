@@ -36,6 +36,7 @@ static void load_config() {
   c.pool_tile = env_int("VFA_POOL_TILE", 1);
   c.pool_tile_cap = env_int("VFA_POOL_TILE_CAP", 100);
   c.tile_variant = env_int("VFA_TILE_VARIANT", 0);
+  c.tile_order = env_int("VFA_TILE_ORDER", 0);
   c.pool_list = env_int("VFA_POOL_LIST", 1);
   c.pool_quad = env_int("VFA_POOL_QUAD", 1);
   c.pool_list_cap = env_int("VFA_POOL_LIST_CAP", 0);

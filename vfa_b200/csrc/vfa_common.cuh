@@ -53,6 +53,7 @@ struct RuntimeConfig {
   int pool_tile;          // VFA_POOL_TILE      1 (default): staged-tile pooling for batch >= 2; 2: any batch; 0: off
   int pool_tile_cap;      // VFA_POOL_TILE_CAP  pool sizes of the tiles' chunk lists in percent (100)
   int tile_variant;       // VFA_TILE_VARIANT   pool_tile_kernel debug bits
+  int tile_order;         // VFA_TILE_ORDER     tile_order_kernel: 0 = by size (default), 1 = force the bitonic sort, 2 = identity
   int pool_list;          // VFA_POOL_LIST      0: walking kernel instead of the quads' texel lists
   int pool_quad;          // VFA_POOL_QUAD      0: one-cell-per-warp comparison kernel
   int pool_list_cap;      // VFA_POOL_LIST_CAP  list entries per (view, scale, layer) of a quad's slot (0 = default)

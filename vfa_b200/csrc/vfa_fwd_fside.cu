@@ -942,27 +942,7 @@ using namespace fside;
 // covered texels per (scale, view, layer) plane; from it one byte per (tile, layer) tells ygemm_kernel (and the backward's
 // dFeature / dWeight products) which tiles to skip altogether.  Zero-weight taps are marked too (superset of what the
 // pooling kernels fetch).
-struct CoverMap {
-  int word_base[VFA_MAX_SCALES];     // first 32-bit word of scale s; planes (v * nl + n) follow each other, `words` apart
-  int words[VFA_MAX_SCALES];         // ceil(hw / 32)
-  int hw[VFA_MAX_SCALES], fw[VFA_MAX_SCALES];
-  int total_words;
-};
-
-static CoverMap make_cover_map(const AggParams& p) {
-  CoverMap cm;
-  int base = 0;
-  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
-    const int ss = s < p.S ? s : 0;
-    cm.hw[s] = p.sc[ss].fh * p.sc[ss].fw;
-    cm.fw[s] = p.sc[ss].fw;
-    cm.words[s] = (cm.hw[s] + 31) / 32;
-    cm.word_base[s] = base;
-    if (s < p.S) base += p.V * p.nl * cm.words[s];
-  }
-  cm.total_words = base;
-  return cm;
-}
+// (CoverMap / make_cover_map: vfa_pool.cuh -- the chunk-list builder of vfa_pool_tile.cu fills the same bitmap)
 
 __global__ void __launch_bounds__(256) cover_mark_kernel(AggParams p, const TapRec* __restrict__ recs, CoverMap cm,
                                                          uint32_t* __restrict__ bits) {
@@ -1891,7 +1871,7 @@ static int launch_quad_lists(const AggParams& p, const TapRec* recs, void* list_
 
 // staged-tile pooling (vfa_pool_tile.cu): the default; 0 bytes = not available for this problem (the quads' lists serve it)
 size_t tile_pool_workspace_bytes(const AggParams& p);
-int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStream_t st);
+int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, void* cover_ws, cudaStream_t st);
 int launch_pool_tile(fside::PoolArgs q, void* ws, int nb, bool y_bf16, cudaStream_t st);
 void tile_pool_overflow_view(const AggParams& p, void* ws, const uint8_t** tile_ovf, int* tiles_x);
 
@@ -1958,12 +1938,17 @@ int launch_fwd_fside(const AggParams& p_in, const uint8_t* const* wprep, const T
   // row-compacted GEMM unless VFA_FSIDE_COMPACT=0 (whole 256-row tiles, skipped by the need bytes) or VFA_FSIDE_NO_SKIP=1
   const bool compact = runtime_config().fside_compact != 0 && runtime_config().fside_no_skip == 0;
   if (!(variant & 256)) {       // (debug bit 256: reuse tap records, coverage bitmap, lists and need bytes of the previous call)
-    if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
+    // the chunk-list builder sees every covered (layer, texel) row of every tile: it fills the coverage bitmap on its way
+    // (one pass over the records less); without it cover_mark_kernel does
+    const bool build_tiles = tile_bytes != 0 && !(variant & 64);
+    if (build_tiles) {
+      if (int rc = launch_tile_build(p, recs, list_ws, fs_ws, st)) return rc;
+    } else {
+      if (int rc = launch_cover_mark(p, recs, fs_ws, st)) return rc;
+    }
     if (compact)
       if (int rc = launch_rowlists(p, fs_ws, cb, st)) return rc;
-    if (tile_bytes != 0 && !(variant & 64)) {
-      if (int rc = launch_tile_build(p, recs, list_ws, st)) return rc;
-    } else if (LL.total != 0 && !(variant & 64)) {
+    if (!build_tiles && LL.total != 0 && !(variant & 64)) {
       if (int rc = launch_quad_lists(p, recs, list_ws, st)) return rc;
     }
   }

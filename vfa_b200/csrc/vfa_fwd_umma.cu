@@ -120,7 +120,14 @@ using namespace umma;
 
 // collapse.weight [C, C*nl] (column c*nl+n)  ->  per scale, per K chunk kc = n*(C/32) + c/32 a 64 KB block
 // [hi: 256 rows x 128 B swizzled][lo: same], hi = tf32(w), lo = tf32(w - hi).
-__global__ void __launch_bounds__(256) prep_weight_umma_kernel(const float* __restrict__ w, uint8_t* __restrict__ wp, int nl) {
+struct PrepWeightArgs {
+  const float* w[VFA_MAX_SCALES];
+  uint8_t* wp[VFA_MAX_SCALES];
+};
+// grid.y = scale: one launch re-lays the collapse weights of every scale
+__global__ void __launch_bounds__(256) prep_weight_umma_kernel(const PrepWeightArgs a, int nl) {
+  const float* __restrict__ w = blockIdx.y == 0 ? a.w[0] : (blockIdx.y == 1 ? a.w[1] : a.w[2]);
+  uint8_t* __restrict__ wp = blockIdx.y == 0 ? a.wp[0] : (blockIdx.y == 1 ? a.wp[1] : a.wp[2]);
   const int K = CH * nl;
   const long long total = (long long)CH * K;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -852,10 +859,13 @@ int prep_weights_umma(const AggParams& p, const float* const* d_weight, void* ws
   const size_t per_scale = (size_t)p.nl * (CH / KCH) * (2 * B_BYTES);
   if ((flags & VFA_FLAG_BF16_MMA) && !grid_side_requested(flags))      // bf16 slabs in the same (larger) per-scale slots
     return prep_weights_bf16(p, d_weight, ws, per_scale, st);
+  PrepWeightArgs a = {};
   for (int s = 0; s < p.S; ++s) {
-    prep_weight_umma_kernel<<<148 * 4, 256, 0, st>>>(d_weight[s], reinterpret_cast<uint8_t*>(ws) + s * per_scale, p.nl);
-    VFA_LAUNCH_CHECK("prep_weight_umma_kernel");
+    a.w[s] = d_weight[s];
+    a.wp[s] = reinterpret_cast<uint8_t*>(ws) + s * per_scale;
   }
+  prep_weight_umma_kernel<<<dim3(148 * 2, p.S), 256, 0, st>>>(a, p.nl);
+  VFA_LAUNCH_CHECK("prep_weight_umma_kernel");
   return VFA_OK;
 }
 

@@ -5,6 +5,31 @@
 #include "vfa_common.cuh"
 
 namespace vfa {
+
+// Bitmap of the texels some visible box covers, per (scale, view, layer) plane: the row-compacted GEMM multiplies only
+// those rows.  Filled by cover_mark_kernel (vfa_fwd_fside.cu) or, on its way, by tile_build_kernel (vfa_pool_tile.cu).
+struct CoverMap {
+  int word_base[VFA_MAX_SCALES];     // first 32-bit word of scale s; planes (v * nl + n) follow each other, `words` apart
+  int words[VFA_MAX_SCALES];         // ceil(hw / 32)
+  int hw[VFA_MAX_SCALES], fw[VFA_MAX_SCALES];
+  int total_words;
+};
+
+inline CoverMap make_cover_map(const AggParams& p) {
+  CoverMap cm;
+  int base = 0;
+  for (int s = 0; s < VFA_MAX_SCALES; ++s) {
+    const int ss = s < p.S ? s : 0;
+    cm.hw[s] = p.sc[ss].fh * p.sc[ss].fw;
+    cm.fw[s] = p.sc[ss].fw;
+    cm.words[s] = (cm.hw[s] + 31) / 32;
+    cm.word_base[s] = base;
+    if (s < p.S) base += p.V * p.nl * cm.words[s];
+  }
+  cm.total_words = base;
+  return cm;
+}
+
 namespace fside {
 
 constexpr int CH = 256;

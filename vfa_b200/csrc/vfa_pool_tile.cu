@@ -102,6 +102,8 @@ struct BuildArgs {
   uint32_t desc_cap, blob_cap16;
   int tiles_x, VS;
   int max_words;               // bitmap words of the largest scale (shared-memory layout)
+  uint32_t* cover;             // coverage bitmap of the row-compacted GEMM (CoverMap layout; nullptr = not wanted)
+  int cover_base[VFA_MAX_SCALES];
 };
 
 // The box of one (cell, layer), walked by one thread from the tile's records in shared memory: every texel with a non-zero
@@ -237,6 +239,24 @@ __global__ void __launch_bounds__(256, 4) tile_build_kernel(const BuildArgs a) {
   }
   __syncthreads();
   BUILD_PHASE(1);
+  // the tile's covered rows -> the coverage bitmap of the GEMM (plane n of the shared bitmap starts at bit n * hw, a plane
+  // of the global one at a word boundary: funnel shift; most words are zero and cost two shared-memory reads)
+  if (a.cover != nullptr) {
+    const int cwords = (hw + 31) >> 5;
+    uint32_t* cplane = a.cover + pick(a.cover_base, s) + (size_t)((vs / p.S) * p.nl) * cwords;
+    for (int i = tid; i < p.nl * cwords; i += 256) {
+      const int n = i / cwords, w = i - n * cwords;
+      const int b0 = n * hw + w * 32;
+      const int sw = b0 >> 5, sh = b0 & 31;
+      uint32_t m = __funnelshift_r(bits[sw], sw + 1 < nwords ? bits[sw + 1] : 0u, sh);
+      const int valid = hw - w * 32;
+      if (valid < 32) m &= (1u << valid) - 1u;
+      if (m != 0u) {
+        uint32_t* dst = cplane + (size_t)n * cwords + w;
+        if ((*dst & m) != m) atomicOr(dst, m);
+      }
+    }
+  }
   // pass 2: rank of every covered row = exclusive prefix of the popcounts (a thread scans a contiguous span of words)
   const int span = (nwords + 255) / 256;
   uint32_t local = 0;
@@ -683,6 +703,7 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
           const float4 bi0 = *reinterpret_cast<const float4*>(bias_s + s * CH + lane * 4);
           const float4 bi1 = *reinterpret_cast<const float4*>(bias_s + s * CH + CH / 2 + lane * 4);
           const float bb[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+          uint32_t bits4 = 0;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float* o = out_s + (q * 4 + c) * CH + ((lane ^ cell_key(q, c)) << 2);
@@ -700,12 +721,24 @@ __global__ void __launch_bounds__(POOL_THREADS, 1) pool_tile_kernel(const TilePo
             o1.x += fmaxf(tt[4], 0.f); o1.y += fmaxf(tt[5], 0.f); o1.z += fmaxf(tt[6], 0.f); o1.w += fmaxf(tt[7], 0.f);
             *reinterpret_cast<float4*>(o) = o0;
             *reinterpret_cast<float4*>(o + CH / 2) = o1;
-            if (MASK) {
-              const int cy = ty0 + cy0 + (c >> 1), cx = tx0 + cx0 + (c & 1);
-              const bool ok = cy < p.L && cx < p.W;
-              fside::store_mask_words(p.mask + (((size_t)b * p.V + v) * p.S + s) * (CH / 32) * p.LW + (ok ? cy * p.W + cx : 0),
-                                      (size_t)p.LW, lane, bits, ok);
-            }
+            if (MASK) bits4 |= bits << (8 * c);
+          }
+          if (MASK) {
+            // ReLU bits of the quad's four cells: a lane holds eight nibbles (cell c: channels [4l, 4l + 4) and [128 + 4l,
+            // ...) -> nibble 2c, 2c + 1); mask word j of the lane's group of eight (cell j >> 1, half j & 1; global word
+            // (j & 1) * 4 + lane / 8) is the nibble j of lanes 0 .. 7 of the group in lane order: an 8 x 8 nibble transpose
+            // in three exchange steps, after which every lane stores one word (was: 24 shuffles, 8 stores by 4 lanes)
+            uint32_t x = bits4;
+            uint32_t y = __shfl_xor_sync(0xffffffffu, x, 4);
+            x = (lane & 4) ? (x & 0xffff0000u) | (y >> 16) : (x & 0x0000ffffu) | (y << 16);
+            y = __shfl_xor_sync(0xffffffffu, x, 2);
+            x = (lane & 2) ? (x & 0xff00ff00u) | ((y >> 8) & 0x00ff00ffu) : (x & 0x00ff00ffu) | ((y << 8) & 0xff00ff00u);
+            y = __shfl_xor_sync(0xffffffffu, x, 1);
+            x = (lane & 1) ? (x & 0xf0f0f0f0u) | ((y >> 4) & 0x0f0f0f0fu) : (x & 0x0f0f0f0fu) | ((y << 4) & 0xf0f0f0f0u);
+            const int j = lane & 7, c = j >> 1;
+            const int cy = ty0 + cy0 + (c >> 1), cx = tx0 + cx0 + (c & 1);
+            if (cy < p.L && cx < p.W)
+              p.mask[((((size_t)b * p.V + v) * p.S + s) * (CH / 32) + (j & 1) * 4 + (lane >> 3)) * p.LW + cy * p.W + cx] = x;
           }
         }
 #ifdef VFA_TILE_PROFILE
@@ -791,13 +824,13 @@ constexpr int ORDER_BINS = VFA_ORDER_BINS;
 
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ tile_work,
                                                           const uint8_t* __restrict__ tile_ovf, int n_tiles,
-                                                          int* __restrict__ order) {
+                                                          int* __restrict__ order, int mode) {
   extern __shared__ unsigned long long okeys[];
-  if (n_tiles > ORDER_CAP) {
+  if (n_tiles > ORDER_CAP || mode == 2) {
     for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) order[i] = i;
     return;
   }
-  if (n_tiles <= RANK_CAP) {
+  if (n_tiles <= RANK_CAP && mode != 1) {
     // few tiles (every shipped rig): rank = number of larger keys, 32-bit keys read four at a time -- ~2 us instead of the
     // ~10 us of the 45 barrier-separated bitonic stages
     // The work is quantised to ORDER_BINS levels and tiles of one level keep their row-major order: neighbours (which
@@ -910,7 +943,7 @@ using namespace ptile;
 size_t tile_pool_workspace_bytes(const AggParams& p) { return tile_layout(p).total; }
 
 // chunk lists of every tile from the tap records (once per table; static for fixed cameras)
-int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStream_t st) {
+int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, void* cover_ws, cudaStream_t st) {
   const TileLayout L = tile_layout(p);
   if (L.total == 0) return VFA_OK;
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
@@ -930,6 +963,12 @@ int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStre
   a.tiles_x = L.tiles_x;
   a.VS = L.VS;
   a.max_words = L.max_words;
+  a.cover = reinterpret_cast<uint32_t*>(cover_ws);
+  if (cover_ws != nullptr) {
+    const CoverMap cm = make_cover_map(p);
+    for (int s = 0; s < VFA_MAX_SCALES; ++s) a.cover_base[s] = cm.word_base[s];
+    VFA_CUDA(cudaMemsetAsync(cover_ws, 0, (size_t)cm.total_words * sizeof(uint32_t), st));
+  }
   VFA_CUDA(cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.build_smem));
   tile_build_kernel<<<L.n_tiles * L.VS, 256, L.build_smem, st>>>(a);
   VFA_LAUNCH_CHECK("tile_build_kernel");
@@ -952,7 +991,8 @@ int launch_tile_build(const AggParams& p, const TapRec* recs, void* ws, cudaStre
   if (osm > 48 * 1024)
     VFA_CUDA(cudaFuncSetAttribute(tile_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm));
   tile_order_kernel<<<1, np2 < 1024 ? (np2 < 32 ? 32 : np2) : 1024, osm, st>>>(a.tile_work, a.tile_ovf, L.n_tiles,
-                                                                            reinterpret_cast<int*>(w8 + L.off_order));
+                                                                            reinterpret_cast<int*>(w8 + L.off_order),
+                                                                            runtime_config().tile_order);
   VFA_LAUNCH_CHECK("tile_order_kernel");
   return VFA_OK;
 }
