@@ -499,10 +499,10 @@ def main():
     for _ in range(max(3, args.warmup)):
         step()
     path = vfa_b200.last_kernel_path()
-    tile_pool = path.startswith('fside') and B >= 2 and os.environ.get('VFA_POOL_TILE', '1') != '0'
+    tile_pool = path.startswith('fside') and os.environ.get('VFA_POOL_TILE', '1') != '0'
     pool_name = 'pool_tile_kernel' if tile_pool else 'pool_list_kernel'
     # launches of this repo's kernels per step: table_build + prep_weight (all scales) + tap records + {fused grid-side kernel |
-    # pooling lists with the coverage bitmap (tile_build_kernel + tile_order_kernel; single frames: cover_mark_kernel +
+    # pooling lists with the coverage bitmap (tile_build_kernel + tile_order_kernel; VFA_POOL_TILE=0: cover_mark_kernel +
     # qlist_build_kernel) + row lists + unit table + per frame chunk: compacted ygemm + pooling kernel + its completion pass
     # (pool_quad_kernel<OVF>)}; memsets not counted
     launches_per_step = 3 + (4 + 3 * nums['fside_chunks'] if path.startswith('fside') else 1)

@@ -337,7 +337,7 @@ def test_feature_side_chunking_and_ragged_grids(libenv):
 
 
 def test_list_pooling_equals_walking_pooling_bit_for_bit(libenv):
-    """The default pooling reads precomputed texel lists (pool_list_kernel); quads whose list does not fit its slot are
+    """The list pooling (VFA_POOL_TILE=0) reads precomputed texel lists (pool_list_kernel); quads whose list does not fit its slot are
     pooled by the walking kernel (pool_quad_kernel, completion pass).  Both apply the same weights in the same order, so
     any split of the quads between them gives the same bits: default slots (every quad listed), slots of 1 and 3 entries
     per iteration (most / some quads walked), for inference and for the training variant that writes the ReLU mask, on a
@@ -351,6 +351,7 @@ def test_list_pooling_equals_walking_pooling_bit_for_bit(libenv):
     feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=V, seed=8)]
     table = vfa_b200.build_table(_geom(g.name, grid.shape[:2]), calibs.cuda(), grid.cuda())
     libenv.delenv('VFA_POOL_LIST_CAP', raising=False)
+    libenv.setenv('VFA_POOL_TILE', '0')              # the list kernel (the staged-tile pooling is the default)
     ref = vfa_b200.aggregate(feats, table, ws, bs)
     assert vfa_b200.last_kernel_path() == 'fside_tf32x3'
     simt = vfa_b200.aggregate(feats, table, ws, bs, flags=vfa_b200.FLAG_FORCE_SIMT)

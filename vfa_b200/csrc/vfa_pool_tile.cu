@@ -901,9 +901,10 @@ static bool tile_enabled() { return runtime_config().pool_tile != 0 && runtime_c
 static TileLayout tile_layout(const AggParams& p) {
   TileLayout L = {};
   L.VS = p.V * p.S;
-  // The chunk lists cost 0.3 ms to build (the quads' texel lists 0.15 ms) and save 0.1 ms of pooling per frame: they pay
-  // from two frames per call on (VFA_POOL_TILE=2 forces them for any batch).
-  if (!tile_enabled() || L.VS > 32 || (p.B < 2 && !p.y_bf16 && runtime_config().pool_tile < 2)) return L;
+  // The chunk lists (with the coverage bitmap) cost what the quads' texel lists + cover_mark_kernel cost (0.2 ms) and
+  // the pooling of a frame is a third faster from them: they serve every batch size, single frames included (MultiviewC
+  // 984 -> 1152 frames/s at batch 1).  VFA_POOL_TILE=0 selects the list kernel.
+  if (!tile_enabled() || L.VS > 32) return L;
   size_t max_bits = 0;
   for (int s = 0; s < p.S; ++s) max_bits = max_bits > (size_t)p.nl * p.sc[s].fh * p.sc[s].fw ? max_bits : (size_t)p.nl * p.sc[s].fh * p.sc[s].fw;
   L.max_words = (int)((max_bits + 31) / 32);
