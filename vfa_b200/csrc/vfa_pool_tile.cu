@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256, 4) tile_build_kernel(const BuildArgs a) {
     }
   }
   // pass 2: rank of every covered row = exclusive prefix of the popcounts (a thread scans a contiguous span of words)
-  const int span = (nwords + 255) / 256;
+  const int span = ((nwords + 255) / 256) | 1;        // odd: thread t starts at word t * span -- no shared-memory bank conflicts
   uint32_t local = 0;
   for (int w = tid * span; w < min(nwords, (tid + 1) * span); ++w) local += __popc(bits[w]);
   uint32_t U = 0;
