@@ -185,8 +185,12 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}-shaped aggregation forward', 'batch_per_gpu': 1, 'views': geom.n_views,
-                   'channels': geom.channels, 'grid': list(geom.grid_shape) + [geom.n_layers]},
+        # the same workload as the GPU arm's line (the reference processes the frames of a batch one after the other --
+        # vfanet.py:64-82 is batch 1 by construction -- so its frames/s do not depend on the batch size); `sample` says what
+        # one timed step covers
+        'config': {'workload': f'{args.workload}-shaped aggregation forward', 'batch_per_gpu': args.batch, 'views': geom.n_views,
+                   'channels': geom.channels, 'grid': list(geom.grid_shape) + [geom.n_layers],
+                   'feature_maps': [list(s_) for s_ in geom.feature_sizes()], 'sample': sample},
         'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample,
                          'host_cpus': os.cpu_count()},
         'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

@@ -25,7 +25,8 @@ def test_reference_arm_line():
     d = _run('--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-views', '1')
     assert BASE_KEYS <= set(d) and d['impl'] == 'reference'
     assert d['metric'] == 'aggregation_frames_per_s' and d['unit'] == 'frames/s' and d['higher_is_better'] is True
-    assert d['value'] > 0 and d['config']['workload'].startswith('MultiviewC')
+    assert d['value'] > 0 and d['config']['workload'] == 'MultiviewC-shaped aggregation forward'      # the GPU arm's workload
+    assert d['config']['batch_per_gpu'] == 4 and d['config']['views'] == 7 and d['config']['channels'] == 256
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
