@@ -541,7 +541,11 @@ def main():
     if path.startswith('fside') and plain:
         table = vfa_b200.build_table(cgeom, calibs, grid)
         per_kernel = {}
-        for kname, bits in (('ygemm_kernel', 64 | 256), (pool_name, 128 | 256), ('ygemm_kernel_all_tiles', 64)):
+        for kname, bits in ((pool_name, 128 | 256), ('ygemm_kernel', 64 | 256), ('ygemm_kernel_all_tiles', 64)):
+            # every loop starts from an idle GPU: back to back, the loop behind 20 launches of the tensor-bound GEMM ran up to
+            # 15 % slower on some boxes (clock / power state carried over), while the step itself never moved
+            torch.cuda.synchronize()
+            time.sleep(0.25)
             os.environ['VFA_UMMA_VARIANT'] = str(bits)
             if kname == 'ygemm_kernel_all_tiles':        # every (tile, layer) multiplied: the GEMM's own efficiency
                 os.environ['VFA_FSIDE_NO_SKIP'] = '1'
