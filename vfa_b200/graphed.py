@@ -4,7 +4,7 @@ A forward call is 12 kernel launches (projection table, tap records, coverage, r
 ...) issued from Python through ctypes; at batch 1 the GPU work of a MultiviewC-shaped frame (~0.9 ms) is no longer much
 larger than the host time of issuing it.  `GraphedAggregator` owns static input / output / workspace buffers, captures
 the whole sequence once (the library enqueues on the current stream, allocates nothing and never synchronises, so it is
-capturable as it stands) and replays it per frame batch: one `cudaGraphLaunch` instead of 12 launches + their Python.
+capturable as it stands) and replays it per frame batch: one `cudaGraphLaunch` instead of 10 launches + their Python.
 Moving cameras are supported -- the table is rebuilt INSIDE the graph from the static calibration buffer.  Inference
 only (frozen, pre-laid weights; no autograd).
 """
