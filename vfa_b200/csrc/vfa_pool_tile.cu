@@ -6,11 +6,13 @@
 // pipe (multi-line LDGs replay at ~2 cycles per line).  Here the 16 quads of a tile share the rows:
 //
 //   tile_build_kernel (once per table)  per (tile, view, scale): bitmap of the (layer, texel) rows any box of the tile
-//       covers -> rank of every row -> CHUNKS of TR consecutive ranks.  Per chunk a descriptor (row offsets, blob
-//       address) and a blob: per quad the entries (slot of the row inside the chunk, the four cell weights wy * wx),
-//       ordered by slot -- a deterministic order, whatever the thread schedule of the builder.
-//   pool_tile_kernel  persistent, one CTA per SM: a producer warp walks the chunk descriptors of its tiles and issues
-//       one 1 KB bulk copy per row (+ one for the blob) into a ring of shared-memory stages (mbarrier complete_tx);
+//       covers (ORed into the coverage bitmap of the row-compacted GEMM on the way) -> rank of every row -> CHUNKS of TR
+//       consecutive ranks.  Per chunk a descriptor (its rows as runs of consecutive rows, blob address) and a blob: per
+//       quad the entries (slot of the row inside the chunk, the four cell weights wy * wx), ordered by slot -- a
+//       deterministic order, whatever the thread schedule of the builder.
+//   tile_order_kernel  tiles by descending chunk count (8 levels), the order in which the scheduler deals them.
+//   pool_tile_kernel  persistent, one CTA per SM: four producer warps walk the chunk descriptors of the CTA's tiles and
+//       issue one bulk copy per run (+ one for the blob) into a ring of shared-memory stages (mbarrier complete_tx);
 //       16 consumer warps (one per quad, lane l = channels [4l, 4l+4) and [128+4l, ...)) wait for a stage, apply the
 //       rows their entries name with LDS.128 + packed FMAs, release the stage; after the last chunk of a (view, scale):
 //       + bias, ReLU, ReLU mask, sum into the tile's partial sums (64 KB of shared memory, swizzled); after the last
